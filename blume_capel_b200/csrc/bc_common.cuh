@@ -1,0 +1,71 @@
+// bc_common.cuh -- shared definitions for the sm_100a Blume-Capel engine.
+//
+// Bit-exact spec.  Reference rule being restated:
+// /root/reference/main.cpp:94 (proposal), :97-103 (neighbour sum), :105-106 (dE), :109 (accept).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bc {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
+constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
+constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
+
+constexpr uint32_t STREAM_COARSE = 0u;
+constexpr uint32_t STREAM_FINE = 1u;
+constexpr uint32_t STREAM_INIT = 2u;
+
+constexpr int TABLE_ENTRIES = 54;        // 18*c + 9*flip + S
+constexpr int TAB16_WORDS = 27;          // 54 x u16 -> 27 words: every entry in its own bank
+constexpr uint32_t ONES = 0x01010101u;   // code 1 == spin 0 in every byte
+
+// Philox4x32-10 with a runtime key.  The multiply pairs compile to IMAD.WIDE.U32.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * PHILOX_W0);
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)r * PHILOX_W1);
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ uint32_t ctr3_of(int64_t t, uint32_t stream, int colour) {
+    return ((uint32_t)((uint64_t)t >> 32) << 4) | (stream << 1) | (uint32_t)(colour & 1);
+}
+
+// Raw per-(measurement, replica) accumulators written by the sweep kernels (all exact integers):
+//   [0] sum c  over colour-0 sites   [1] sum c^2 over colour-0 sites
+//   [2] sum c  over colour-1 sites   [3] sum c^2 over colour-1 sites
+//   [4] sum c*S over colour-1 sites  [5] sum S  over colour-1 sites        (c = s+1, S = nb+4)
+// M = A0+A2-N, Q = (A1+A3) - 2(A0+A2) + N, B = A4 - 4*A2 - A5 + 4*N1  (N1 = #colour-1 sites).
+constexpr int OBS_RAW = 6;
+
+struct SweepParams {
+    uint8_t* own;            // colour array being updated   [replica][y][Wc]
+    const uint8_t* other;    // the other colour's array      [replica][y][Wc]
+    const uint16_t* tab16;   // [replica][54] coarse thresholds incl. flip in bit 15 (see engine)
+    const uint32_t* tab31;   // [replica][54] full thresholds (tie resolution)
+    unsigned long long* obs; // raw accumulators [slot][replica][OBS_RAW] or nullptr
+    unsigned long long* ties;// tie counter (diagnostics)
+    const int64_t* t_ptr;    // optional device-resident sweep counter (graph replay); t = *t_ptr + t
+    const int64_t* slot_ptr; // optional device-resident obs slot base
+    int64_t t;               // sweep index (or offset to *t_ptr)
+    int64_t slot;            // obs slot (or offset to *slot_ptr)
+    int L;                   // lattice size
+    int Wc;                  // compact row stride in bytes
+    int cpr;                 // 16-byte chunks per compact row (fast kernel)
+    int strips;              // row strips per replica (fast kernel), rows per strip = L / strips
+    int n_replicas;
+    uint32_t key0, key1;     // Philox key of replica 0; replica r uses (key0, key1 ^ r)
+};
+
+}  // namespace bc

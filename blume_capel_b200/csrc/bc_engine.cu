@@ -1,0 +1,539 @@
+// bc_engine.cu -- host side of libbc_engine.so: the C ABI of include/bc_engine.h on top of
+// the kernels in bc_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+//
+// Replaces the in-process hot path of the reference, `refill_random(); step(lattice);`
+// (/root/reference/main.cpp:343-347, 363-367), for the Metropolis part of step()
+// (main.cpp:159-161, metropolis() at main.cpp:89-112).
+#include "../../include/bc_engine.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bc_kernels.cuh"
+
+using namespace bc;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct bc_engine {
+    int L = 0, boundary = 0, n_rep = 0, device = 0;
+    uint64_t seed = 0;
+    int Wc = 0;
+    size_t colour_bytes = 0;  // bytes of one colour array (all replicas)
+    uint8_t* d_c[2] = {nullptr, nullptr};
+    uint16_t* d_tab16 = nullptr;
+    uint32_t* d_tab31 = nullptr;
+    std::vector<uint32_t> h_tab31;
+    std::vector<uint8_t> params_set;
+    unsigned long long* d_obs = nullptr;
+    size_t obs_slots_cap = 0;
+    unsigned long long* d_ties = nullptr;
+    int8_t* d_stage = nullptr;
+    size_t stage_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_timing = false;
+    int64_t t = 0;
+    int64_t launches = 0;
+    // pending (not yet fetched) measurements of the last bc_sweep
+    int64_t pending_meas = 0;
+    std::vector<int64_t> pending_sweeps;
+    // options
+    int opt_rows = 0;  // rows per thread, 0 = auto
+    int opt_force_generic = 0;
+    std::string err;
+};
+
+#define BC_CUDA(e, call)                                                                         \
+    do {                                                                                         \
+        cudaError_t _st = (call);                                                                \
+        if (_st != cudaSuccess) {                                                                \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_st);                      \
+            return BC_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+static int fail(bc_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// acceptance table: thr31[18c + 9f + S] for the reference rule main.cpp:94,105-106,109
+// ---------------------------------------------------------------------------------------------
+static void build_table(double T, double D, double J, uint32_t thr31[TABLE_ENTRIES], uint16_t tab16[TABLE_ENTRIES]) {
+    const double B = 1 / T;  // main.cpp:321
+    for (int c = 0; c < 3; ++c)
+        for (int f = 0; f < 2; ++f)
+            for (int S = 0; S < 9; ++S) {
+                const int cur = c - 1, nb = S - 4;
+                const int prop = (cur + 2 + f) % 3 - 1;                                          // main.cpp:94
+                const double de = -J * (prop - cur) * nb + D * (prop * prop - cur * cur);        // main.cpp:105-106
+                uint32_t thr;
+                if (de <= 0) {                                                                   // main.cpp:109
+                    thr = 0x80000000u;
+                } else {
+                    long long q = std::llround(std::exp(-B * de) * 2147483648.0);
+                    if (q < 0) q = 0;
+                    if (q > 2147483648LL) q = 2147483648LL;
+                    thr = (uint32_t)q;
+                }
+                const int i = 18 * c + 9 * f + S;
+                thr31[i] = thr;
+                // coarse 16-bit key compared against h16 = flip<<15 | u15: accept iff h16 < E, tie iff ==.
+                // E = flip<<15 + (thr31>>16), clamped to 65535 (the clamp only turns the single value
+                // h16 = 65535 of an always-accept entry into a tie, which the exact path then accepts).
+                uint32_t E = ((uint32_t)f << 15) + (thr >> 16);
+                if (E > 65535u) E = 65535u;
+                tab16[i] = (uint16_t)E;
+            }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" int bc_abi_version(void) { return BC_ABI_VERSION; }
+
+extern "C" const char* bc_last_error(const bc_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void bc_destroy(bc_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
+    cudaFree(e->d_tab16); cudaFree(e->d_tab31);
+    cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int launch_fill(bc_engine* e, uint8_t* p, size_t n, uint8_t v) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    fill_kernel<<<blocks, 256, 0, e->stream>>>(p, n, v);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device,
+                         uint64_t seed) {
+    if (!out) return fail(nullptr, BC_ERR_ARG, "bc_create: out is NULL");
+    *out = nullptr;
+    if (L < 2 || L > (1 << 20)) return fail(nullptr, BC_ERR_ARG, "bc_create: L out of range [2, 2^20]");
+    if (boundary != BC_PERIODIC && boundary != BC_OPEN) return fail(nullptr, BC_ERR_ARG, "bc_create: bad boundary");
+    if (boundary == BC_PERIODIC && (L & 1))
+        return fail(nullptr, BC_ERR_ARG, "bc_create: the periodic checkerboard needs even L");
+    if (n_replicas < 1) return fail(nullptr, BC_ERR_ARG, "bc_create: n_replicas < 1");
+    if (storage != BC_STORAGE_INT8) return fail(nullptr, BC_ERR_UNSUPPORTED, "bc_create: only BC_STORAGE_INT8");
+    int ndev = 0;
+    cudaError_t st = cudaGetDeviceCount(&ndev);
+    if (st != cudaSuccess || ndev == 0)
+        return fail(nullptr, BC_ERR_CUDA,
+                    std::string("bc_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(st));
+    if (device < 0 || device >= ndev) return fail(nullptr, BC_ERR_ARG, "bc_create: device index out of range");
+
+    bc_engine* e = new bc_engine();
+    e->L = L; e->boundary = boundary; e->n_rep = n_replicas; e->device = device; e->seed = seed;
+    e->Wc = (((L + 1) / 2) + 15) / 16 * 16;
+    e->colour_bytes = (size_t)n_replicas * (size_t)L * (size_t)e->Wc;
+    e->h_tab31.assign((size_t)n_replicas * TABLE_ENTRIES, 0u);
+    e->params_set.assign((size_t)n_replicas, 0);
+    auto bail = [&](const char* what, cudaError_t s) {
+        g_create_error = std::string("bc_create: ") + what + ": " + cudaGetErrorString(s);
+        bc_destroy(e);
+        return (int)BC_ERR_CUDA;
+    };
+    if ((st = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", st);
+    if ((st = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", st);
+    if ((st = cudaEventCreate(&e->ev0)) != cudaSuccess) return bail("event", st);
+    if ((st = cudaEventCreate(&e->ev1)) != cudaSuccess) return bail("event", st);
+    if ((st = cudaMalloc(&e->d_c[0], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
+    if ((st = cudaMalloc(&e->d_c[1], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
+    if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
+    if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
+    if ((st = cudaMalloc(&e->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc ties", st);
+    if ((st = cudaMemsetAsync(e->d_ties, 0, sizeof(unsigned long long), e->stream)) != cudaSuccess) return bail("memset", st);
+    // all spins 0 (code 1), including the pad bytes of each compact row
+    if (launch_fill(e, e->d_c[0], e->colour_bytes, 1) != BC_OK || launch_fill(e, e->d_c[1], e->colour_bytes, 1) != BC_OK) {
+        g_create_error = e->err;
+        bc_destroy(e);
+        return BC_ERR_CUDA;
+    }
+    if ((st = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", st);
+    *out = e;
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameters
+// ---------------------------------------------------------------------------------------------
+extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, double J) {
+    if (!e) return BC_ERR_ARG;
+    if (replica < -1 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_set_params: replica out of range");
+    if (!(T > 0) || !std::isfinite(T) || !std::isfinite(D) || !std::isfinite(J))
+        return fail(e, BC_ERR_ARG, "bc_set_params: need finite D, J and T > 0");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    uint32_t thr[TABLE_ENTRIES];
+    uint16_t t16[TABLE_ENTRIES];
+    build_table(T, D, J, thr, t16);
+    const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? e->n_rep : replica + 1;
+    std::vector<uint16_t> h16((size_t)(r1 - r0) * TABLE_ENTRIES);
+    for (int r = r0; r < r1; ++r) {
+        std::memcpy(&e->h_tab31[(size_t)r * TABLE_ENTRIES], thr, sizeof(thr));
+        std::memcpy(&h16[(size_t)(r - r0) * TABLE_ENTRIES], t16, sizeof(t16));
+        e->params_set[r] = 1;
+    }
+    // synchronous copies: the tables are tiny and the host vectors are temporaries
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    BC_CUDA(e, cudaMemcpy(e->d_tab31 + (size_t)r0 * TABLE_ENTRIES, &e->h_tab31[(size_t)r0 * TABLE_ENTRIES],
+                          (size_t)(r1 - r0) * TABLE_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    BC_CUDA(e, cudaMemcpy(e->d_tab16 + (size_t)r0 * TABLE_ENTRIES, h16.data(),
+                          h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return BC_OK;
+}
+
+extern "C" int bc_get_table(const bc_engine* e, int replica, uint32_t thr31[54]) {
+    if (!e || !thr31) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return BC_ERR_ARG;
+    if (!e->params_set[replica]) return BC_ERR_STATE;
+    std::memcpy(thr31, &e->h_tab31[(size_t)replica * TABLE_ENTRIES], TABLE_ENTRIES * sizeof(uint32_t));
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lattice state
+// ---------------------------------------------------------------------------------------------
+static int ensure_stage(bc_engine* e, size_t bytes) {
+    if (e->stage_cap >= bytes) return BC_OK;
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->d_stage) BC_CUDA(e, cudaFree(e->d_stage));
+    e->d_stage = nullptr; e->stage_cap = 0;
+    BC_CUDA(e, cudaMalloc(&e->d_stage, bytes));
+    e->stage_cap = bytes;
+    return BC_OK;
+}
+
+extern "C" int bc_init_random(bc_engine* e, int replica) {
+    if (!e) return BC_ERR_ARG;
+    if (replica < -1 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_init_random: replica out of range");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const int r0 = replica < 0 ? 0 : replica, n = replica < 0 ? e->n_rep : 1;
+    const long long total = (long long)n * e->L * e->L;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n, (uint32_t)e->seed,
+                                               (uint32_t)(e->seed >> 32));
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins) {
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * e->L * e->L;
+    int rc = ensure_stage(e, bytes);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
+    const long long total = (long long)n * e->L * e->Wc;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
+    return BC_OK;
+}
+
+static int download_range(bc_engine* e, int r0, int n, int8_t* spins) {
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * e->L * e->L;
+    int rc = ensure_stage(e, bytes);
+    if (rc != BC_OK) return rc;
+    const long long total = (long long)bytes;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return BC_OK;
+}
+
+extern "C" int bc_upload(bc_engine* e, int replica, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_upload: replica out of range");
+    return upload_range(e, replica, 1, spins);
+}
+extern "C" int bc_download(bc_engine* e, int replica, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_download: replica out of range");
+    return download_range(e, replica, 1, spins);
+}
+extern "C" int bc_upload_all(bc_engine* e, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return upload_range(e, 0, e->n_rep, spins);
+}
+extern "C" int bc_download_all(bc_engine* e, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return download_range(e, 0, e->n_rep, spins);
+}
+
+extern "C" int bc_get_sweep_counter(const bc_engine* e, int64_t* t) {
+    if (!e || !t) return BC_ERR_ARG;
+    *t = e->t;
+    return BC_OK;
+}
+extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
+    if (!e || t < 0) return BC_ERR_ARG;
+    e->t = t;
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------------------------
+typedef void (*fast_fn)(const SweepParams);
+
+template <int COL, bool DYN, bool MEAS, bool OPEN>
+static fast_fn fast_ptr() { return sweep_fast_kernel<COL, DYN, MEAS, OPEN>; }
+
+static fast_fn pick_fast(int col, bool dyn, bool meas, bool open) {
+    static const fast_fn tbl[2][2][2][2] = {
+        {{{fast_ptr<0, false, false, false>(), fast_ptr<0, false, false, true>()},
+          {fast_ptr<0, false, true, false>(), fast_ptr<0, false, true, true>()}},
+         {{fast_ptr<0, true, false, false>(), fast_ptr<0, true, false, true>()},
+          {fast_ptr<0, true, true, false>(), fast_ptr<0, true, true, true>()}}},
+        {{{fast_ptr<1, false, false, false>(), fast_ptr<1, false, false, true>()},
+          {fast_ptr<1, false, true, false>(), fast_ptr<1, false, true, true>()}},
+         {{fast_ptr<1, true, false, false>(), fast_ptr<1, true, false, true>()},
+          {fast_ptr<1, true, true, false>(), fast_ptr<1, true, true, true>()}}}};
+    return tbl[col][dyn ? 1 : 0][meas ? 1 : 0][open ? 1 : 0];
+}
+
+struct LaunchPlan {
+    bool fast = false;
+    bool dyn = false;
+    int cpr = 0, strips = 0, rows = 0;
+    unsigned grid = 0;
+};
+
+static bool rows_valid(int L, int cpr, int R) {
+    if (R < 1 || L % R) return false;
+    return (((long long)(L / R) * cpr) % 32) == 0;
+}
+
+static LaunchPlan make_plan(const bc_engine* e) {
+    LaunchPlan p;
+    const int L = e->L;
+    if (L % 32 == 0 && !e->opt_force_generic) {
+        p.fast = true;
+        p.cpr = L / 32;
+        int R = 0;
+        if (e->opt_rows > 0 && rows_valid(L, p.cpr, e->opt_rows)) {
+            R = e->opt_rows;
+        } else {
+            const long long want = 148LL * 1536;  // enough threads to fill the chip
+            const int cand[4] = {16, 8, 4, 2};
+            for (int i = 0; i < 4 && !R; ++i)
+                if (rows_valid(L, p.cpr, cand[i]) && (long long)e->n_rep * (L / cand[i]) * p.cpr >= want) R = cand[i];
+            if (!R) R = rows_valid(L, p.cpr, 2) ? 2 : 1;
+        }
+        p.rows = R;
+        p.dyn = (R & 1) != 0;
+        p.strips = L / R;
+        const long long items = (long long)e->n_rep * p.strips * p.cpr;
+        p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
+    } else {
+        const long long items = (long long)e->n_rep * L * ((L + 1) / 2);
+        p.grid = (unsigned)((items + 255) / 256);
+    }
+    return p;
+}
+
+static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot) {
+    SweepParams P;
+    P.own = e->d_c[col];
+    P.other = e->d_c[1 - col];
+    P.tab16 = e->d_tab16;
+    P.tab31 = e->d_tab31;
+    P.obs = e->d_obs;
+    P.ties = e->d_ties;
+    P.t_ptr = nullptr;
+    P.slot_ptr = nullptr;
+    P.t = t;
+    P.slot = slot;
+    P.L = e->L;
+    P.Wc = e->Wc;
+    P.cpr = plan.cpr;
+    P.strips = plan.strips;
+    P.n_replicas = e->n_rep;
+    P.key0 = (uint32_t)e->seed;
+    P.key1 = (uint32_t)(e->seed >> 32);
+    if (plan.fast) {
+        fast_fn fn = pick_fast(col, plan.dyn, measure, e->boundary == BC_OPEN);
+        fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
+    } else {
+        if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
+        else sweep_generic_kernel<false><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
+    }
+    ++e->launches;
+    return BC_OK;
+}
+
+static void raw_to_obs(const bc_engine* e, const unsigned long long* raw, int64_t sweep, bc_obs* o) {
+    const int64_t N = (int64_t)e->L * e->L;
+    const int64_t N1 = N / 2;  // colour-1 sites ((0,0) is colour 0)
+    const int64_t A0 = (int64_t)raw[0], A1 = (int64_t)raw[1], A2 = (int64_t)raw[2], A3 = (int64_t)raw[3];
+    const int64_t A4 = (int64_t)raw[4], A5 = (int64_t)raw[5];
+    o->sweep = sweep;
+    o->M = A0 + A2 - N;
+    o->Q = (A1 + A3) - 2 * (A0 + A2) + N;
+    o->B = A4 - 4 * A2 - A5 + 4 * N1;
+}
+
+static int fetch_pending(bc_engine* e, bc_obs* out) {
+    const int64_t n = e->pending_meas;
+    if (n == 0) return BC_OK;
+    std::vector<unsigned long long> raw((size_t)n * e->n_rep * OBS_RAW);
+    BC_CUDA(e, cudaMemcpyAsync(raw.data(), e->d_obs, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int64_t m = 0; m < n; ++m)
+        for (int r = 0; r < e->n_rep; ++r)
+            raw_to_obs(e, &raw[((size_t)m * e->n_rep + r) * OBS_RAW], e->pending_sweeps[m], &out[(size_t)m * e->n_rep + r]);
+    return BC_OK;
+}
+
+extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out) {
+    if (!e) return BC_ERR_ARG;
+    if (n_sweeps < 0 || measure_every < 0) return fail(e, BC_ERR_ARG, "bc_sweep: negative count");
+    for (int r = 0; r < e->n_rep; ++r)
+        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, "bc_sweep: bc_set_params not called for every replica");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const LaunchPlan plan = make_plan(e);
+
+    // measured sweeps: t with (t+1) % measure_every == 0
+    e->pending_meas = 0;
+    e->pending_sweeps.clear();
+    if (measure_every > 0)
+        for (int64_t t = e->t; t < e->t + n_sweeps; ++t)
+            if ((t + 1) % measure_every == 0) e->pending_sweeps.push_back(t);
+    const int64_t n_meas = (int64_t)e->pending_sweeps.size();
+    if (n_meas > 0) {
+        if ((size_t)n_meas > e->obs_slots_cap) {
+            BC_CUDA(e, cudaStreamSynchronize(e->stream));
+            if (e->d_obs) BC_CUDA(e, cudaFree(e->d_obs));
+            e->d_obs = nullptr; e->obs_slots_cap = 0;
+            BC_CUDA(e, cudaMalloc(&e->d_obs, (size_t)n_meas * e->n_rep * OBS_RAW * sizeof(unsigned long long)));
+            e->obs_slots_cap = (size_t)n_meas;
+        }
+        BC_CUDA(e, cudaMemsetAsync(e->d_obs, 0, (size_t)n_meas * e->n_rep * OBS_RAW * sizeof(unsigned long long), e->stream));
+    }
+
+    BC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    int64_t slot = 0;
+    for (int64_t s = 0; s < n_sweeps; ++s) {
+        const int64_t t = e->t + s;
+        const bool measure = measure_every > 0 && ((t + 1) % measure_every == 0);
+        launch_half(e, plan, 0, measure, t, slot);
+        launch_half(e, plan, 1, measure, t, slot);
+        if (measure) ++slot;
+    }
+    BC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
+    e->have_timing = true;
+    BC_CUDA(e, cudaGetLastError());
+    e->t += n_sweeps;
+    e->pending_meas = n_meas;
+    if (out && n_meas > 0) {
+        int rc = fetch_pending(e, out);
+        if (rc != BC_OK) return rc;
+        return n_meas * e->n_rep;
+    }
+    return 0;
+}
+
+extern "C" int64_t bc_read_obs(bc_engine* e, bc_obs* out, int64_t max_records) {
+    if (!e || !out) return BC_ERR_ARG;
+    const int64_t n = e->pending_meas * e->n_rep;
+    if (max_records < n) return fail(e, BC_ERR_ARG, "bc_read_obs: buffer too small");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    int rc = fetch_pending(e, out);
+    if (rc != BC_OK) return rc;
+    return n;
+}
+
+extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
+    if (!e || !out) return BC_ERR_ARG;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    unsigned long long* d_raw = nullptr;
+    const size_t bytes = (size_t)e->n_rep * OBS_RAW * sizeof(unsigned long long);
+    BC_CUDA(e, cudaMalloc(&d_raw, bytes));
+    cudaError_t st = cudaMemsetAsync(d_raw, 0, bytes, e->stream);
+    const long long total = (long long)e->n_rep * e->L * e->L;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (st == cudaSuccess) {
+        measure_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], e->L, e->Wc, e->n_rep, e->boundary == BC_OPEN, d_raw);
+        ++e->launches;
+        st = cudaGetLastError();
+    }
+    std::vector<unsigned long long> raw((size_t)e->n_rep * OBS_RAW);
+    if (st == cudaSuccess) st = cudaMemcpyAsync(raw.data(), d_raw, bytes, cudaMemcpyDeviceToHost, e->stream);
+    if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+    cudaFree(d_raw);
+    if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_measure: ") + cudaGetErrorString(st));
+    for (int r = 0; r < e->n_rep; ++r) raw_to_obs(e, &raw[(size_t)r * OBS_RAW], e->t - 1, &out[r]);
+    return BC_OK;
+}
+
+extern "C" int bc_sync(bc_engine* e) {
+    if (!e) return BC_ERR_ARG;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t bc_launch_count(const bc_engine* e) { return e ? e->launches : (int64_t)BC_ERR_ARG; }
+
+extern "C" int bc_last_sweep_ms(bc_engine* e, float* ms) {
+    if (!e || !ms) return BC_ERR_ARG;
+    if (!e->have_timing) return fail(e, BC_ERR_STATE, "bc_last_sweep_ms: no bc_sweep yet");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    BC_CUDA(e, cudaEventSynchronize(e->ev1));
+    BC_CUDA(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return BC_OK;
+}
+
+extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
+    if (!e || !name) return BC_ERR_ARG;
+    const std::string n(name);
+    if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }
+    return fail(e, BC_ERR_ARG, "bc_set_option: unknown option " + n);
+}
+
+extern "C" int bc_tie_count(bc_engine* e, int64_t* ties) {
+    if (!e || !ties) return BC_ERR_ARG;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    unsigned long long v = 0;
+    BC_CUDA(e, cudaMemcpyAsync(&v, e->d_ties, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    *ties = (int64_t)v;
+    return BC_OK;
+}
+
+extern "C" int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, int* grid, int* block) {
+    if (!e) return BC_ERR_ARG;
+    const LaunchPlan p = make_plan(e);
+    if (fast) *fast = p.fast;
+    if (rows_per_thread) *rows_per_thread = p.rows;
+    if (grid) *grid = (int)p.grid;
+    if (block) *block = p.fast ? FAST_THREADS : 256;
+    return BC_OK;
+}

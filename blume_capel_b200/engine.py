@@ -1,0 +1,206 @@
+"""ctypes binding of include/bc_engine.h.
+
+Mirrors the reference's run interface for the hot path: the object owns what main()
+owns in /root/reference/main.cpp (lattice main.cpp:335, parameters B, D, J main.cpp:24,
+321-323) and ``sweep`` replaces the loop body ``refill_random(); step(lattice);``
+(main.cpp:343-347, 363-367).  There is no CPU fallback: if the CUDA library is missing or
+no GPU is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+PERIODIC, OPEN = 0, 1
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class BCError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"bc_engine error {code}: {msg}")
+        self.code = code
+
+
+class Obs(C.Structure):
+    _fields_ = [("sweep", C.c_int64), ("M", C.c_int64), ("Q", C.c_int64), ("B", C.c_int64)]
+
+
+OBS_DTYPE = np.dtype([("sweep", "<i8"), ("M", "<i8"), ("Q", "<i8"), ("B", "<i8")])
+
+_lib = None
+
+# every symbol include/bc_engine.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "bc_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "bc_destroy": (None, [_P]),
+    "bc_last_error": (C.c_char_p, [_P]),
+    "bc_abi_version": (C.c_int, []),
+    "bc_set_params": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double]),
+    "bc_get_table": (C.c_int, [_P, C.c_int, _P]),
+    "bc_init_random": (C.c_int, [_P, C.c_int]),
+    "bc_upload": (C.c_int, [_P, C.c_int, _P]),
+    "bc_download": (C.c_int, [_P, C.c_int, _P]),
+    "bc_upload_all": (C.c_int, [_P, _P]),
+    "bc_download_all": (C.c_int, [_P, _P]),
+    "bc_get_sweep_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "bc_set_sweep_counter": (C.c_int, [_P, C.c_int64]),
+    "bc_sweep": (C.c_int64, [_P, C.c_int64, C.c_int64, _P]),
+    "bc_read_obs": (C.c_int64, [_P, _P, C.c_int64]),
+    "bc_measure": (C.c_int, [_P, _P]),
+    "bc_sync": (C.c_int, [_P]),
+    "bc_launch_count": (C.c_int64, [_P]),
+    "bc_last_sweep_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "bc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "bc_describe_plan": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bc_tie_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+}
+
+
+def library_path() -> str:
+    return os.environ.get("BC_ENGINE_LIB", os.path.join(_HERE, "libbc_engine.so"))
+
+
+def load_library():
+    """Load libbc_engine.so (in-tree build) and type every exported entry point."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise BCError(-2, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class Engine:
+    """n_replicas independent L x L spin-1 lattices on one GPU."""
+
+    def __init__(self, L: int, boundary: int = PERIODIC, n_replicas: int = 1, device: int = 0, seed: int = 0):
+        self._lib = load_library()
+        self._h = _P()
+        rc = self._lib.bc_create(C.byref(self._h), L, boundary, n_replicas, 0, device, seed & (2**64 - 1))
+        if rc != 0:
+            raise BCError(rc, (self._lib.bc_last_error(None) or b"").decode())
+        self.L, self.boundary, self.n_replicas, self.device, self.seed = L, boundary, n_replicas, device, seed
+
+    # -- helpers
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise BCError(rc, (self._lib.bc_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- parameters
+    def set_params(self, T: float, D: float, J: float = 1.0, replica: int = -1):
+        self._check(self._lib.bc_set_params(self._h, replica, T, D, J))
+
+    def table(self, replica: int = 0) -> np.ndarray:
+        t = np.zeros(54, np.uint32)
+        self._check(self._lib.bc_get_table(self._h, replica, t.ctypes.data))
+        return t
+
+    # -- state
+    def init_random(self, replica: int = -1):
+        self._check(self._lib.bc_init_random(self._h, replica))
+
+    def upload(self, spins: np.ndarray, replica: Optional[int] = None):
+        a = np.ascontiguousarray(spins, dtype=np.int8)
+        if replica is None:
+            assert a.size == self.n_replicas * self.L * self.L
+            self._check(self._lib.bc_upload_all(self._h, a.ctypes.data))
+        else:
+            assert a.size == self.L * self.L
+            self._check(self._lib.bc_upload(self._h, replica, a.ctypes.data))
+
+    def download(self, replica: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if replica is None:
+            a = out if out is not None else np.empty((self.n_replicas, self.L, self.L), np.int8)
+            self._check(self._lib.bc_download_all(self._h, a.ctypes.data))
+        else:
+            a = out if out is not None else np.empty((self.L, self.L), np.int8)
+            self._check(self._lib.bc_download(self._h, replica, a.ctypes.data))
+        return a
+
+    @property
+    def sweep_counter(self) -> int:
+        t = C.c_int64()
+        self._check(self._lib.bc_get_sweep_counter(self._h, C.byref(t)))
+        return t.value
+
+    @sweep_counter.setter
+    def sweep_counter(self, t: int):
+        self._check(self._lib.bc_set_sweep_counter(self._h, t))
+
+    # -- hot path
+    def sweep(self, n_sweeps: int, measure_every: int = 0, fetch: bool = True) -> Optional[np.ndarray]:
+        """Run n_sweeps; returns obs records shaped (n_meas, n_replicas) (structured) or None."""
+        if measure_every > 0 and fetch:
+            t0 = self.sweep_counter
+            n_meas = (t0 + n_sweeps) // measure_every - t0 // measure_every
+            buf = np.zeros((max(n_meas, 0), self.n_replicas), OBS_DTYPE)
+            n = self._check(self._lib.bc_sweep(self._h, n_sweeps, measure_every, buf.ctypes.data if n_meas else None))
+            assert n == n_meas * self.n_replicas, (n, n_meas)
+            return buf
+        self._check(self._lib.bc_sweep(self._h, n_sweeps, measure_every, None))
+        return None
+
+    def read_obs(self, n_meas: int) -> np.ndarray:
+        buf = np.zeros((n_meas, self.n_replicas), OBS_DTYPE)
+        n = self._check(self._lib.bc_read_obs(self._h, buf.ctypes.data, buf.size))
+        return buf.reshape(-1)[:n].reshape(-1, self.n_replicas)
+
+    def measure(self) -> np.ndarray:
+        buf = np.zeros(self.n_replicas, OBS_DTYPE)
+        self._check(self._lib.bc_measure(self._h, buf.ctypes.data))
+        return buf
+
+    def sync(self):
+        self._check(self._lib.bc_sync(self._h))
+
+    # -- introspection
+    @property
+    def launch_count(self) -> int:
+        return self._lib.bc_launch_count(self._h)
+
+    def last_sweep_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.bc_last_sweep_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.bc_set_option(self._h, name.encode(), value))
+
+    def plan(self) -> dict:
+        f, r, g, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.bc_describe_plan(self._h, C.byref(f), C.byref(r), C.byref(g), C.byref(b)))
+        return {"fast": bool(f.value), "rows_per_thread": r.value, "grid": g.value, "block": b.value}
+
+    @property
+    def tie_count(self) -> int:
+        t = C.c_int64()
+        self._check(self._lib.bc_tie_count(self._h, C.byref(t)))
+        return t.value

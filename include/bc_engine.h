@@ -1,0 +1,136 @@
+/*
+ * bc_engine.h -- C ABI of the B200 Blume-Capel checkerboard Metropolis engine
+ *                (libbc_engine.so, built from blume_capel_b200/csrc/).
+ *
+ * The reference (j2apps/blume_capel) has no plugin / FFI layer: its hot path is the
+ * in-process call   refill_random(); step(lattice);   made from main()'s two driver loops
+ * (/root/reference/main.cpp:342-348 burn-in, main.cpp:361-368 collection) with the
+ * parameters passed as globals (B, D, J at main.cpp:24) and the lattice owned by main()
+ * (main.cpp:335).  This header is the boundary a maintainer binds instead of those calls;
+ * each entry point names the reference code it replaces.  INTEGRATION.md shows the patch.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative bc_status on failure; the text of
+ *     the last failure on a handle is bc_last_error(handle) (bc_create failures:
+ *     bc_last_error(NULL)).  No C++ exception crosses this boundary.
+ *   - the caller owns every host buffer; the engine owns all device memory and one stream.
+ *   - a handle is bound to ONE GPU and is not thread-safe; distinct handles may be driven
+ *     from distinct host threads / processes (one process per GPU in multi-GPU runs).
+ *   - bc_sweep is asynchronous on the engine's stream unless it has to return observables;
+ *     bc_sync / bc_download / bc_read_obs wait for it.
+ *   - there is NO CPU fallback: without a CUDA device bc_create fails with BC_ERR_CUDA.
+ *   - spins on the host side are int8 in {-1,0,+1}, row-major idx = x + y*L, exactly the
+ *     reference layout (main.cpp:98-101, int instead of int8).
+ */
+#ifndef BC_ENGINE_H
+#define BC_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BC_ABI_VERSION 1
+
+typedef struct bc_engine bc_engine; /* opaque */
+
+enum bc_status {
+    BC_OK = 0,
+    BC_ERR_ARG = -1,     /* bad argument (odd L on a torus, replica out of range, ...) */
+    BC_ERR_CUDA = -2,    /* CUDA runtime error (text in bc_last_error) */
+    BC_ERR_NCCL = -3,    /* NCCL error */
+    BC_ERR_STATE = -4,   /* call not valid in this state (parameters not set, ...) */
+    BC_ERR_UNSUPPORTED = -5
+};
+
+enum bc_boundary { BC_PERIODIC = 0, BC_OPEN = 1 };
+enum bc_storage { BC_STORAGE_INT8 = 0 };
+
+/* Exact integer observables of one replica after one measured sweep.
+ * E = -J*B + D*Q (H of main.cpp:105-106), m = M/N, q = Q/N. */
+typedef struct {
+    int64_t sweep; /* global index of the sweep just completed */
+    int64_t M;     /* sum_i s_i                                  */
+    int64_t Q;     /* sum_i s_i^2                                */
+    int64_t B;     /* sum over bonds s_i s_j, each bond (+x,+y of every site) once */
+} bc_obs;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+
+/* Replaces: `int lattice[N]` + globals set up in main() (main.cpp:303-335).
+ * L: linear size (run time, not the -DL_MACRO compile-time constant of main.cpp:14-16,39);
+ * periodic needs even L.  n_replicas independent lattices of the same L are updated per
+ * launch (replica r uses Philox key (seed_lo, seed_hi ^ r)). */
+int bc_create(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device, uint64_t seed);
+void bc_destroy(bc_engine* e);
+const char* bc_last_error(const bc_engine* e);
+int bc_abi_version(void);
+
+/* ---- parameters -------------------------------------------------------------------- */
+
+/* Replaces: B = 1/atof(argv[5]); D = atof(argv[6]); J = atof(argv[7]) (main.cpp:321-323).
+ * Rebuilds the 54-entry integer acceptance table for `replica` (-1 = all replicas). */
+int bc_set_params(bc_engine* e, int replica, double T, double D, double J);
+
+/* The table the kernels use: thr31[54], index 18*(s+1) + 9*flip + (nb+4); accept iff
+ * u31 < thr31.  Lets a test compare it with the literal expression of main.cpp:105-109. */
+int bc_get_table(const bc_engine* e, int replica, uint32_t thr31[54]);
+
+/* ---- lattice state ----------------------------------------------------------------- */
+
+/* Replaces generate_lattice() (main.cpp:166-171): iid uniform {-1,0,1}, from the Philox
+ * init stream (reproducible, unlike the reference's random_device seeding).  replica -1 = all. */
+int bc_init_random(bc_engine* e, int replica);
+
+/* Replaces get_lattice_from_burn()'s result (main.cpp:281-299) / export_clusters()' input
+ * (main.cpp:232): whole-lattice transfer in the reference layout.  spins: L*L int8. */
+int bc_upload(bc_engine* e, int replica, const int8_t* spins);
+int bc_download(bc_engine* e, int replica, int8_t* spins);
+/* all replicas at once, spins: n_replicas * L*L int8, replica-major */
+int bc_upload_all(bc_engine* e, const int8_t* spins);
+int bc_download_all(bc_engine* e, int8_t* spins);
+
+/* Sweep counter = the full RNG state besides the seed (Philox is counter based), so
+ * (lattice, seed, counter) is an exact checkpoint. */
+int bc_get_sweep_counter(const bc_engine* e, int64_t* t);
+int bc_set_sweep_counter(bc_engine* e, int64_t t);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+
+/* Replaces the loop body `refill_random(); step(lattice);` (main.cpp:343-347, 363-367) for
+ * the Metropolis part of step() (main.cpp:159-161): n_sweeps checkerboard sweeps (one sweep
+ * = N attempts = colour 0 then colour 1) of every replica.  If measure_every > 0, after every
+ * sweep t with (t+1) % measure_every == 0 the observables of each replica are accumulated in
+ * the same pass; they are written to `out` (host, caller-owned, n_meas*n_replicas records,
+ * measurement-major then replica) if out != NULL, and the call then waits for completion.
+ * Returns the number of records written (>= 0) or a negative status. */
+int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out);
+
+/* Fetch the records of the last bc_sweep that was called with out == NULL (waits for it).
+ * Returns the number of records written or a negative status. */
+int64_t bc_read_obs(bc_engine* e, bc_obs* out, int64_t max_records);
+
+/* Observables of the current configuration (separate reduction kernel, no update). */
+int bc_measure(bc_engine* e, bc_obs* out /* n_replicas records */);
+
+int bc_sync(bc_engine* e);
+
+/* ---- introspection for benchmarks / tests ------------------------------------------ */
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t bc_launch_count(const bc_engine* e);
+/* Device time in ms of the last bc_sweep call, CUDA events on the engine's stream. */
+int bc_last_sweep_ms(bc_engine* e, float* ms);
+/* Select kernel variant for experiments: name/value pairs, e.g. ("rows_per_thread", 4),
+ * ("use_graph", 1), ("force_generic", 1).  Unknown names give BC_ERR_ARG. */
+int bc_set_option(bc_engine* e, const char* name, int64_t value);
+/* The launch geometry bc_sweep would use now (any pointer may be NULL). */
+int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, int* grid, int* block);
+/* Ties (coarse 15-bit draw == coarse threshold) resolved by the fine stream so far. */
+int bc_tie_count(bc_engine* e, int64_t* ties);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BC_ENGINE_H */

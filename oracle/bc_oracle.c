@@ -1,0 +1,289 @@
+/*
+ * bc_oracle.c -- CPU oracle (TEST INFRASTRUCTURE ONLY; see bc_oracle.h).
+ *
+ * Plain C restatement of the reference's per-site Metropolis rule
+ * (/root/reference/main.cpp:89-112) under the engine's checkerboard schedule and
+ * Philox4x32-10 stream.  Written for clarity, one site at a time, no SIMD: it is
+ * the thing the CUDA kernels must match bit for bit.
+ */
+#include "bc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------------------------------------------------------------- Philox4x32-10 */
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+void bc_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0;
+        uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static void site_key(uint64_t seed, uint32_t replica, uint32_t key[2]) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32) ^ replica;
+}
+
+static void site_ctr(uint32_t g, uint32_t y, int64_t t, uint32_t stream, int colour, uint32_t ctr[4]) {
+    ctr[0] = g;
+    ctr[1] = y;
+    ctr[2] = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
+    ctr[3] = ((uint32_t)((uint64_t)t >> 32) << 4) | (stream << 1) | (uint32_t)(colour & 1);
+}
+
+/* 16-bit draw for same-colour site number k of row y: Philox call per 8 sites (g = k>>3),
+ * halfword j = k&7 -> word j>>1, low half if j even, high half if j odd. */
+static uint32_t draw16(uint64_t seed, uint32_t replica, uint32_t k, uint32_t y, int64_t t, uint32_t stream,
+                       int colour) {
+    uint32_t key[2], ctr[4], w[4];
+    site_key(seed, replica, key);
+    site_ctr(k >> 3, y, t, stream, colour, ctr);
+    bc_oracle_philox4x32_10(ctr, key, w);
+    uint32_t j = k & 7u;
+    uint32_t word = w[j >> 1];
+    return (j & 1u) ? (word >> 16) : (word & 0xFFFFu);
+}
+
+/* ---------------------------------------------------------------- acceptance table */
+double bc_oracle_reference_de(int cur, int flip, int nb, double D, double J, int* proposal) {
+    /* main.cpp:94 */
+    const int prop = (cur + 2 + flip) % 3 - 1;
+    if (proposal) *proposal = prop;
+    /* main.cpp:105-106 */
+    const double de = -J * (prop - cur) * nb + D * (prop * prop - cur * cur);
+    return de;
+}
+
+void bc_oracle_build_table(double T, double D, double J, uint32_t thr31[54]) {
+    const double B = 1 / T; /* main.cpp:321 */
+    for (int c = 0; c < 3; ++c)
+        for (int f = 0; f < 2; ++f)
+            for (int S = 0; S < 9; ++S) {
+                const double de = bc_oracle_reference_de(c - 1, f, S - 4, D, J, NULL);
+                uint32_t thr;
+                if (de <= 0) { /* main.cpp:109 short-circuit: always accept */
+                    thr = 0x80000000u;
+                } else {
+                    double p = exp(-B * de) * 2147483648.0;
+                    long long q = llround(p);
+                    if (q < 0) q = 0;
+                    if (q > 2147483648LL) q = 2147483648LL;
+                    thr = (uint32_t)q;
+                }
+                thr31[18 * c + 9 * f + S] = thr;
+            }
+}
+
+/* ---------------------------------------------------------------- init / observables */
+void bc_oracle_init_random(int L, uint64_t seed, uint32_t replica, int8_t* spins) {
+    uint32_t key[2];
+    site_key(seed, replica, key);
+    const int64_t N = (int64_t)L * L;
+    for (int64_t i = 0; i < N; ++i) {
+        uint32_t ctr[4] = {(uint32_t)(i >> 2), (uint32_t)((uint64_t)i >> 34), 0u, BC_STREAM_INIT << 1};
+        uint32_t w[4];
+        bc_oracle_philox4x32_10(ctr, key, w);
+        uint32_t r = w[i & 3];
+        spins[i] = (int8_t)((int)(((uint64_t)r * 3u) >> 32) - 1);
+    }
+}
+
+void bc_oracle_observables(int L, int boundary, const int8_t* spins, int64_t* M, int64_t* Q, int64_t* B) {
+    int64_t m = 0, q = 0, b = 0;
+    for (int y = 0; y < L; ++y)
+        for (int x = 0; x < L; ++x) {
+            const int s = spins[x + (int64_t)y * L];
+            m += s;
+            q += s * s;
+            int r = 0, d = 0;
+            if (x + 1 < L) r = spins[(x + 1) + (int64_t)y * L];
+            else if (boundary == BC_ORACLE_PERIODIC) r = spins[0 + (int64_t)y * L];
+            if (y + 1 < L) d = spins[x + (int64_t)(y + 1) * L];
+            else if (boundary == BC_ORACLE_PERIODIC) d = spins[x];
+            b += s * (r + d);
+        }
+    if (M) *M = m;
+    if (Q) *Q = q;
+    if (B) *B = b;
+}
+
+/* ---------------------------------------------------------------- the sweep */
+static int64_t g_ties = 0;
+int64_t bc_oracle_tie_count(int reset) {
+    int64_t v = g_ties;
+    if (reset) g_ties = 0;
+    return v;
+}
+
+static int nb_code_sum(int L, int boundary, const int8_t* spins, int x, int y) {
+    /* main.cpp:97-103: sum over the 4 neighbours; here in code space c = s+1 so S = nb + 4.
+     * Open boundary: an off-lattice neighbour contributes spin 0 (code 1). */
+    int S = 0;
+    const int dxs[4] = {1, -1, 0, 0}, dys[4] = {0, 0, 1, -1};
+    for (int d = 0; d < 4; ++d) {
+        int nx = x + dxs[d], ny = y + dys[d];
+        if (boundary == BC_ORACLE_PERIODIC) {
+            nx = (nx + L) % L;
+            ny = (ny + L) % L;
+            S += spins[nx + (int64_t)ny * L] + 1;
+        } else {
+            if (nx < 0 || nx >= L || ny < 0 || ny >= L) S += 1;
+            else S += spins[nx + (int64_t)ny * L] + 1;
+        }
+    }
+    return S;
+}
+
+void bc_oracle_half_sweep_rows(int L, int boundary, int8_t* spins, const uint32_t thr31[54], uint64_t seed,
+                               uint32_t replica, int64_t t, int colour, int y0, int y1) {
+    uint32_t key[2];
+    site_key(seed, replica, key);
+    for (int y = y0; y < y1; ++y) {
+        const int p = (y + colour) & 1;
+        uint32_t k = 0;
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int x = p; x < L; x += 2, ++k) {
+            const int64_t idx = x + (int64_t)y * L;
+            const int c = spins[idx] + 1;
+            /* coarse 16-bit draw: one Philox call per 8 same-colour sites of the row (== draw16) */
+            const uint32_t j = k & 7u;
+            if (j == 0) {
+                uint32_t ctr[4];
+                site_ctr(k >> 3, (uint32_t)y, t, BC_STREAM_COARSE, colour, ctr);
+                bc_oracle_philox4x32_10(ctr, key, w);
+            }
+            const uint32_t h = (j & 1u) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu);
+            const int flip = (int)(h >> 15);
+            const uint32_t u15 = h & 0x7FFFu;
+            const int S = nb_code_sum(L, boundary, spins, x, y);
+            const uint32_t thr = thr31[18 * c + 9 * flip + S];
+            const uint32_t thr_c = thr >> 16;
+            int accept;
+            if (u15 < thr_c) accept = 1;
+            else if (u15 > thr_c) accept = 0;
+            else {
+                /* tie on the 15 coarse bits: resolve with 16 fine bits; u31 = u15<<16 | f16 < thr31 */
+                const uint32_t f16 = draw16(seed, replica, k, (uint32_t)y, t, BC_STREAM_FINE, colour);
+                accept = f16 < (thr & 0xFFFFu);
+                ++g_ties;
+            }
+            if (accept) spins[idx] = (int8_t)((c + 1 + flip) % 3 - 1); /* main.cpp:94 in code space */
+        }
+    }
+}
+
+int64_t bc_oracle_sweep(int L, int boundary, int8_t* spins, const uint32_t thr31[54], uint64_t seed,
+                        uint32_t replica, int64_t t0, int64_t n_sweeps, int64_t measure_every,
+                        bc_oracle_obs* obs) {
+    if (L < 1 || n_sweeps < 0) return -1;
+    if (boundary == BC_ORACLE_PERIODIC && (L & 1)) return -2; /* checkerboard needs even L on a torus */
+    int64_t n_obs = 0;
+    for (int64_t t = t0; t < t0 + n_sweeps; ++t) {
+        bc_oracle_half_sweep_rows(L, boundary, spins, thr31, seed, replica, t, 0, 0, L);
+        bc_oracle_half_sweep_rows(L, boundary, spins, thr31, seed, replica, t, 1, 0, L);
+        if (obs && measure_every > 0 && ((t + 1) % measure_every) == 0) {
+            obs[n_obs].sweep = t;
+            bc_oracle_observables(L, boundary, spins, &obs[n_obs].M, &obs[n_obs].Q, &obs[n_obs].B);
+            ++n_obs;
+        }
+    }
+    return n_obs;
+}
+
+/* ---------------------------------------------------------------- exact enumeration */
+int bc_oracle_enumerate(int L, double T, double D, double J, double out[5]) {
+    if (L < 1 || L > 4) return -1;
+    const int N = L * L;
+    int8_t s[16];
+    memset(s, 0, sizeof(s));
+    for (int i = 0; i < N; ++i) s[i] = -1;
+    double Z = 0, sE = 0, sAm = 0, sQ = 0, sM2 = 0, sM4 = 0;
+    const double beta = 1.0 / T;
+    /* energies are shifted by a running minimum Emin; accumulators are rescaled when it drops */
+    double Emin = 1e300;
+    for (;;) {
+        int64_t M, Q, B;
+        bc_oracle_observables(L, BC_ORACLE_PERIODIC, s, &M, &Q, &B);
+        const double E = -J * (double)B + D * (double)Q;
+        if (E < Emin) {
+            const double f = (Emin > 1e299) ? 0.0 : exp(-beta * (Emin - E));
+            Z *= f; sE *= f; sAm *= f; sQ *= f; sM2 *= f; sM4 *= f;
+            Emin = E;
+        }
+        const double w = exp(-beta * (E - Emin));
+        const double m = (double)M / N;
+        Z += w;
+        sE += w * E;
+        sAm += w * fabs(m);
+        sQ += w * (double)Q / N;
+        sM2 += w * m * m;
+        sM4 += w * m * m * m * m;
+        /* next state (base-3 counter over {-1,0,1}) */
+        int i = 0;
+        while (i < N) {
+            if (s[i] < 1) { ++s[i]; break; }
+            s[i] = -1;
+            ++i;
+        }
+        if (i == N) break;
+    }
+    out[0] = sE / Z / N;
+    out[1] = sAm / Z;
+    out[2] = sQ / Z;
+    out[3] = 1.0 - (sM4 / Z) / (3.0 * (sM2 / Z) * (sM2 / Z));
+    out[4] = N * (sM2 / Z - (sAm / Z) * (sAm / Z));
+    return 0;
+}
+
+/* ---------------------------------------------------------------- literal reference attempt loop */
+static inline uint64_t splitmix64(uint64_t* x) {
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int64_t bc_oracle_reference_metropolis(int L, int32_t* lattice, double T, double D, double J,
+                                       int64_t n_attempts, uint64_t seed) {
+    /* main.cpp:89-112, one attempt per iteration: random site, 2-way proposal, periodic
+     * neighbour sum through a modL table, double-precision dE, exp() only on uphill moves. */
+    const int N = L * L;
+    const double B = 1 / T;
+    int* modL = (int*)malloc(sizeof(int) * (size_t)(2 * L));
+    for (int i = 0; i < 2 * L; ++i) modL[i] = i % L;
+    const int dx[4] = {1, L - 1, 0, 0}, dy[4] = {0, 0, 1, L - 1};
+    uint64_t st = seed;
+    int64_t accepted = 0;
+    for (int64_t a = 0; a < n_attempts; ++a) {
+        const uint64_t r = splitmix64(&st);
+        const int posn = (int)(((r & 0xFFFFFFFFull) * (uint64_t)N) >> 32);
+        const int flip = (int)((r >> 32) & 1);
+        const int current = lattice[posn];
+        const int proposal = (current + 2 + flip) % 3 - 1;
+        int neighbors = 0;
+        const int x = modL[posn % L + 0] , y = posn / L;
+        for (int d = 0; d < 4; ++d) neighbors += lattice[modL[x + dx[d]] + modL[y + dy[d]] * L];
+        const double de = -J * (proposal - current) * neighbors + D * (proposal * proposal - current * current);
+        if (de <= 0 || (double)(splitmix64(&st) >> 11) * (1.0 / 9007199254740992.0) < exp(-B * de)) {
+            lattice[posn] = proposal;
+            ++accepted;
+        }
+    }
+    free(modL);
+    return accepted;
+}

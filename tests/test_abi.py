@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/bc_engine.h declares (no GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bc_engine.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bc_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(bc):
+    lib = bc.load_library()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libbc_engine.so does not export {n}"
+    from blume_capel_b200 import engine
+    assert sorted(engine.SYMBOLS) == names, "python binding and header disagree"
+
+
+def test_abi_version(bc):
+    assert bc.load_library().bc_abi_version() == 1
+
+
+def test_no_torch_types_or_cpp_in_header():
+    src = open(os.path.join(ROOT, "include", "bc_engine.h")).read()
+    assert "torch" not in src and "std::" not in src and "at::" not in src
+    assert 'extern "C"' in src
+
+
+def test_argument_errors_need_no_gpu(bc):
+    lib = bc.load_library()
+    h = C.c_void_p()
+    assert lib.bc_create(C.byref(h), 33, 0, 1, 0, 0, 0) == -1  # odd torus -> BC_ERR_ARG
+    assert b"even" in lib.bc_last_error(None)
+    assert lib.bc_create(C.byref(h), 32, 5, 1, 0, 0, 0) == -1
+    assert lib.bc_create(C.byref(h), 32, 0, 0, 0, 0, 0) == -1
+    assert lib.bc_create(C.byref(h), 32, 0, 1, 9, 0, 0) == -5  # unsupported storage
+    assert lib.bc_create(None, 32, 0, 1, 0, 0, 0) == -1
+
+
+def test_fails_loudly_without_a_gpu(bc):
+    """No CPU fallback: on a box without CUDA, bc_create must fail with BC_ERR_CUDA."""
+    lib = bc.load_library()
+    h = C.c_void_p()
+    rc = lib.bc_create(C.byref(h), 32, 0, 1, 0, 0, 0)
+    if rc == 0:
+        lib.bc_destroy(h)
+        pytest.skip("a CUDA device is present")
+    assert rc == -2
+    assert b"no CPU fallback" in lib.bc_last_error(None)
+    with pytest.raises(bc.BCError):
+        bc.Engine(32)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The shipped package and library must not import, link or mention oracle/."""
+    pkg = os.path.join(ROOT, "blume_capel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "bc_oracle" not in text and "oracle." not in text and "from oracle" not in text, f

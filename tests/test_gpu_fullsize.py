@@ -1,0 +1,104 @@
+"""Full-size checks at BASELINE.json sizes through size-independent properties."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TC = (0.608, 1.966, 1.0)
+
+
+def np_observables(s, periodic=True):
+    s = s.astype(np.int64)
+    M = int(s.sum()); Q = int((s * s).sum())
+    if periodic:
+        B = int((s * np.roll(s, -1, 1)).sum() + (s * np.roll(s, -1, 0)).sum())
+    else:
+        B = int((s[:, :-1] * s[:, 1:]).sum() + (s[:-1, :] * s[1:, :]).sum())
+    return M, Q, B
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_L4096_fast_equals_generic_and_fused_obs(bc, boundary):
+    """Two independently written kernels (tiled SWAR vs one-thread-per-site) agree at L=4096,
+    and the fused observables equal a numpy recomputation from the downloaded lattice."""
+    L, n = 4096, 6
+    res = []
+    for generic in (0, 1):
+        e = bc.Engine(L, boundary, 1, 0, 0x5EED0002)
+        e.set_option("force_generic", generic)
+        e.set_params(*TC)
+        e.init_random()
+        obs = e.sweep(n, 3)
+        res.append((e.download(0), obs, e.measure()))
+        e.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in ("M", "Q", "B"):
+        assert np.array_equal(res[0][1][f], res[1][1][f])
+    M, Q, B = np_observables(res[0][0], boundary == 0)
+    last = res[0][1][-1, 0]
+    assert (last["M"], last["Q"], last["B"]) == (M, Q, B)
+    sm = res[0][2][0]
+    assert (sm["M"], sm["Q"], sm["B"]) == (M, Q, B)
+
+
+def test_rows_per_thread_invariance_L4096(bc):
+    L, n = 4096, 4
+    out = []
+    for rows in (2, 4, 8, 16):
+        e = bc.Engine(L, 0, 1, 0, 11)
+        e.set_option("rows_per_thread", rows)
+        e.set_params(*TC)
+        e.init_random()
+        e.sweep(n)
+        assert e.plan()["rows_per_thread"] == rows
+        out.append(e.download(0))
+        e.close()
+    for o in out[1:]:
+        assert np.array_equal(o, out[0])
+
+
+def test_replica_batch_equals_single_runs(bc):
+    """Replica r of a batch uses key (seed_lo, seed_hi ^ r): equal to a 1-replica engine with that seed."""
+    L, n, seed = 1024, 5, 0x1234_0000_0042
+    e = bc.Engine(L, 0, 4, 0, seed)
+    e.set_params(*TC)
+    e.init_random()
+    obs = e.sweep(n, 1)
+    batch = e.download()
+    e.close()
+    for r in (0, 3):
+        s = bc.Engine(L, 0, 1, 0, seed ^ (r << 32))
+        s.set_params(*TC)
+        s.init_random()
+        o1 = s.sweep(n, 1)
+        assert np.array_equal(s.download(0), batch[r])
+        assert np.array_equal(o1[:, 0]["B"], obs[:, r]["B"])
+        s.close()
+
+
+def test_upload_download_roundtrip_large(bc):
+    rng = np.random.default_rng(0)
+    s = rng.integers(-1, 2, size=(2, 2048, 2048), dtype=np.int8)
+    e = bc.Engine(2048, 0, 2, 0, 0)
+    e.upload(s)
+    assert np.array_equal(e.download(), s)
+    e.upload(s[1], 0)
+    assert np.array_equal(e.download(0), s[1])
+    e.close()
+
+
+def test_J0_limit_statistics(bc):
+    """J = 0: sites independent, <q> = 2e^{-D/T}/(1+2e^{-D/T}), <m> = 0."""
+    L, T, D = 1024, 1.0, 0.7
+    e = bc.Engine(L, 0, 1, 0, 2024)
+    e.set_params(T, D, 0.0)
+    e.init_random()
+    e.sweep(30)
+    obs = e.sweep(20, 1)
+    e.close()
+    N = L * L
+    q = obs[:, 0]["Q"].mean() / N
+    q_exact = 2 * np.exp(-D / T) / (1 + 2 * np.exp(-D / T))
+    # 20 nearly independent samples of N sites: sigma ~ sqrt(q(1-q)/(20 N)) ~ 1e-4
+    assert abs(q - q_exact) < 6e-4, (q, q_exact)
+    assert abs(obs[:, 0]["M"].mean() / N) < 2e-3
+    assert np.all(obs[:, 0]["B"] * 0 == 0)

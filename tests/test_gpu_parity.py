@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit.
+
+Sizes are chosen so the oracle finishes in seconds; full-size (BASELINE.json) checks use
+size-independent properties in test_gpu_fullsize.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TC = (0.608, 1.966, 1.0)  # tricritical point of main.cpp:34-36
+
+
+def run_pair(bc, oracle, L, boundary, n_rep, n_sweeps, seed, params=TC, opts=(), measure_every=1, start="random"):
+    eng = bc.Engine(L, boundary, n_rep, 0, seed)
+    for k, v in opts:
+        eng.set_option(k, v)
+    eng.set_params(*params)
+    tab = oracle.build_table(*params)
+    ref = np.zeros((n_rep, L, L), np.int8)
+    if start == "random":
+        eng.init_random()
+        for r in range(n_rep):
+            ref[r] = oracle.init_random(L, seed, r)
+    else:
+        rng = np.random.default_rng(seed)
+        ref[:] = rng.integers(-1, 2, size=ref.shape, dtype=np.int8)
+        eng.upload(ref)
+    got0 = eng.download()
+    assert np.array_equal(got0, ref), "initial lattice differs"
+    obs = eng.sweep(n_sweeps, measure_every)
+    got = eng.download()
+    ref_obs = []
+    for r in range(n_rep):
+        ref_obs.append(oracle.sweep(ref[r], tab, seed, r, 0, n_sweeps, measure_every, boundary))
+    plan = eng.plan()
+    eng.close()
+    return got, ref, obs, ref_obs, plan
+
+
+@pytest.mark.parametrize("L", [2, 4, 6, 8, 12, 16, 24, 48])
+def test_generic_kernel_periodic(bc, oracle, L):
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, 3, 20, 0xBC00 + L)
+    assert not plan["fast"]
+    assert np.array_equal(got, ref)
+    for r in range(3):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
+
+
+@pytest.mark.parametrize("L", [3, 5, 8, 17, 33])
+def test_generic_kernel_open(bc, oracle, L):
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.OPEN, 2, 15, 0x0BE0 + L)
+    assert np.array_equal(got, ref)
+    for r in range(2):
+        for f in ("M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
+
+
+@pytest.mark.parametrize("L,rows", [(32, 1), (32, 0), (64, 0), (64, 2), (64, 4), (96, 0), (96, 3), (128, 0),
+                                    (128, 8), (128, 16), (256, 16)])
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_fast_kernel(bc, oracle, L, rows, boundary):
+    n_rep = 3 if L <= 128 else 1
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, 12, 0xFA57 + L + rows,
+                                            opts=(("rows_per_thread", rows),))
+    assert plan["fast"]
+    if rows:
+        assert plan["rows_per_thread"] == rows
+    assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
+
+
+@pytest.mark.parametrize("params", [(0.608, 1.966, 1.0), (2.2691853, -1000.0, 1.0), (1.0, 0.5, 0.0), (0.3, 1.0, 1.0),
+                                    (5.0, -2.0, -1.0)])
+def test_parameter_points(bc, oracle, params):
+    """Ising limit D=-1000 (main.cpp:27-29), J=0, low T, antiferromagnetic J."""
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, 64, bc.PERIODIC, 2, 10, 77, params=params, start="upload")
+    assert np.array_equal(got, ref)
+    assert np.array_equal(obs[:, 1]["B"], ref_obs[1]["B"])
+
+
+def test_measure_every_and_counter(bc, oracle):
+    got, ref, obs, ref_obs, _ = run_pair(bc, oracle, 64, 0, 2, 23, 5, measure_every=5)
+    assert obs.shape == (4, 2)
+    assert list(obs[:, 0]["sweep"]) == [4, 9, 14, 19]
+    assert np.array_equal(obs[:, 0]["M"], ref_obs[0]["M"])
+    assert np.array_equal(got, ref)
+
+
+def test_table_equals_oracle(bc, oracle):
+    eng = bc.Engine(32, 0, 2, 0, 1)
+    for p in [(0.608, 1.966, 1.0), (2.2691853, -1000.0, 1.0), (0.1, 3.0, 1.0), (10.0, 0.0, 0.0)]:
+        eng.set_params(*p)
+        assert np.array_equal(eng.table(1), oracle.build_table(*p))
+    eng.set_params(1.0, 1.0, 1.0, replica=1)
+    assert np.array_equal(eng.table(1), oracle.build_table(1.0, 1.0, 1.0))
+    assert np.array_equal(eng.table(0), oracle.build_table(10.0, 0.0, 0.0))
+    eng.close()
+
+
+def test_per_replica_parameters(bc, oracle):
+    """Replicas of one launch may sit at different (T, D) (finite-size-scaling grids)."""
+    L, n_rep, seed = 64, 4, 99
+    eng = bc.Engine(L, 0, n_rep, 0, seed)
+    pts = [(0.58 + 0.02 * r, 1.94 + 0.01 * r, 1.0) for r in range(n_rep)]
+    for r, p in enumerate(pts):
+        eng.set_params(*p, replica=r)
+    eng.init_random()
+    obs = eng.sweep(8, 1)
+    got = eng.download()
+    for r, p in enumerate(pts):
+        ref = oracle.init_random(L, seed, r)
+        ro = oracle.sweep(ref, oracle.build_table(*p), seed, r, 0, 8, 1)
+        assert np.array_equal(got[r], ref), r
+        assert np.array_equal(obs[:, r]["B"], ro["B"])
+    eng.close()
+
+
+def test_standalone_measure(bc, oracle):
+    rng = np.random.default_rng(3)
+    for L, b in [(10, 0), (64, 0), (7, 1), (64, 1)]:
+        s = rng.integers(-1, 2, size=(2, L, L), dtype=np.int8)
+        eng = bc.Engine(L, b, 2, 0, 0)
+        eng.upload(s)
+        m = eng.measure()
+        for r in range(2):
+            assert (m[r]["M"], m[r]["Q"], m[r]["B"]) == oracle.observables(s[r], b)
+        eng.close()
+
+
+def test_checkpoint_resume(bc):
+    """(lattice, seed, sweep counter) is a complete checkpoint."""
+    a = bc.Engine(128, 0, 1, 0, 4242)
+    a.set_params(*TC)
+    a.init_random()
+    a.sweep(10)
+    full = a.download(0)
+    b = bc.Engine(128, 0, 1, 0, 4242)
+    b.set_params(*TC)
+    b.init_random()
+    b.sweep(4)
+    half = b.download(0)
+    t = b.sweep_counter
+    b.close()
+    c = bc.Engine(128, 0, 1, 0, 4242)
+    c.set_params(*TC)
+    c.upload(half, 0)
+    c.sweep_counter = t
+    c.sweep(6)
+    assert np.array_equal(c.download(0), full)
+    a.close(); c.close()
+
+
+def test_ties_are_resolved_like_the_oracle(bc, oracle):
+    """Enough attempts that coarse ties (2^-15 per uphill attempt) occur; lattice must still match."""
+    L, n = 128, 40
+    oracle.tie_count(reset=True)
+    got, ref, obs, ref_obs, _ = run_pair(bc, oracle, L, 0, 1, n, 31337, measure_every=0)
+    assert np.array_equal(got, ref)
+    assert oracle.tie_count() > 0  # the case was exercised
+
+
+def test_errors(bc):
+    with pytest.raises(bc.BCError):
+        bc.Engine(33, bc.PERIODIC)  # odd torus
+    with pytest.raises(bc.BCError):
+        bc.Engine(32, 7)
+    e = bc.Engine(32)
+    with pytest.raises(bc.BCError):
+        e.sweep(1)  # parameters not set
+    with pytest.raises(bc.BCError):
+        e.set_params(-1.0, 0.0)
+    with pytest.raises(bc.BCError):
+        e.set_option("nope", 1)
+    e.close()
+
+
+def test_committed_golden_trajectories(bc):
+    """GPU against tests/golden/trajectories.npz (written by the oracle, make_golden.py)."""
+    import json, os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "trajectories.npz"))
+    meta = json.loads(str(d["meta"]))
+    for i, m in enumerate(meta):
+        # replica r of a batch == single engine with seed ^ (r << 32)
+        e = bc.Engine(m["L"], m["boundary"], m["replica"] + 1, 0, m["seed"])
+        e.set_params(m["T"], m["D"], m["J"])
+        e.init_random()
+        assert np.array_equal(e.download(m["replica"]), d[f"init_{i}"]), i
+        obs = e.sweep(m["n_sweeps"], 1)[:, m["replica"]]
+        assert np.array_equal(e.download(m["replica"]), d[f"final_{i}"]), i
+        assert np.array_equal(np.stack([obs["M"], obs["Q"], obs["B"]]), d[f"obs_{i}"]), i
+        e.close()

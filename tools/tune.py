@@ -1,0 +1,42 @@
+"""Quick device-side timing of bc_sweep variants (development aid, not the bench)."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import blume_capel_b200 as bc
+
+TC = (0.608, 1.966, 1.0)
+
+def run(L, n_rep, rows, sweeps, measure_every=0, boundary=0, opts=()):
+    e = bc.Engine(L, boundary, n_rep, 0, 1)
+    e.set_option("rows_per_thread", rows)
+    for k, v in opts:
+        e.set_option(k, v)
+    e.set_params(*TC)
+    e.init_random()
+    e.sweep(5, 0)
+    e.sync()
+    best = 1e30
+    for rep in range(3):
+        e.sweep(sweeps, measure_every, fetch=False)
+        e.sync()
+        best = min(best, e.last_sweep_ms())
+    plan = e.plan()
+    e.close()
+    ups = L * L * n_rep * sweeps / (best * 1e6)
+    return ups, best, plan
+
+if __name__ == "__main__":
+    cases = []
+    for n_rep, sweeps in ((1, 200), (64, 10)):
+        for rows in (0, 2, 4, 8, 16):
+            cases.append((4096, n_rep, rows, sweeps, 0))
+    cases.append((4096, 64, 0, 10, 1))
+    cases.append((4096, 1, 0, 200, 1))
+    cases.append((1024, 64, 0, 50, 0))
+    cases.append((256, 512, 0, 50, 0))
+    cases.append((64, 4096, 0, 50, 0))
+    cases.append((32, 8192, 0, 50, 0))
+    for c in cases:
+        ups, ms, plan = run(*c)
+        print(json.dumps({"L": c[0], "n_rep": c[1], "rows": c[2], "sweeps": c[3], "measure_every": c[4],
+                          "updates_per_ns": round(ups, 1), "ms": round(ms, 3), "plan": plan}), flush=True)
