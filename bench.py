@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- spin-updates/ns of the B200 Blume-Capel checkerboard Metropolis engine.
+
+Contract (one JSON line on stdout from rank 0):
+    python bench.py --gpus N --steps K --warmup W            # our CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code
+
+Workload (BASELINE.json configs[1]): 2D square L=4096 periodic, single (T, D) = (0.608, 1.966)
+near the tricritical point, int8 spins.  To keep the working set larger than the 126 MB L2
+(timing rule) the launch is batched over 64 independent replicas of that lattice at that
+(T, D) (1 GiB of spins): one "step" = SWEEPS_PER_STEP checkerboard sweeps of the whole
+batch with the fused observables measured every MEASURE_EVERY sweeps.
+  value : whole-job spin-updates/ns with the lattices resident in HBM (CUDA events on the
+          engine's stream, max over ranks).
+  e2e   : the same step through the C ABI from HOST buffers: bc_upload_all (pinned host ->
+          device) + bc_sweep + observables device -> host + bc_download_all, all inside the
+          timed region.
+Multi-GPU (N > 1): one process per GPU under torchrun, the replicas are sharded (64 per GPU,
+weak scaling), no data-path collective; torch.distributed only for barrier + max-over-ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L = 4096
+N_REPLICAS = 64
+T, D, J = 0.608, 1.966, 1.0
+SWEEPS_PER_STEP = 100
+MEASURE_EVERY = 10
+SEED = 0x5EED0002
+ALGO_BYTES_PER_UPDATE = 3.0  # int8: per sweep every spin is read twice and written once
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the reference's own implementation
+# ---------------------------------------------------------------------------------------------
+def reference_sample(n_procs, L_ref=32, nsteps=1):
+    """Runs n_procs independent instances of the UNMODIFIED reference binary (oracle/_ref/tri-L,
+    built from /root/reference/main.cpp; OpenMP threads do not speed a single run up)
+    and returns (Metropolis attempts, wall seconds).  Falls back to the oracle's literal port of
+    main.cpp:89-112 when the binary is not present."""
+    from oracle import ref_runner
+    if ref_runner.available(L_ref):
+        from concurrent.futures import ThreadPoolExecutor
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=n_procs) as ex:
+            list(ex.map(lambda r: ref_runner.run_reference(L_ref, T, D, J, nsteps, run=r), range(n_procs)))
+        wall = time.perf_counter() - t0
+        return n_procs * ref_runner.metropolis_attempts(L_ref, nsteps), wall, "reference", \
+            (f"{n_procs} x oracle/_ref/tri-{L_ref} (unmodified main.cpp, burner.sh:11 flags) burn=0 nsteps={nsteps}: "
+             f"{9 * L_ref * L_ref} step() calls each = Metropolis attempts + Wolff clusters + mt19937 refills; "
+             "rate counts Metropolis attempts only")
+    import numpy as np
+    from oracle import oracle
+    lat = np.ones((64, 64), np.int32)
+    n = 100_000_000
+    t0 = time.perf_counter()
+    oracle.reference_metropolis(lat, T, D, J, n, 1)
+    wall = time.perf_counter() - t0
+    return n, wall, "port", "oracle literal port of main.cpp:89-112, L=64, 1e8 attempts, 1 thread"
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        reference_sample(cores)
+    attempts, wall = 0, 0.0
+    kind = sample = None
+    for _ in range(args.steps):
+        a, w, kind, sample = reference_sample(cores)
+        attempts += a
+        wall += w
+    value = attempts / wall / 1e9
+    line = {
+        "impl": "reference", "metric": "spin-updates/ns", "value": value, "unit": "spin-updates/ns",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "spin-updates/ns", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "spin-updates/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference cannot be built for L >= 512 (main.cpp:57-59); its per-attempt rate is size independent",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": f"L={L} periodic int8, (T,D,J)=({T},{D},{J}), {N_REPLICAS} replicas/GPU batched "
+                        f"(1 GiB/GPU > 126 MB L2, no L2 flush needed), {SWEEPS_PER_STEP} sweeps/step, "
+                        f"fused observables every {MEASURE_EVERY} sweeps",
+            "L": L, "replicas_per_gpu": N_REPLICAS, "sweeps_per_step": SWEEPS_PER_STEP,
+            "measure_every": MEASURE_EVERY, "boundary": "periodic", "storage": "int8",
+            "parallelism": f"replicas x{n_gpus}", "l2": "working set > L2"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    import blume_capel_b200 as bc
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = bc.Engine(L, bc.PERIODIC, N_REPLICAS, local_rank, SEED + (rank << 40))
+    eng.set_params(T, D, J)
+    eng.init_random()
+    n_meas = SWEEPS_PER_STEP // MEASURE_EVERY
+    updates_per_step = float(L) * L * N_REPLICAS * SWEEPS_PER_STEP
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
+    eng.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
+    ms = eng.timer_stop()
+    launches = eng.launch_count - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    last_obs = eng.read_obs(n_meas)
+
+    # ---- end to end through the C ABI from pinned host buffers
+    host = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True)
+    host_np = host.numpy()
+    eng.download(out=host_np)
+    obs_buf = None
+    for _ in range(min(args.warmup, 2)):
+        eng.upload(host_np)
+        obs_buf = eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY)
+        eng.download(out=host_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.upload(host_np)                                 # h2d: the step's input lattices
+        obs_buf = eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY)  # d2h: the step's observables
+        eng.download(out=host_np)                           # d2h: the sample for the dump
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    ms_t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = ms_t.tolist()
+
+    if rank == 0:
+        total_updates = updates_per_step * args.steps * world
+        value = total_updates / (ms_max * 1e6)
+        e2e_value = total_updates / (e2e_ms_max * 1e6)
+        peak, peak_src = measured_peak()
+        # dominant kernel = sweep_fast_kernel (one launch per half-sweep): algorithmic bytes per launch
+        # = 1.5 B x sites of the batch; duration = timed region / launches (back-to-back on one stream)
+        sweep_launches = 2 * SWEEPS_PER_STEP * args.steps
+        bytes_per_launch = 1.5 * L * L * N_REPLICAS
+        avg_launch_ms = ms / max(launches, 1)
+        achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        # bounded CPU sample of the reference on this box's host cores
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            a, w, kind, sample = reference_sample(1, 32, 2)
+            cpu = {"value": a / w / 1e9, "unit": "spin-updates/ns", "cores": 1, "kind": kind, "sample": sample}
+        N = L * L
+        line = {
+            "metric": "spin-updates/ns", "value": value, "unit": "spin-updates/ns", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": "spin-updates/ns",
+                    "h2d_bytes_per_step": int(host_np.nbytes),
+                    "d2h_bytes_per_step": int(host_np.nbytes + obs_buf.nbytes)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "bc::sweep_fast_kernel",
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": avg_launch_ms, "sweep_launches": sweep_launches},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
+                      "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": eng.tie_count},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

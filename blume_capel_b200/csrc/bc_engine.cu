@@ -36,7 +36,7 @@ struct bc_engine {
     int8_t* d_stage = nullptr;
     size_t stage_cap = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool have_timing = false;
     int64_t t = 0;
     int64_t launches = 0;
@@ -46,6 +46,7 @@ struct bc_engine {
     // options
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_force_generic = 0;
+    int opt_variant = 1;  // per-site compare formulation of the fast kernel
     std::string err;
 };
 
@@ -110,6 +111,8 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->tm0) cudaEventDestroy(e->tm0);
+    if (e->tm1) cudaEventDestroy(e->tm1);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -126,7 +129,7 @@ extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, i
                          uint64_t seed) {
     if (!out) return fail(nullptr, BC_ERR_ARG, "bc_create: out is NULL");
     *out = nullptr;
-    if (L < 2 || L > (1 << 20)) return fail(nullptr, BC_ERR_ARG, "bc_create: L out of range [2, 2^20]");
+    if (L < 2 || L > 65536) return fail(nullptr, BC_ERR_ARG, "bc_create: L out of range [2, 65536]");
     if (boundary != BC_PERIODIC && boundary != BC_OPEN) return fail(nullptr, BC_ERR_ARG, "bc_create: bad boundary");
     if (boundary == BC_PERIODIC && (L & 1))
         return fail(nullptr, BC_ERR_ARG, "bc_create: the periodic checkerboard needs even L");
@@ -154,6 +157,8 @@ extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", st);
     if ((st = cudaEventCreate(&e->ev0)) != cudaSuccess) return bail("event", st);
     if ((st = cudaEventCreate(&e->ev1)) != cudaSuccess) return bail("event", st);
+    if ((st = cudaEventCreate(&e->tm0)) != cudaSuccess) return bail("event", st);
+    if ((st = cudaEventCreate(&e->tm1)) != cudaSuccess) return bail("event", st);
     if ((st = cudaMalloc(&e->d_c[0], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
     if ((st = cudaMalloc(&e->d_c[1], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
@@ -299,25 +304,25 @@ extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*fast_fn)(const SweepParams);
 
-template <int COL, bool DYN, bool MEAS, bool OPEN>
-static fast_fn fast_ptr() { return sweep_fast_kernel<COL, DYN, MEAS, OPEN>; }
+template <int COL, bool SMALL, bool MEAS, int VAR>
+static fast_fn fast_ptr() { return sweep_fast_kernel<COL, SMALL, MEAS, VAR>; }
 
-static fast_fn pick_fast(int col, bool dyn, bool meas, bool open) {
+static fast_fn pick_fast(int col, bool small, bool meas, int var) {
     static const fast_fn tbl[2][2][2][2] = {
-        {{{fast_ptr<0, false, false, false>(), fast_ptr<0, false, false, true>()},
-          {fast_ptr<0, false, true, false>(), fast_ptr<0, false, true, true>()}},
-         {{fast_ptr<0, true, false, false>(), fast_ptr<0, true, false, true>()},
-          {fast_ptr<0, true, true, false>(), fast_ptr<0, true, true, true>()}}},
-        {{{fast_ptr<1, false, false, false>(), fast_ptr<1, false, false, true>()},
-          {fast_ptr<1, false, true, false>(), fast_ptr<1, false, true, true>()}},
-         {{fast_ptr<1, true, false, false>(), fast_ptr<1, true, false, true>()},
-          {fast_ptr<1, true, true, false>(), fast_ptr<1, true, true, true>()}}}};
-    return tbl[col][dyn ? 1 : 0][meas ? 1 : 0][open ? 1 : 0];
+        {{{fast_ptr<0, false, false, 0>(), fast_ptr<0, false, false, 1>()},
+          {fast_ptr<0, false, true, 0>(), fast_ptr<0, false, true, 1>()}},
+         {{fast_ptr<0, true, false, 0>(), fast_ptr<0, true, false, 1>()},
+          {fast_ptr<0, true, true, 0>(), fast_ptr<0, true, true, 1>()}}},
+        {{{fast_ptr<1, false, false, 0>(), fast_ptr<1, false, false, 1>()},
+          {fast_ptr<1, false, true, 0>(), fast_ptr<1, false, true, 1>()}},
+         {{fast_ptr<1, true, false, 0>(), fast_ptr<1, true, false, 1>()},
+          {fast_ptr<1, true, true, 0>(), fast_ptr<1, true, true, 1>()}}}};
+    return tbl[col][small ? 1 : 0][meas ? 1 : 0][var ? 1 : 0];
 }
 
 struct LaunchPlan {
     bool fast = false;
-    bool dyn = false;
+    bool small = false;
     int cpr = 0, strips = 0, rows = 0;
     unsigned grid = 0;
 };
@@ -344,8 +349,8 @@ static LaunchPlan make_plan(const bc_engine* e) {
             if (!R) R = rows_valid(L, p.cpr, 2) ? 2 : 1;
         }
         p.rows = R;
-        p.dyn = (R & 1) != 0;
         p.strips = L / R;
+        p.small = (R & 1) != 0 || (((long long)p.strips * p.cpr) % FAST_THREADS) != 0;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
     } else {
@@ -372,10 +377,11 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.cpr = plan.cpr;
     P.strips = plan.strips;
     P.n_replicas = e->n_rep;
+    P.open = e->boundary == BC_OPEN;
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
-        fast_fn fn = pick_fast(col, plan.dyn, measure, e->boundary == BC_OPEN);
+        fast_fn fn = pick_fast(col, plan.small, measure, e->opt_variant);
         fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
@@ -510,10 +516,27 @@ extern "C" int bc_last_sweep_ms(bc_engine* e, float* ms) {
     return BC_OK;
 }
 
+extern "C" int bc_timer_start(bc_engine* e) {
+    if (!e) return BC_ERR_ARG;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    BC_CUDA(e, cudaEventRecord(e->tm0, e->stream));
+    return BC_OK;
+}
+
+extern "C" int bc_timer_stop(bc_engine* e, float* ms) {
+    if (!e || !ms) return BC_ERR_ARG;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    BC_CUDA(e, cudaEventRecord(e->tm1, e->stream));
+    BC_CUDA(e, cudaEventSynchronize(e->tm1));
+    BC_CUDA(e, cudaEventElapsedTime(ms, e->tm0, e->tm1));
+    return BC_OK;
+}
+
 extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "variant") { e->opt_variant = value != 0; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }
     return fail(e, BC_ERR_ARG, "bc_set_option: unknown option " + n);
 }

@@ -18,6 +18,14 @@ __device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return __ldg(reinterp
 __device__ __forceinline__ uint32_t ldg4(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 
+// PRMT with the full 4-bit selector nibbles: bit 3 of a nibble replicates the SIGN of the selected
+// byte over the output byte (0x00 / 0xFF).  __byte_perm() masks that bit off, hence the PTX.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // Exact rule for a site whose coarse compare tied: u31 = (u15 << 16 | f16) < thr31.
 __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_t thr31) {
     return (((h16 & 0x7FFFu) << 16) | f16) < thr31;
@@ -29,82 +37,105 @@ __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_
 // Work item id = blockIdx.x*128 + threadIdx.x -> (replica, strip, j), j fastest, so a warp
 // reads 512 contiguous bytes per row; items/replica is a multiple of 32 (host guarantees),
 // so a warp never spans replicas.
-//   DYNPAR = false: rows per strip is even; the row parity is static per unrolled row.
-//   DYNPAR = true : any strip height (used with 1 row per thread for small lattices).
+//   SMALL = false: rows per strip is even (row parity static per unrolled row) and
+//                  items/replica is a multiple of 128 (one replica, one table per CTA).
+//   SMALL = true : any strip height, up to 4 replicas per CTA (small lattices).
+//   VAR          : formulation of the per-site compare:
+//                  0 = ISETP/SEL per site; 1 = IMAD difference + PRMT sign masks + SWAR tie test.
+// The instruction budget, not HBM, limits this kernel: the ALU pipe
+// (LOP3/PRMT/SHF/ISETP) is the scarce one, so VAR 1 moves work to the FMA pipe (IMAD).
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
+#ifndef BC_FAST_MIN_BLOCKS
+#define BC_FAST_MIN_BLOCKS 8
+#endif
 
-template <int COL, bool DYNPAR, bool MEASURE, bool OPEN>
-__global__ void __launch_bounds__(FAST_THREADS)
+template <int COL, bool SMALL, bool MEASURE, int VAR>
+__global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
-    __shared__ __align__(16) uint32_t s_tab[FAST_MAX_REPL_PER_CTA * TAB16_WORDS];
+    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
 
-    const int ipr = P.strips * P.cpr;  // items per replica
-    const long long gid0 = (long long)blockIdx.x * FAST_THREADS;
-    const int rep0 = (int)(gid0 / ipr);
-    for (int i = threadIdx.x; i < FAST_MAX_REPL_PER_CTA * TAB16_WORDS; i += FAST_THREADS) {
-        const int r = rep0 + i / TAB16_WORDS;
-        s_tab[i] = (r < P.n_replicas)
+    const uint32_t ipr = (uint32_t)(P.strips * P.cpr);  // items per replica
+    const unsigned long long gid0 = (unsigned long long)blockIdx.x * FAST_THREADS;
+    const uint32_t rep0 = (uint32_t)(gid0 / ipr);
+    for (int i = threadIdx.x; i < (SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS; i += FAST_THREADS) {
+        const uint32_t r = rep0 + i / TAB16_WORDS;
+        s_tab[i] = (r < (uint32_t)P.n_replicas)
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
     }
     __syncthreads();
 
-    const long long gid = gid0 + threadIdx.x;
-    const int rep = (int)(gid / ipr);
-    if (rep >= P.n_replicas) return;  // whole warps only (ipr % 32 == 0)
-    const int rem = (int)(gid - (long long)rep * ipr);
-    const int strip = rem / P.cpr;
-    const int j = rem - strip * P.cpr;
-    const int L = P.L;
-    const int rows = L / P.strips;
-    const int y0 = strip * rows;
-    const int Wc = P.Wc;
+    uint32_t rep, rem;
+    if (SMALL) {
+        const unsigned long long gid = gid0 + threadIdx.x;
+        rep = (uint32_t)(gid / ipr);
+        if (rep >= (uint32_t)P.n_replicas) return;  // whole warps only (ipr % 32 == 0)
+        rem = (uint32_t)(gid - (unsigned long long)rep * ipr);
+    } else {
+        rep = rep0;  // ipr % 128 == 0: the CTA lies inside one replica
+        rem = (uint32_t)(gid0 - (unsigned long long)rep0 * ipr) + threadIdx.x;
+    }
+    const uint32_t strip = rem / (uint32_t)P.cpr;
+    const uint32_t j = rem - strip * (uint32_t)P.cpr;
+    const uint32_t L = (uint32_t)P.L;
+    const uint32_t rows = L / (uint32_t)P.strips;
+    const uint32_t y0 = strip * rows;
+    const uint32_t Wc = (uint32_t)P.Wc;
+    const bool open = P.open != 0;
 
     int64_t t = P.t;
     if (P.t_ptr) t += *P.t_ptr;
-    const uint32_t k0 = P.key0, k1 = P.key1 ^ (uint32_t)rep;
+    const uint32_t k0 = P.key0, k1 = P.key1 ^ rep;
     const uint32_t ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
     const uint32_t ctr3 = ctr3_of(t, STREAM_COARSE, COL);
 
-    const char* tab = reinterpret_cast<const char*>(s_tab) + (rep - rep0) * (TAB16_WORDS * 4);
+    // shared-memory table of this thread's replica: uniform for !SMALL
+    const char* tab = reinterpret_cast<const char*>(s_tab) + (SMALL ? (rep - rep0) * (TAB16_WORDS * 4) : 0u);
     const size_t rep_base = (size_t)rep * (size_t)L * (size_t)Wc;
-    uint8_t* own_base = P.own + rep_base + (size_t)j * 16;
-    const uint8_t* oth_base = P.other + rep_base + (size_t)j * 16;
-    const uint8_t* oth_rep = P.other + rep_base;
-    const int jr = (j + 1 == P.cpr) ? 0 : j + 1;   // chunk holding k+1 of our last site
-    const int jl = (j == 0) ? P.cpr - 1 : j - 1;   // chunk holding k-1 of our first site
-    const int off_r = jr * 16, off_l = jl * 16 + 12;
-    const bool edge_r = OPEN && (j + 1 == P.cpr), edge_l = OPEN && (j == 0);
+    uint8_t* own_col = P.own + rep_base + (size_t)j * 16;            // + y*Wc
+    const uint8_t* oth_col = P.other + rep_base + (size_t)j * 16;    // + y*Wc
+    const uint32_t jr = (j + 1 == (uint32_t)P.cpr) ? 0u : j + 1;     // chunk holding k+1 of our last site
+    const uint32_t jl = (j == 0) ? (uint32_t)P.cpr - 1 : j - 1;      // chunk holding k-1 of our first site
+    const uint8_t* side_r = P.other + rep_base + (size_t)jr * 16;       // first word of the right chunk
+    const uint8_t* side_l = P.other + rep_base + (size_t)jl * 16 + 12;  // last word of the left chunk
+    const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
 
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
-    auto load_other = [&](int y) -> uint4 {
-        if (y < 0) { if (OPEN) return ones4; y += L; }
-        if (y >= L) { if (OPEN) return ones4; y -= L; }
-        return ldg16(oth_base + (size_t)y * Wc);
-    };
+    const uint32_t total = L * Wc;  // bytes of one replica's colour array (< 2^32: L <= 65536)
 
     uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
 
-    uint4 upv = load_other(y0 - 1);
-    uint4 midv = load_other(y0);
-    // one row of the strip; PARC::value is the row parity (y+COL)&1, or -1 for "compute it"
-    auto do_row = [&](const int y, auto parc) {
+    // rows y0-1 and y0 of the other colour (periodic wrap or open boundary = all-zero-spin row)
+    uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
+    uint4 upv, midv;
+    if (y0 == 0) upv = open ? ones4 : ldg16(oth_col + (total - Wc));
+    else upv = ldg16(oth_col + (off - Wc));
+    midv = ldg16(oth_col + off);
+
+    // one row of the strip; PARV is the row parity (y+COL)&1, or -1 for "compute it"
+    auto do_row = [&](const uint32_t y, auto parc) {
         constexpr int PARV = decltype(parc)::value;
-        const int par = (PARV < 0) ? ((y + COL) & 1) : PARV;
-        const uint4 dnv = load_other(y + 1);
-        const uint32_t side = par ? (edge_r ? 0x00000001u : ldg4(oth_rep + (size_t)y * Wc + off_r))
-                                  : (edge_l ? 0x01000000u : ldg4(oth_rep + (size_t)y * Wc + off_l));
-        uint8_t* own_ptr = own_base + (size_t)y * Wc;
+        const int par = (PARV < 0) ? (int)((y + COL) & 1u) : PARV;
+        uint32_t off_dn = off + Wc;
+        uint4 dnv;
+        if (off_dn == total) {
+            dnv = open ? ones4 : ldg16(oth_col);
+        } else {
+            dnv = ldg16(oth_col + off_dn);
+        }
+        const uint32_t side = par ? (edge_r ? 0x00000001u : ldg4(side_r + off))
+                                  : (edge_l ? 0x01000000u : ldg4(side_l + off));
+        uint8_t* own_ptr = own_col + off;
         const uint4 ownv = *reinterpret_cast<const uint4*>(own_ptr);
 
         // coarse randoms: one Philox call per 8 sites; 16 bits per site
         uint32_t q[8];
         {
             uint32_t qa[4], qb[4];
-            philox4x32_10(2u * (uint32_t)j, (uint32_t)y, ctr2, ctr3, k0, k1, qa);
-            philox4x32_10(2u * (uint32_t)j + 1u, (uint32_t)y, ctr2, ctr3, k0, k1, qb);
+            philox4x32_10(2u * j, y, ctr2, ctr3, k0, k1, qa);
+            philox4x32_10(2u * j + 1u, y, ctr2, ctr3, k0, k1, qb);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { q[i] = qa[i]; q[4 + i] = qb[i]; }
         }
@@ -113,8 +144,10 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
         const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
         const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-        uint32_t idx[4], xr[4], msk[4], S[4];
+        uint32_t idx[4], nw[4], S[4];
+        uint32_t xr[4], msk[4];  // proposal xor, accept byte masks (0xFF per accepted site)
         bool tie = false;
+        uint32_t tieacc = 0;
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) {
             // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
@@ -123,43 +156,74 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
             const uint32_t sh = par ? sr : sl;
             const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
             const uint32_t ra = q[2 * wi], rb = q[2 * wi + 1];
-            // flip bits = bit 15 of each halfword -> one per byte
-            const uint32_t f4 = (__byte_perm(ra, rb, 0x7531) >> 7) & ONES;
             const uint32_t c4 = o[wi];
-            // byte offsets into the u16 table: 2*(18c + 9f + S) <= 106
-            const uint32_t idx4 = c4 * 36u + f4 * 18u + S4 * 2u;
-            // proposal (main.cpp:94 in code space): p = (c + 1 + f) mod 3
-            const uint32_t t4 = c4 + f4 + ONES;                    // 1..4
-            const uint32_t ge = ((t4 + 0x05050505u) >> 3) & ONES;  // t >= 3
-            const uint32_t p4 = t4 - 3u * ge;
-            // per-site compare with the coarse threshold (flip sits in bit 15 of both sides)
-            const uint32_t a0 = idx4 & 0xFFu;
-            const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
-            const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
-            const uint32_t a3 = idx4 >> 24;
-            const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tab + a0);
-            const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tab + a1);
-            const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tab + a2);
-            const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tab + a3);
-            const uint32_t h0 = ra & 0xFFFFu, h1 = ra >> 16, h2 = rb & 0xFFFFu, h3 = rb >> 16;
-            uint32_t m4 = 0;
-            m4 += (h0 < E0) ? 0x00000001u : 0u;
-            m4 += (h1 < E1) ? 0x00000100u : 0u;
-            m4 += (h2 < E2) ? 0x00010000u : 0u;
-            m4 += (h3 < E3) ? 0x01000000u : 0u;
-            tie = tie || (h0 == E0) || (h1 == E1) || (h2 == E2) || (h3 == E3);
-            idx[wi] = idx4;
-            xr[wi] = c4 ^ p4;
-            msk[wi] = m4;
+            if (VAR == 0) {
+                // flip bits = bit 15 of each halfword -> one per byte
+                const uint32_t f4 = (__byte_perm(ra, rb, 0x7531) >> 7) & ONES;
+                // byte offsets into the u16 table: 2*(18c + 9f + S) <= 106
+                const uint32_t idx4 = c4 * 36u + f4 * 18u + S4 * 2u;
+                // proposal (main.cpp:94 in code space): p = (c + 1 + f) mod 3
+                const uint32_t t4 = c4 + f4 + ONES;                    // 1..4
+                const uint32_t ge = ((t4 + 0x05050505u) >> 3) & ONES;  // t >= 3
+                const uint32_t p4 = t4 - 3u * ge;
+                const uint32_t a0 = idx4 & 0xFFu;
+                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
+                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
+                const uint32_t a3 = idx4 >> 24;
+                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tab + a0);
+                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tab + a1);
+                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tab + a2);
+                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tab + a3);
+                const uint32_t h0 = ra & 0xFFFFu, h1 = ra >> 16, h2 = rb & 0xFFFFu, h3 = rb >> 16;
+                uint32_t m4 = 0;
+                m4 += (h0 < E0) ? 0x00000001u : 0u;
+                m4 += (h1 < E1) ? 0x00000100u : 0u;
+                m4 += (h2 < E2) ? 0x00010000u : 0u;
+                m4 += (h3 < E3) ? 0x01000000u : 0u;
+                tie = tie || (h0 == E0) || (h1 == E1) || (h2 == E2) || (h3 == E3);
+                idx[wi] = idx4;
+                xr[wi] = c4 ^ p4;
+                msk[wi] = m4 * 0xFFu;
+            } else {
+                // flips as byte masks (PRMT sign replication of bytes 1,3 of ra and rb), then 0/1 bytes
+                const uint32_t fFF = prmt(ra, rb, 0xFDB9u);
+                const uint32_t f4 = fFF & ONES;
+                const uint32_t idx4 = c4 * 36u + (f4 * 18u + (S4 + S4));
+                // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
+                const uint32_t q1 = c4 * 2u + (f4 + ONES);                 // 2c + f + 1 in 1..6
+                const uint32_t ge = ((q1 + 0x04040404u) >> 3) & ONES;      // 2c + f >= 3
+                xr[wi] = q1 - 3u * ge;
+                const uint32_t a0 = idx4 & 0xFFu;
+                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
+                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
+                const uint32_t a3 = idx4 >> 24;
+                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tab + a0);
+                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tab + a1);
+                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tab + a2);
+                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tab + a3);
+                // d = (h - E) * 65536 + (noise < 65536): sign(d) <=> h < E, top half zero <=> h == E.
+                // h - E lies in [-32768, 32767], so the 32-bit difference cannot wrap.
+                const uint32_t d0 = (ra << 16) - E0 * 65536u;
+                const uint32_t d1 = ra - E1 * 65536u;
+                const uint32_t d2 = (rb << 16) - E2 * 65536u;
+                const uint32_t d3 = rb - E3 * 65536u;
+                const uint32_t H01 = __byte_perm(d0, d1, 0x7632);  // [d0.hi16, d1.hi16]
+                const uint32_t H23 = __byte_perm(d2, d3, 0x7632);
+                msk[wi] = prmt(H01, H23, 0xFDB9u);            // 0xFF where d < 0
+                tieacc |= (H01 - 0x00010001u) & ~H01;               // has-zero-halfword test (bit 15 / 31)
+                tieacc |= (H23 - 0x00010001u) & ~H23;
+                idx[wi] = idx4;
+            }
             S[wi] = S4;
         }
+        if (VAR != 0) tie = (tieacc & 0x80008000u) != 0u;
 
         if (tie) {
             // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
             uint32_t fa[4], fb[4];
             const uint32_t ctr3f = ctr3_of(t, STREAM_FINE, COL);
-            philox4x32_10(2u * (uint32_t)j, (uint32_t)y, ctr2, ctr3f, k0, k1, fa);
-            philox4x32_10(2u * (uint32_t)j + 1u, (uint32_t)y, ctr2, ctr3f, k0, k1, fb);
+            philox4x32_10(2u * j, y, ctr2, ctr3f, k0, k1, fa);
+            philox4x32_10(2u * j + 1u, y, ctr2, ctr3f, k0, k1, fb);
             const uint32_t* t31 = P.tab31 + (size_t)rep * TABLE_ENTRIES;
 #pragma unroll
             for (int s = 0; s < 16; ++s) {
@@ -171,15 +235,14 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 if (h == E) {
                     const uint32_t fw = (s < 8) ? fa[(s & 7) >> 1] : fb[(s & 7) >> 1];
                     const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
-                    if (exact_accept(h, f16, __ldg(t31 + (a >> 1)))) msk[wi] |= (1u << (8 * b));
+                    if (exact_accept(h, f16, __ldg(t31 + (a >> 1)))) msk[wi] |= (0xFFu << (8 * b));
                     ++n_ties;
                 }
             }
         }
 
-        uint32_t nw[4];
 #pragma unroll
-        for (int wi = 0; wi < 4; ++wi) nw[wi] = o[wi] ^ (xr[wi] & (msk[wi] * 0xFFu));
+        for (int wi = 0; wi < 4; ++wi) nw[wi] = o[wi] ^ (xr[wi] & msk[wi]);
         *reinterpret_cast<uint4*>(own_ptr) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
 
         if (MEASURE) {
@@ -195,12 +258,13 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         }
         upv = midv;
         midv = dnv;
+        off = off_dn;
     };
-    if (DYNPAR) {
-        for (int r = 0; r < rows; ++r) do_row(y0 + r, std::integral_constant<int, -1>{});
+    if (SMALL) {
+        for (uint32_t r = 0; r < rows; ++r) do_row(y0 + r, std::integral_constant<int, -1>{});
     } else {
         // y0 and rows are even: parities alternate COL, 1-COL statically
-        for (int r = 0; r < rows; r += 2) {
+        for (uint32_t r = 0; r < rows; r += 2) {
             do_row(y0 + r, std::integral_constant<int, COL>{});
             do_row(y0 + r + 1, std::integral_constant<int, 1 - COL>{});
         }

@@ -54,6 +54,8 @@ SYMBOLS = {
     "bc_sync": (C.c_int, [_P]),
     "bc_launch_count": (C.c_int64, [_P]),
     "bc_last_sweep_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "bc_timer_start": (C.c_int, [_P]),
+    "bc_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "bc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "bc_describe_plan": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bc_tie_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -189,6 +191,14 @@ class Engine:
     def last_sweep_ms(self) -> float:
         ms = C.c_float()
         self._check(self._lib.bc_last_sweep_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def timer_start(self):
+        self._check(self._lib.bc_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.bc_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
     def set_option(self, name: str, value: int):

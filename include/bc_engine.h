@@ -122,6 +122,10 @@ int bc_sync(bc_engine* e);
 int64_t bc_launch_count(const bc_engine* e);
 /* Device time in ms of the last bc_sweep call, CUDA events on the engine's stream. */
 int bc_last_sweep_ms(bc_engine* e, float* ms);
+/* CUDA-event stopwatch on the engine's stream (bench.py times K steps with it):
+ * bc_timer_start records an event, bc_timer_stop records another, waits, returns the ms between. */
+int bc_timer_start(bc_engine* e);
+int bc_timer_stop(bc_engine* e, float* ms);
 /* Select kernel variant for experiments: name/value pairs, e.g. ("rows_per_thread", 4),
  * ("use_graph", 1), ("force_generic", 1).  Unknown names give BC_ERR_ARG. */
 int bc_set_option(bc_engine* e, const char* name, int64_t value);

@@ -1,4 +1,5 @@
-"""Quick device-side timing of bc_sweep variants (development aid, not the bench)."""
+"""Quick device-side timing of bc_sweep variants (development aid, not the bench).
+usage: python tools/tune.py [quick|full]   (BC_ENGINE_LIB selects an alternative build)"""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -26,17 +27,28 @@ def run(L, n_rep, rows, sweeps, measure_every=0, boundary=0, opts=()):
     return ups, best, plan
 
 if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
+    tag = os.environ.get("BC_ENGINE_LIB", "default")
     cases = []
-    for n_rep, sweeps in ((1, 200), (64, 10)):
-        for rows in (0, 2, 4, 8, 16):
-            cases.append((4096, n_rep, rows, sweeps, 0))
-    cases.append((4096, 64, 0, 10, 1))
-    cases.append((4096, 1, 0, 200, 1))
-    cases.append((1024, 64, 0, 50, 0))
-    cases.append((256, 512, 0, 50, 0))
-    cases.append((64, 4096, 0, 50, 0))
-    cases.append((32, 8192, 0, 50, 0))
+    if mode == "quick":
+        for var in (0, 1):
+            cases.append((4096, 64, 0, 10, 0, 0, (("variant", var),)))
+            cases.append((4096, 64, 8, 10, 0, 0, (("variant", var),)))
+            cases.append((4096, 1, 4, 200, 0, 0, (("variant", var),)))
+    else:
+        for var in (0, 1):
+            for n_rep, sweeps in ((1, 200), (64, 10)):
+                for rows in (2, 4, 8, 16, 32):
+                    cases.append((4096, n_rep, rows, sweeps, 0, 0, (("variant", var),)))
+        cases.append((4096, 64, 0, 10, 1))
+        cases.append((4096, 64, 0, 10, 0, 1))
+        cases.append((4096, 1, 0, 200, 1))
+        cases.append((1024, 64, 0, 50, 0))
+        cases.append((256, 512, 0, 50, 0))
+        cases.append((64, 4096, 0, 50, 0))
+        cases.append((32, 8192, 0, 50, 0))
     for c in cases:
         ups, ms, plan = run(*c)
-        print(json.dumps({"L": c[0], "n_rep": c[1], "rows": c[2], "sweeps": c[3], "measure_every": c[4],
+        print(json.dumps({"lib": os.path.basename(tag), "L": c[0], "n_rep": c[1], "rows": c[2], "sweeps": c[3],
+                          "measure_every": c[4] if len(c) > 4 else 0, "opts": c[6] if len(c) > 6 else (),
                           "updates_per_ns": round(ups, 1), "ms": round(ms, 3), "plan": plan}), flush=True)
