@@ -46,7 +46,6 @@ struct bc_engine {
     // options
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_force_generic = 0;
-    int opt_variant = 1;  // per-site compare formulation of the fast kernel
     std::string err;
 };
 
@@ -304,20 +303,13 @@ extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*fast_fn)(const SweepParams);
 
-template <int COL, bool SMALL, bool MEAS, int VAR>
-static fast_fn fast_ptr() { return sweep_fast_kernel<COL, SMALL, MEAS, VAR>; }
-
-static fast_fn pick_fast(int col, bool small, bool meas, int var) {
-    static const fast_fn tbl[2][2][2][2] = {
-        {{{fast_ptr<0, false, false, 0>(), fast_ptr<0, false, false, 1>()},
-          {fast_ptr<0, false, true, 0>(), fast_ptr<0, false, true, 1>()}},
-         {{fast_ptr<0, true, false, 0>(), fast_ptr<0, true, false, 1>()},
-          {fast_ptr<0, true, true, 0>(), fast_ptr<0, true, true, 1>()}}},
-        {{{fast_ptr<1, false, false, 0>(), fast_ptr<1, false, false, 1>()},
-          {fast_ptr<1, false, true, 0>(), fast_ptr<1, false, true, 1>()}},
-         {{fast_ptr<1, true, false, 0>(), fast_ptr<1, true, false, 1>()},
-          {fast_ptr<1, true, true, 0>(), fast_ptr<1, true, true, 1>()}}}};
-    return tbl[col][small ? 1 : 0][meas ? 1 : 0][var ? 1 : 0];
+static fast_fn pick_fast(int col, bool small, bool meas) {
+    static const fast_fn tbl[2][2][2] = {
+        {{sweep_fast_kernel<0, false, false>, sweep_fast_kernel<0, false, true>},
+         {sweep_fast_kernel<0, true, false>, sweep_fast_kernel<0, true, true>}},
+        {{sweep_fast_kernel<1, false, false>, sweep_fast_kernel<1, false, true>},
+         {sweep_fast_kernel<1, true, false>, sweep_fast_kernel<1, true, true>}}};
+    return tbl[col][small ? 1 : 0][meas ? 1 : 0];
 }
 
 struct LaunchPlan {
@@ -343,8 +335,8 @@ static LaunchPlan make_plan(const bc_engine* e) {
             R = e->opt_rows;
         } else {
             const long long want = 148LL * 1536;  // enough threads to fill the chip
-            const int cand[4] = {16, 8, 4, 2};
-            for (int i = 0; i < 4 && !R; ++i)
+            const int cand[5] = {32, 16, 8, 4, 2};
+            for (int i = 0; i < 5 && !R; ++i)
                 if (rows_valid(L, p.cpr, cand[i]) && (long long)e->n_rep * (L / cand[i]) * p.cpr >= want) R = cand[i];
             if (!R) R = rows_valid(L, p.cpr, 2) ? 2 : 1;
         }
@@ -381,7 +373,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
-        fast_fn fn = pick_fast(col, plan.small, measure, e->opt_variant);
+        fast_fn fn = pick_fast(col, plan.small, measure);
         fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
@@ -536,7 +528,6 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
-    if (n == "variant") { e->opt_variant = value != 0; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }
     return fail(e, BC_ERR_ARG, "bc_set_option: unknown option " + n);
 }

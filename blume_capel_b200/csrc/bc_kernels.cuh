@@ -26,6 +26,27 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
+// 32-bit multiply-add kept as one IMAD (FMA pipe); plain C++ lets the compiler strength-reduce it
+// into ALU-pipe adds/shifts, and the ALU pipe is the bottleneck of the sweep kernel.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// cp.async (LDGSTS): global -> shared without staging registers; completion per thread via groups
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Exact rule for a site whose coarse compare tied: u31 = (u15 << 16 | f16) < thr31.
 __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_t thr31) {
     return (((h16 & 0x7FFFu) << 16) | f16) < thr31;
@@ -33,28 +54,39 @@ __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_
 
 // ------------------------------------------------------------------------------------------
 // Fast kernel: L % 32 == 0.  One thread = one 16-byte chunk column j, marching down the
-// L/strips rows of its strip with the three rows of the other colour held in registers.
+// L/strips rows of its strip with the three rows of the other colour held in registers and the
+// loads of the NEXT row (other-colour row y+2, side word, own chunk) issued before the current
+// row is computed (software prefetch: the kernel is instruction-bound, so exposed load latency
+// is pure loss).
 // Work item id = blockIdx.x*128 + threadIdx.x -> (replica, strip, j), j fastest, so a warp
 // reads 512 contiguous bytes per row; items/replica is a multiple of 32 (host guarantees),
 // so a warp never spans replicas.
 //   SMALL = false: rows per strip is even (row parity static per unrolled row) and
 //                  items/replica is a multiple of 128 (one replica, one table per CTA).
 //   SMALL = true : any strip height, up to 4 replicas per CTA (small lattices).
-//   VAR          : formulation of the per-site compare:
-//                  0 = ISETP/SEL per site; 1 = IMAD difference + PRMT sign masks + SWAR tie test.
-// The instruction budget, not HBM, limits this kernel: the ALU pipe
-// (LOP3/PRMT/SHF/ISETP) is the scarce one, so VAR 1 moves work to the FMA pipe (IMAD).
+// Per-site compare: d = r - E*65536 on the FMA pipe (IMAD), accept masks
+// from the sign bytes with PRMT sign replication, ties (coarse draw == coarse threshold) from a
+// SWAR has-zero-halfword test; the ALU pipe (LOP3/PRMT/SHF/ISETP) is the scarce resource.
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
+#ifndef BC_NDP4A
+#define BC_NDP4A 4   // how many of the 4 per-word table-offset extractions run on the FMA-heavy pipe
+#endif
+#ifndef BC_SHL_PRMT
+#define BC_SHL_PRMT 1
+#endif
 #ifndef BC_FAST_MIN_BLOCKS
-#define BC_FAST_MIN_BLOCKS 8
+#define BC_FAST_MIN_BLOCKS 6
 #endif
 
-template <int COL, bool SMALL, bool MEASURE, int VAR>
+template <int COL, bool SMALL, bool MEASURE>
 __global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
+    __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
+    __shared__ uint4 s_own[2][FAST_THREADS];     // thread-private own chunks (current / next row)
+    __shared__ uint32_t s_side[2][FAST_THREADS];  // thread-private side words
 
     const uint32_t ipr = (uint32_t)(P.strips * P.cpr);  // items per replica
     const unsigned long long gid0 = (unsigned long long)blockIdx.x * FAST_THREADS;
@@ -96,10 +128,10 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const size_t rep_base = (size_t)rep * (size_t)L * (size_t)Wc;
     uint8_t* own_col = P.own + rep_base + (size_t)j * 16;            // + y*Wc
     const uint8_t* oth_col = P.other + rep_base + (size_t)j * 16;    // + y*Wc
+    const uint8_t* oth_rep = P.other + rep_base;
     const uint32_t jr = (j + 1 == (uint32_t)P.cpr) ? 0u : j + 1;     // chunk holding k+1 of our last site
     const uint32_t jl = (j == 0) ? (uint32_t)P.cpr - 1 : j - 1;      // chunk holding k-1 of our first site
-    const uint8_t* side_r = P.other + rep_base + (size_t)jr * 16;       // first word of the right chunk
-    const uint8_t* side_l = P.other + rep_base + (size_t)jl * 16 + 12;  // last word of the left chunk
+    const uint32_t side_r = jr * 16, side_l = jl * 16 + 12;          // byte offsets inside a row
     const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
 
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
@@ -107,166 +139,171 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 
     uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
 
-    // rows y0-1 and y0 of the other colour (periodic wrap or open boundary = all-zero-spin row)
-    uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
-    uint4 upv, midv;
-    if (y0 == 0) upv = open ? ones4 : ldg16(oth_col + (total - Wc));
-    else upv = ldg16(oth_col + (off - Wc));
-    midv = ldg16(oth_col + off);
+    // The 18*(f+1) term of the table offset is computed with f+1 instead of f: bias the base by -18.
+    const char* tabm = tab - 18;
 
-    // one row of the strip; PARV is the row parity (y+COL)&1, or -1 for "compute it"
-    auto do_row = [&](const uint32_t y, auto parc) {
-        constexpr int PARV = decltype(parc)::value;
-        const int par = (PARV < 0) ? (int)((y + COL) & 1u) : PARV;
-        uint32_t off_dn = off + Wc;
-        uint4 dnv;
-        if (off_dn == total) {
-            dnv = open ? ones4 : ldg16(oth_col);
-        } else {
-            dnv = ldg16(oth_col + off_dn);
-        }
-        const uint32_t side = par ? (edge_r ? 0x00000001u : ldg4(side_r + off))
-                                  : (edge_l ? 0x01000000u : ldg4(side_l + off));
-        uint8_t* own_ptr = own_col + off;
-        const uint4 ownv = *reinterpret_cast<const uint4*>(own_ptr);
-
-        // coarse randoms: one Philox call per 8 sites; 16 bits per site
-        uint32_t q[8];
-        {
-            uint32_t qa[4], qb[4];
-            philox4x32_10(2u * j, y, ctr2, ctr3, k0, k1, qa);
-            philox4x32_10(2u * j + 1u, y, ctr2, ctr3, k0, k1, qb);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { q[i] = qa[i]; q[4 + i] = qb[i]; }
-        }
-
+    // Update the 16 sites of row y (byte offset `off`) given the other colour's rows y-1, y, y+1
+    // (upv, midv, dnv), the side word and the own chunk.  PAR = (y+COL)&1.
+    auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
+                          const uint4& dnv, const uint32_t side, const uint4& ownv) {
         const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
         const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
         const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
         const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-        uint32_t idx[4], nw[4], S[4];
-        uint32_t xr[4], msk[4];  // proposal xor, accept byte masks (0xFF per accepted site)
-        bool tie = false;
-        uint32_t tieacc = 0;
+        uint32_t nw[4];
 #pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-            // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
-            const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
-            const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
-            const uint32_t sh = par ? sr : sl;
-            const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
-            const uint32_t ra = q[2 * wi], rb = q[2 * wi + 1];
-            const uint32_t c4 = o[wi];
-            if (VAR == 0) {
-                // flip bits = bit 15 of each halfword -> one per byte
-                const uint32_t f4 = (__byte_perm(ra, rb, 0x7531) >> 7) & ONES;
-                // byte offsets into the u16 table: 2*(18c + 9f + S) <= 106
-                const uint32_t idx4 = c4 * 36u + f4 * 18u + S4 * 2u;
-                // proposal (main.cpp:94 in code space): p = (c + 1 + f) mod 3
-                const uint32_t t4 = c4 + f4 + ONES;                    // 1..4
-                const uint32_t ge = ((t4 + 0x05050505u) >> 3) & ONES;  // t >= 3
-                const uint32_t p4 = t4 - 3u * ge;
-                const uint32_t a0 = idx4 & 0xFFu;
-                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
-                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
-                const uint32_t a3 = idx4 >> 24;
-                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tab + a0);
-                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tab + a1);
-                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tab + a2);
-                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tab + a3);
-                const uint32_t h0 = ra & 0xFFFFu, h1 = ra >> 16, h2 = rb & 0xFFFFu, h3 = rb >> 16;
-                uint32_t m4 = 0;
-                m4 += (h0 < E0) ? 0x00000001u : 0u;
-                m4 += (h1 < E1) ? 0x00000100u : 0u;
-                m4 += (h2 < E2) ? 0x00010000u : 0u;
-                m4 += (h3 < E3) ? 0x01000000u : 0u;
-                tie = tie || (h0 == E0) || (h1 == E1) || (h2 == E2) || (h3 == E3);
-                idx[wi] = idx4;
-                xr[wi] = c4 ^ p4;
-                msk[wi] = m4 * 0xFFu;
-            } else {
-                // flips as byte masks (PRMT sign replication of bytes 1,3 of ra and rb), then 0/1 bytes
-                const uint32_t fFF = prmt(ra, rb, 0xFDB9u);
-                const uint32_t f4 = fFF & ONES;
-                const uint32_t idx4 = c4 * 36u + (f4 * 18u + (S4 + S4));
+        for (int half = 0; half < 2; ++half) {
+            // coarse randoms: one Philox call per 8 sites, 16 bits per site
+            uint32_t q[4];
+            philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
+            uint32_t idx[2], xr[2], msk[2], Ssave[2];
+            uint32_t tieacc = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < 2; ++w2) {
+                const int wi = 2 * half + w2;
+                // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
+                const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
+                const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
+                const uint32_t sh = par ? sr : sl;
+                const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
+                const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
+                const uint32_t c4 = o[wi];
+                // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
+                const uint32_t fO = (prmt(ra, rb, 0xFDB9u) & 0x03030303u) ^ ONES;
+                // byte offsets into the u16 table (base biased by -18): 36c + 18(f+1) + 2S <= 124
+                const uint32_t idx4 = imad(S4, 2u, imad(fO, 18u, c4 * 36u));
                 // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
-                const uint32_t q1 = c4 * 2u + (f4 + ONES);                 // 2c + f + 1 in 1..6
-                const uint32_t ge = ((q1 + 0x04040404u) >> 3) & ONES;      // 2c + f >= 3
-                xr[wi] = q1 - 3u * ge;
+                const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
+                const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
+                xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
+                // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
+#if BC_NDP4A >= 4
+                const uint32_t a0 = __dp4a(idx4, 0x00000001u, 0u);
+                const uint32_t a3 = __dp4a(idx4, 0x01000000u, 0u);
+#else
                 const uint32_t a0 = idx4 & 0xFFu;
+                const uint32_t a3 = idx4 >> 24;
+#endif
+#if BC_NDP4A >= 2
+                const uint32_t a1 = __dp4a(idx4, 0x00000100u, 0u);
+                const uint32_t a2 = __dp4a(idx4, 0x00010000u, 0u);
+#else
                 const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
                 const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
-                const uint32_t a3 = idx4 >> 24;
-                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tab + a0);
-                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tab + a1);
-                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tab + a2);
-                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tab + a3);
+#endif
+                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tabm + a0);
+                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
+                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
+                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
                 // d = (h - E) * 65536 + (noise < 65536): sign(d) <=> h < E, top half zero <=> h == E.
                 // h - E lies in [-32768, 32767], so the 32-bit difference cannot wrap.
-                const uint32_t d0 = (ra << 16) - E0 * 65536u;
-                const uint32_t d1 = ra - E1 * 65536u;
-                const uint32_t d2 = (rb << 16) - E2 * 65536u;
-                const uint32_t d3 = rb - E3 * 65536u;
+#if BC_SHL_PRMT
+                const uint32_t ral = __byte_perm(ra, 0u, 0x1044), rbl = __byte_perm(rb, 0u, 0x1044);
+#else
+                const uint32_t ral = ra << 16, rbl = rb << 16;
+#endif
+                const uint32_t d0 = imad(E0, 0xFFFF0000u, ral);
+                const uint32_t d1 = imad(E1, 0xFFFF0000u, ra);
+                const uint32_t d2 = imad(E2, 0xFFFF0000u, rbl);
+                const uint32_t d3 = imad(E3, 0xFFFF0000u, rb);
                 const uint32_t H01 = __byte_perm(d0, d1, 0x7632);  // [d0.hi16, d1.hi16]
                 const uint32_t H23 = __byte_perm(d2, d3, 0x7632);
-                msk[wi] = prmt(H01, H23, 0xFDB9u);            // 0xFF where d < 0
-                tieacc |= (H01 - 0x00010001u) & ~H01;               // has-zero-halfword test (bit 15 / 31)
-                tieacc |= (H23 - 0x00010001u) & ~H23;
-                idx[wi] = idx4;
+                msk[w2] = prmt(H01, H23, 0xFDB9u);                  // 0xFF where d < 0
+                tieacc |= imad(H01, 1u, 0xFFFEFFFFu) & ~H01;        // has-zero-halfword test (bits 15, 31)
+                tieacc |= imad(H23, 1u, 0xFFFEFFFFu) & ~H23;
+                idx[w2] = idx4;
+                Ssave[w2] = S4;
             }
-            S[wi] = S4;
-        }
-        if (VAR != 0) tie = (tieacc & 0x80008000u) != 0u;
-
-        if (tie) {
-            // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
-            uint32_t fa[4], fb[4];
-            const uint32_t ctr3f = ctr3_of(t, STREAM_FINE, COL);
-            philox4x32_10(2u * j, y, ctr2, ctr3f, k0, k1, fa);
-            philox4x32_10(2u * j + 1u, y, ctr2, ctr3f, k0, k1, fb);
-            const uint32_t* t31 = P.tab31 + (size_t)rep * TABLE_ENTRIES;
+            if ((tieacc & 0x80008000u) != 0u) {
+                // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
+                uint32_t f[4];
+                philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
+                const uint32_t* t31 = P.tab31 + (size_t)rep * TABLE_ENTRIES;
 #pragma unroll
-            for (int s = 0; s < 16; ++s) {
-                const int wi = s >> 2, b = s & 3;
-                const uint32_t a = (idx[wi] >> (8 * b)) & 0xFFu;
-                const uint32_t rw = q[2 * wi + (b >> 1)];
-                const uint32_t h = (b & 1) ? (rw >> 16) : (rw & 0xFFFFu);
-                const uint32_t E = *reinterpret_cast<const uint16_t*>(tab + a);
-                if (h == E) {
-                    const uint32_t fw = (s < 8) ? fa[(s & 7) >> 1] : fb[(s & 7) >> 1];
-                    const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
-                    if (exact_accept(h, f16, __ldg(t31 + (a >> 1)))) msk[wi] |= (0xFFu << (8 * b));
-                    ++n_ties;
+                for (int s = 0; s < 8; ++s) {
+                    const int w2 = s >> 2, b = s & 3;
+                    const uint32_t a = (idx[w2] >> (8 * b)) & 0xFFu;
+                    const uint32_t rw = q[s >> 1];
+                    const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
+                    const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
+                    if (h == E) {
+                        const uint32_t fw = f[s >> 1];
+                        const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
+                        if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] |= (0xFFu << (8 * b));
+                        ++n_ties;
+                    }
                 }
             }
-        }
-
 #pragma unroll
-        for (int wi = 0; wi < 4; ++wi) nw[wi] = o[wi] ^ (xr[wi] & msk[wi]);
-        *reinterpret_cast<uint4*>(own_ptr) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
-
-        if (MEASURE) {
-#pragma unroll
-            for (int wi = 0; wi < 4; ++wi) {
-                a_c = __dp4a(nw[wi], ONES, a_c);
-                a_c2 = __dp4a(nw[wi], nw[wi], a_c2);
-                if (COL == 1) {
-                    a_cS = __dp4a(nw[wi], S[wi], a_cS);
-                    a_S = __dp4a(S[wi], ONES, a_S);
+            for (int w2 = 0; w2 < 2; ++w2) {
+                const int wi = 2 * half + w2;
+                const uint32_t v = o[wi] ^ (xr[w2] & msk[w2]);
+                if (MEASURE) {
+                    a_c = __dp4a(v, ONES, a_c);
+                    a_c2 = __dp4a(v, v, a_c2);
+                    if (COL == 1) {
+                        a_cS = __dp4a(v, Ssave[w2], a_cS);
+                        a_S = __dp4a(Ssave[w2], ONES, a_S);
+                    }
                 }
+                nw[wi] = v;
             }
         }
-        upv = midv;
-        midv = dnv;
-        off = off_dn;
+        *reinterpret_cast<uint4*>(own_col + off) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
     };
-    if (SMALL) {
-        for (uint32_t r = 0; r < rows; ++r) do_row(y0 + r, std::integral_constant<int, -1>{});
+
+    // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour
+    // ---- rows, two own chunks, two side words) filled by cp.async one row ahead: the inputs of row
+    // ---- y+1 are in flight while row y is computed, and they cost no registers while in flight.
+    const uint32_t tid = threadIdx.x;
+    auto stage_other = [&](const int slot, uint32_t o) {  // other-colour row at byte offset o (== total: wrap/open)
+        if (o == total) {
+            if (open) { s_rows[slot][tid] = ones4; return; }
+            o = 0;
+        }
+        cp_async16(&s_rows[slot][tid], oth_col + o);
+    };
+    auto stage_row_inputs = [&](const int slot2, const uint32_t off_row, const int par) {  // own chunk + side word
+        cp_async16(&s_own[slot2][tid], own_col + off_row);
+        if (par) {
+            if (edge_r) s_side[slot2][tid] = 0x00000001u; else cp_async4(&s_side[slot2][tid], oth_rep + off_row + side_r);
+        } else {
+            if (edge_l) s_side[slot2][tid] = 0x01000000u; else cp_async4(&s_side[slot2][tid], oth_rep + off_row + side_l);
+        }
+    };
+
+    uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
+    if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
+    else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
+    cp_async16(&s_rows[1][tid], oth_col + off);
+    stage_other(2, off + Wc);
+    stage_row_inputs(0, off, (int)((y0 + COL) & 1u));
+    cp_async_commit();
+
+    // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
+    auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
+        if (!last) {
+            stage_other((sl + 3) & 3, off + 2 * Wc);
+            stage_row_inputs((sl + 1) & 1, off + Wc, 1 - par);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed has landed: row r is ready
+        const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
+        const uint4 ownv = s_own[sl & 1][tid];
+        const uint32_t side = s_side[sl & 1][tid];
+        update_row(y0 + r, off, par, upv, midv, dnv, side, ownv);
+        off += Wc;
+    };
+
+    if (SMALL || (rows & 3u)) {
+        for (uint32_t r = 0; r < rows; ++r) march(r, (int)((y0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
     } else {
-        // y0 and rows are even: parities alternate COL, 1-COL statically
-        for (uint32_t r = 0; r < rows; r += 2) {
-            do_row(y0 + r, std::integral_constant<int, COL>{});
-            do_row(y0 + r + 1, std::integral_constant<int, 1 - COL>{});
+        // y0 and rows are multiples of 4: parities alternate COL, 1-COL statically; static ring slots
+        for (uint32_t r = 0; r < rows; r += 4) {
+            march(r, COL, false, 0);
+            march(r + 1, 1 - COL, false, 1);
+            march(r + 2, COL, false, 2);
+            march(r + 3, 1 - COL, r + 4 == rows, 3);
         }
     }
 

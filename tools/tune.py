@@ -31,15 +31,15 @@ if __name__ == "__main__":
     tag = os.environ.get("BC_ENGINE_LIB", "default")
     cases = []
     if mode == "quick":
-        for var in (0, 1):
-            cases.append((4096, 64, 0, 10, 0, 0, (("variant", var),)))
-            cases.append((4096, 64, 8, 10, 0, 0, (("variant", var),)))
-            cases.append((4096, 1, 4, 200, 0, 0, (("variant", var),)))
+        cases.append((4096, 64, 0, 10, 0, 0))
+        cases.append((4096, 64, 8, 10, 0, 0))
+        cases.append((4096, 64, 32, 10, 0, 0))
+        cases.append((4096, 64, 0, 10, 1, 0))
+        cases.append((4096, 1, 4, 200, 0, 0))
     else:
-        for var in (0, 1):
-            for n_rep, sweeps in ((1, 200), (64, 10)):
-                for rows in (2, 4, 8, 16, 32):
-                    cases.append((4096, n_rep, rows, sweeps, 0, 0, (("variant", var),)))
+        for n_rep, sweeps in ((1, 200), (64, 10)):
+            for rows in (2, 4, 8, 16, 32, 64):
+                cases.append((4096, n_rep, rows, sweeps, 0, 0))
         cases.append((4096, 64, 0, 10, 1))
         cases.append((4096, 64, 0, 10, 0, 1))
         cases.append((4096, 1, 0, 200, 1))
