@@ -1,0 +1,181 @@
+// bc_run -- host driver with the reference's run interface, on top of the C ABI (bc_engine.h).
+//
+// Same seven positionals as /root/reference/main.cpp:316-324 (documented in job_scripts/run.sh:10-11):
+//     bc_run run root burn nsteps T D J [flags]
+//   burn = 0: load ./{root}/burn/{L}_burn.txt and collect; 1: burn in, write the burn file, stop;
+//   >= 2: burn in, then collect (main.cpp:337-355).  With no arguments the reference's defaults
+//   apply (main.cpp:325-333).  Files, all in the reference's gap format (main.cpp:232-257):
+//     ./{root}/burn/{L}_burn.txt, ./{root}/spin/{L}/{run}/{i}.txt, ./{root}/fk/{L}/{run}/{i}.txt
+// What differs: L is a flag instead of -DL_MACRO; the lattice update is the GPU checkerboard
+// Metropolis sweep (no Wolff move); sweeps per burn-in / per sample default to the reference's
+// attempt counts (1500*N resp. 9*N step() calls of 3 sweeps each, main.cpp:342,362,159) and can be
+// set with flags; --seed makes the run reproducible (the reference seeds from random_device).
+#include <cerrno>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <random>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "../../include/bc_engine.h"
+#include "gap_format.hpp"
+
+namespace {
+
+// Philox4x32-10 on the host, for the FK bond variables only (stream 3 of the engine's key space).
+void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); ++i) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty()) mkdir(cur.c_str(), 0777);
+        }
+        if (i < path.size()) cur += path[i];
+    }
+}
+
+int die(bc_engine* e, const char* what) {
+    std::cerr << "bc_run: " << what << ": " << bc_last_error(e) << std::endl;
+    if (e) bc_destroy(e);
+    return 1;
+}
+
+}  // namespace
+
+int main(int argc, const char* argv[]) {
+    // ---- the reference's positionals and defaults (main.cpp:316-333)
+    int run = 0, burn = 2, nsteps = 1500;
+    std::string root = "NONE";
+    double T = 0.608, D = 1.966, J = 1.0;
+    int argi = 1;
+    if (argc > 1 && std::strncmp(argv[1], "--", 2) != 0) {
+        if (argc < 8) {
+            std::cerr << "usage: bc_run run root burn nsteps T D J [--L n] [--boundary periodic|open] [--seed s]\n"
+                         "              [--device d] [--burn-sweeps n] [--sweeps-per-sample n] [--obs file.csv]\n"
+                         "              [--no-fk] [--mkdir]\n";
+            return 2;
+        }
+        run = std::atoi(argv[1]); root = argv[2]; burn = std::atoi(argv[3]); nsteps = std::atoi(argv[4]);
+        T = std::atof(argv[5]); D = std::atof(argv[6]); J = std::atof(argv[7]);
+        argi = 8;
+    }
+    int L = 64, device = 0, boundary = BC_PERIODIC;
+    bool have_seed = false, write_fk = true, do_mkdir = false;
+    uint64_t seed = 0;
+    int64_t burn_sweeps = -1, sweeps_per_sample = -1;
+    std::string obs_path;
+    for (; argi < argc; ++argi) {
+        const std::string a = argv[argi];
+        auto next = [&]() -> const char* { return argi + 1 < argc ? argv[++argi] : ""; };
+        if (a == "--L") L = std::atoi(next());
+        else if (a == "--boundary") boundary = std::string(next()) == "open" ? BC_OPEN : BC_PERIODIC;
+        else if (a == "--seed") { seed = std::strtoull(next(), nullptr, 0); have_seed = true; }
+        else if (a == "--device") device = std::atoi(next());
+        else if (a == "--burn-sweeps") burn_sweeps = std::atoll(next());
+        else if (a == "--sweeps-per-sample") sweeps_per_sample = std::atoll(next());
+        else if (a == "--obs") obs_path = next();
+        else if (a == "--no-fk") write_fk = false;
+        else if (a == "--mkdir") do_mkdir = true;
+        else { std::cerr << "bc_run: unknown flag " << a << std::endl; return 2; }
+    }
+    if (!have_seed) { std::random_device rd; seed = ((uint64_t)rd() << 32) | rd(); }  // like main.cpp:307-309
+    const int64_t N = (int64_t)L * L;
+    if (burn_sweeps < 0) burn_sweeps = 3 * 1500 * N;        // 1500*N step() calls (main.cpp:342), 3 sweeps each
+    if (sweeps_per_sample < 0) sweeps_per_sample = 3 * 9 * N;  // 9*N step() calls (main.cpp:362)
+
+    const std::string sL = std::to_string(L), sRun = std::to_string(run);
+    const std::string burn_path = "./" + root + "/burn/" + sL + "_burn.txt";
+    const std::string spin_dir = "./" + root + "/spin/" + sL + "/" + sRun + "/";
+    const std::string fk_dir = "./" + root + "/fk/" + sL + "/" + sRun + "/";
+    if (do_mkdir) {  // gen_files.py:5-22 creates these for the reference
+        mkdirs("./" + root + "/burn");
+        mkdirs(spin_dir);
+        mkdirs(fk_dir);
+    }
+
+    bc_engine* eng = nullptr;
+    if (bc_create(&eng, L, boundary, 1, BC_STORAGE_INT8, device, seed) != BC_OK) return die(nullptr, "bc_create");
+    if (bc_set_params(eng, -1, T, D, J) != BC_OK) return die(eng, "bc_set_params");
+    std::vector<int8_t> spins((size_t)N);
+    const bool periodic = boundary == BC_PERIODIC;
+
+    if (burn >= 1) {
+        std::cout << "burning " + sL << std::endl;  // main.cpp:338
+        if (bc_init_random(eng, 0) != BC_OK) return die(eng, "bc_init_random");
+        if (bc_sweep(eng, burn_sweeps, 0, nullptr) < 0) return die(eng, "bc_sweep");
+        if (bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_download");
+        if (!bcgap::write_file(burn_path, bcgap::spin_clusters_to_gap(spins.data(), L, periodic)))
+            std::cerr << "bc_run: cannot write " << burn_path << " (the reference fails silently here)" << std::endl;
+        std::cout << "burnt " + sL << std::endl;  // main.cpp:351
+        if (burn == 1) { bc_destroy(eng); return 0; }
+    }
+
+    // If not burning in, grab the burned-in lattice (main.cpp:358)
+    std::string text;
+    if (!bcgap::read_file(burn_path, text) || !bcgap::gap_to_lattice(text, L, spins.data())) {
+        std::cerr << "bc_run: cannot read burn file " << burn_path << std::endl;
+        bc_destroy(eng);
+        return 1;
+    }
+    if (bc_upload(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_upload");
+    // burn = 0: continue the sweep counter after the nominal burn-in so that a collection run started
+    // with the same --seed does not replay the random numbers the burn-in consumed
+    if (burn < 1 && bc_set_sweep_counter(eng, burn_sweeps) != BC_OK) return die(eng, "bc_set_sweep_counter");
+
+    FILE* obs_file = nullptr;
+    if (!obs_path.empty()) {
+        obs_file = std::fopen(obs_path.c_str(), "w");
+        if (obs_file) std::fprintf(obs_file, "sample,sweep,M,Q,B,E_per_site,m,q\n");
+    }
+    double sE = 0, sAm = 0, sQ = 0, sM2 = 0, sM4 = 0;
+    const double p_fk = 1 - std::exp(-2 * (1 / T) * J);  // main.cpp:371
+    for (int i = 0; i < nsteps; ++i) {
+        bc_obs o;
+        // measure_every = sweeps_per_sample: one fused measurement at the end of the block when aligned
+        if (bc_sweep(eng, sweeps_per_sample, 0, nullptr) < 0) return die(eng, "bc_sweep");
+        if (bc_measure(eng, &o) != BC_OK) return die(eng, "bc_measure");
+        if (bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_download");
+        const double E = (-J * (double)o.B + D * (double)o.Q) / (double)N, m = (double)o.M / (double)N,
+                     q = (double)o.Q / (double)N;
+        sE += E; sAm += std::fabs(m); sQ += q; sM2 += m * m; sM4 += m * m * m * m;
+        if (obs_file)
+            std::fprintf(obs_file, "%d,%lld,%lld,%lld,%lld,%.12g,%.12g,%.12g\n", i, (long long)o.sweep, (long long)o.M,
+                         (long long)o.Q, (long long)o.B, E, m, q);
+        const std::string name = std::to_string(i) + ".txt";
+        bcgap::write_file(spin_dir + name, bcgap::spin_clusters_to_gap(spins.data(), L, periodic));  // main.cpp:369-370
+        if (write_fk) {                                                                               // main.cpp:371-372
+            const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+            const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
+            auto bond = [&](int64_t site, int dir) {
+                uint32_t w[4];
+                philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)i, (3u << 1) | (uint32_t)dir, k0, k1, w);
+                return w[0] < thr;
+            };
+            bcgap::write_file(fk_dir + name, bcgap::clusters_to_gap(spins.data(), L, periodic, bond));
+        }
+    }
+    if (obs_file) std::fclose(obs_file);
+    if (nsteps > 0) {
+        const double n = nsteps, m2 = sM2 / n, am = sAm / n;
+        std::printf("{\"L\": %d, \"T\": %.10g, \"D\": %.10g, \"J\": %.10g, \"samples\": %d, \"sweeps_per_sample\": %lld, "
+                    "\"E_per_site\": %.10g, \"abs_m\": %.10g, \"q\": %.10g, \"U4\": %.10g, \"chi\": %.10g, \"seed\": %llu}\n",
+                    L, T, D, J, nsteps, (long long)sweeps_per_sample, sE / n, am, sQ / n, 1 - (sM4 / n) / (3 * m2 * m2),
+                    (double)N * (m2 - am * am), (unsigned long long)seed);
+    }
+    bc_destroy(eng);
+    return 0;
+}

@@ -1,0 +1,63 @@
+"""Statistical parity: <E>, <|m|>, <q>, U4 from the GPU engine against (i) exact enumeration and
+(ii) the UNMODIFIED reference (tests/golden/reference_stats.json, made by make_reference_stats.py
+from oracle/_ref/tri-L), within stated error bars: |gpu - ref| < 4 * sqrt(err_gpu^2 + err_ref^2).
+
+The GPU runs many independent replicas of checkerboard-only dynamics (no Wolff move), thermalised
+for >> tau ~ L^2.2 sweeps; errors are the spread over 32 blocks of replicas (independent streams).
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TC = (0.608, 1.966, 1.0)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "reference_stats.json")
+
+
+def gpu_estimates(bc, L, n_rep, therm, n_meas, gap, seed):
+    e = bc.Engine(L, 0, n_rep, 0, seed)
+    e.set_params(*TC)
+    e.init_random()
+    e.sweep(therm)
+    e.sweep_counter = (e.sweep_counter + gap - 1) // gap * gap
+    obs = e.sweep(n_meas * gap, gap)
+    e.close()
+    N = L * L
+    m = obs["M"] / N
+    q = obs["Q"] / N
+    E = (-TC[2] * obs["B"] + TC[1] * obs["Q"]) / N
+    nb = 32
+    blocks = np.array_split(np.arange(n_rep), nb)
+
+    def est(idx):
+        mm = m[:, idx]
+        m2, m4, am = (mm**2).mean(), (mm**4).mean(), np.abs(mm).mean()
+        return np.array([E[:, idx].mean(), am, q[:, idx].mean(), 1 - m4 / (3 * m2 * m2), N * (m2 - am * am)])
+
+    full = est(np.arange(n_rep))
+    jk = np.array([est(np.concatenate([b for j, b in enumerate(blocks) if j != i])) for i in range(nb)])
+    err = np.sqrt((nb - 1) / nb * ((jk - jk.mean(0)) ** 2).sum(0))
+    return full, err
+
+
+def test_L4_against_exact_enumeration(bc):
+    exact = np.array([0.13644431, 0.65236652, 0.66068962, 0.49561525, 2.34823069])
+    got, err = gpu_estimates(bc, 4, 8192, 2000, 100, 20, 11)
+    z = (got - exact) / err
+    assert np.all(np.abs(z) < 4.5), (got, err, z)
+    assert np.all(err[:3] < 1e-3)  # the comparison is tight
+
+
+@pytest.mark.parametrize("L,n_rep,therm,n_meas,gap", [(8, 4096, 4000, 60, 100), (16, 2048, 15000, 60, 400),
+                                                      (32, 2048, 60000, 40, 1500)])
+def test_against_unmodified_reference(bc, L, n_rep, therm, n_meas, gap):
+    ref = json.load(open(GOLD))[str(L)]
+    mean, rerr = np.array(ref["mean"]), np.array(ref["err"])
+    got, err = gpu_estimates(bc, L, n_rep, therm, n_meas, gap, 100 + L)
+    z = (got - mean) / np.sqrt(err**2 + rerr**2)
+    # E, |m|, q, U4 (chi is reported but its error bar from 8 reference runs is too crude to gate on)
+    assert np.all(np.abs(z[:4]) < 4.0), dict(L=L, gpu=got.tolist(), gpu_err=err.tolist(), ref=mean.tolist(),
+                                              ref_err=rerr.tolist(), z=z.tolist())
