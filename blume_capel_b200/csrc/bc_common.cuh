@@ -60,7 +60,11 @@ struct SweepParams {
     const int64_t* slot_ptr; // optional device-resident obs slot base
     int64_t t;               // sweep index (or offset to *t_ptr)
     int64_t slot;            // obs slot (or offset to *slot_ptr)
-    int L;                   // lattice size
+    int L;                   // lattice size (columns; also rows unless this is a slab)
+    int rows_arr;            // rows of one replica's colour array (L, or local rows + 2 ghost rows for a slab)
+    int row_first;           // first array row that is updated (0, or 1 when ghost rows are present)
+    int rows_per_strip;      // rows each thread of the fast kernel marches over
+    int y_rng_off;           // global row = array row + y_rng_off (RNG counter and colour parity)
     int Wc;                  // compact row stride in bytes
     int cpr;                 // 16-byte chunks per compact row (fast kernel)
     int strips;              // row strips per replica (fast kernel), rows per strip = L / strips

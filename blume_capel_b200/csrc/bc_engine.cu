@@ -6,6 +6,9 @@
 // (main.cpp:159-161, metropolis() at main.cpp:89-112).
 #include "../../include/bc_engine.h"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound lazily with dlopen, so libbc_engine.so has no NCCL dependency
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,12 +21,60 @@ using namespace bc;
 
 namespace {
 thread_local std::string g_create_error;
-}
+
+// NCCL entry points used by the slab halo exchange, resolved at first use from the libnccl.so.2
+// already in the process (torch's bundled copy under torchrun) or on the library path.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+#define BC_NCCL_SYM(field, name)                                         \
+        field = reinterpret_cast<decltype(field)>(dlsym(handle, name));   \
+        if (!field) { error = std::string("dlsym ") + name; handle = nullptr; return false; }
+        BC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        BC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        BC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        BC_NCCL_SYM(Send, "ncclSend")
+        BC_NCCL_SYM(Recv, "ncclRecv")
+        BC_NCCL_SYM(AllReduce, "ncclAllReduce")
+        BC_NCCL_SYM(GroupStart, "ncclGroupStart")
+        BC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        BC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef BC_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+}  // namespace
 
 struct bc_engine {
     int L = 0, boundary = 0, n_rep = 0, device = 0;
     uint64_t seed = 0;
     int Wc = 0;
+    // geometry of the local piece (== the whole lattice unless this handle is one slab of a decomposition)
+    int Ly = 0;         // owned rows
+    int y_glob0 = 0;    // global row of the first owned row
+    int rows_arr = 0;   // rows of one replica's colour array (Ly, or Ly + 2 ghost rows)
+    int row_first = 0;  // array row of the first owned row
+    bool ghost = false;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
     size_t colour_bytes = 0;  // bytes of one colour array (all replicas)
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
@@ -48,6 +99,22 @@ struct bc_engine {
     int opt_force_generic = 0;
     std::string err;
 };
+
+#define BC_NCCL(e, call)                                                                         \
+    do {                                                                                         \
+        ncclResult_t _st = (call);                                                               \
+        if (_st != ncclSuccess) {                                                                \
+            (e)->err = std::string(#call) + ": " + g_nccl.GetErrorString(_st);                   \
+            return BC_ERR_NCCL;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+static Geom geom_of(const bc_engine* e) {
+    Geom g;
+    g.L = e->L; g.Wc = e->Wc; g.Ly = e->Ly; g.rows_arr = e->rows_arr; g.row_first = e->row_first;
+    g.y_glob0 = e->y_glob0; g.open = e->boundary == BC_OPEN; g.ghost = e->ghost;
+    return g;
+}
 
 #define BC_CUDA(e, call)                                                                         \
     do {                                                                                         \
@@ -105,6 +172,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31);
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
@@ -124,8 +192,8 @@ static int launch_fill(bc_engine* e, uint8_t* p, size_t n, uint8_t v) {
     return BC_OK;
 }
 
-extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device,
-                         uint64_t seed) {
+static int create_common(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device,
+                         uint64_t seed, int nranks, int rank, const void* nccl_id) {
     if (!out) return fail(nullptr, BC_ERR_ARG, "bc_create: out is NULL");
     *out = nullptr;
     if (L < 2 || L > 65536) return fail(nullptr, BC_ERR_ARG, "bc_create: L out of range [2, 65536]");
@@ -134,6 +202,13 @@ extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, i
         return fail(nullptr, BC_ERR_ARG, "bc_create: the periodic checkerboard needs even L");
     if (n_replicas < 1) return fail(nullptr, BC_ERR_ARG, "bc_create: n_replicas < 1");
     if (storage != BC_STORAGE_INT8) return fail(nullptr, BC_ERR_UNSUPPORTED, "bc_create: only BC_STORAGE_INT8");
+    const bool slab = nranks > 0;
+    if (slab) {
+        if (rank < 0 || rank >= nranks) return fail(nullptr, BC_ERR_ARG, "bc_create_slab: rank out of range");
+        if (L % 32 || L % nranks || ((L / nranks) & 1))
+            return fail(nullptr, BC_ERR_ARG, "bc_create_slab: need L % 32 == 0 and an even number of rows per rank");
+        if (nranks > 1 && !nccl_id) return fail(nullptr, BC_ERR_ARG, "bc_create_slab: nccl_id is NULL");
+    }
     int ndev = 0;
     cudaError_t st = cudaGetDeviceCount(&ndev);
     if (st != cudaSuccess || ndev == 0)
@@ -144,7 +219,13 @@ extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, i
     bc_engine* e = new bc_engine();
     e->L = L; e->boundary = boundary; e->n_rep = n_replicas; e->device = device; e->seed = seed;
     e->Wc = (((L + 1) / 2) + 15) / 16 * 16;
-    e->colour_bytes = (size_t)n_replicas * (size_t)L * (size_t)e->Wc;
+    if (slab) {
+        e->nranks = nranks; e->rank = rank; e->ghost = true;
+        e->Ly = L / nranks; e->y_glob0 = rank * e->Ly; e->rows_arr = e->Ly + 2; e->row_first = 1;
+    } else {
+        e->Ly = L; e->y_glob0 = 0; e->rows_arr = L; e->row_first = 0;
+    }
+    e->colour_bytes = (size_t)n_replicas * (size_t)e->rows_arr * (size_t)e->Wc;
     e->h_tab31.assign((size_t)n_replicas * TABLE_ENTRIES, 0u);
     e->params_set.assign((size_t)n_replicas, 0);
     auto bail = [&](const char* what, cudaError_t s) {
@@ -164,14 +245,59 @@ extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc ties", st);
     if ((st = cudaMemsetAsync(e->d_ties, 0, sizeof(unsigned long long), e->stream)) != cudaSuccess) return bail("memset", st);
-    // all spins 0 (code 1), including the pad bytes of each compact row
+    // all spins 0 (code 1), including the pad bytes of each compact row and the ghost rows
     if (launch_fill(e, e->d_c[0], e->colour_bytes, 1) != BC_OK || launch_fill(e, e->d_c[1], e->colour_bytes, 1) != BC_OK) {
         g_create_error = e->err;
         bc_destroy(e);
         return BC_ERR_CUDA;
     }
     if ((st = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", st);
+    if (slab && nranks > 1) {
+        if (!g_nccl.load()) {
+            g_create_error = "bc_create_slab: " + g_nccl.error;
+            bc_destroy(e);
+            return BC_ERR_NCCL;
+        }
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t ns = g_nccl.CommInitRank(&e->comm, nranks, id, rank);
+        if (ns != ncclSuccess) {
+            g_create_error = std::string("bc_create_slab: ncclCommInitRank: ") + g_nccl.GetErrorString(ns);
+            e->comm = nullptr;
+            bc_destroy(e);
+            return BC_ERR_NCCL;
+        }
+    }
     *out = e;
+    return BC_OK;
+}
+
+extern "C" int bc_create(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device,
+                         uint64_t seed) {
+    return create_common(out, L, boundary, n_replicas, storage, device, seed, 0, 0, nullptr);
+}
+
+extern "C" int bc_slab_unique_id(void* id128) {
+    if (!id128) return BC_ERR_ARG;
+    if (!g_nccl.load()) return fail(nullptr, BC_ERR_NCCL, "bc_slab_unique_id: " + g_nccl.error);
+    ncclUniqueId id;
+    ncclResult_t ns = g_nccl.GetUniqueId(&id);
+    if (ns != ncclSuccess) return fail(nullptr, BC_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(ns));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, sizeof(id));
+    return BC_OK;
+}
+
+extern "C" int bc_create_slab(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device,
+                              uint64_t seed, int n_ranks, int rank, const void* nccl_id128) {
+    if (n_ranks < 1) return fail(nullptr, BC_ERR_ARG, "bc_create_slab: n_ranks < 1");
+    return create_common(out, L, boundary, n_replicas, storage, device, seed, n_ranks, rank, nccl_id128);
+}
+
+extern "C" int bc_local_rows(const bc_engine* e, int* rows, int* first_global_row) {
+    if (!e) return BC_ERR_ARG;
+    if (rows) *rows = e->Ly;
+    if (first_global_row) *first_global_row = e->y_glob0;
     return BC_OK;
 }
 
@@ -212,6 +338,49 @@ extern "C" int bc_get_table(const bc_engine* e, int replica, uint32_t thr31[54])
 }
 
 // ---------------------------------------------------------------------------------------------
+// slab halo exchange: after colour `col` was updated, its first owned row goes to the bottom ghost row
+// of the rank above and its last owned row to the top ghost row of the rank below (periodic wrap; an
+// open lattice keeps code-1 ghost rows at the global edges).  32 KiB per message at L = 65536.
+// ---------------------------------------------------------------------------------------------
+static int exchange_halo(bc_engine* e, int col) {
+    if (!e->ghost) return BC_OK;
+    const bool periodic = e->boundary == BC_PERIODIC;
+    const size_t Wc = (size_t)e->Wc, rep_stride = (size_t)e->rows_arr * Wc;
+    if (e->nranks == 1) {
+        if (!periodic) return BC_OK;
+        const long long total = 2LL * e->Wc * e->n_rep;
+        halo_self_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(e->d_c[col], geom_of(e), e->n_rep);
+        ++e->launches;
+        BC_CUDA(e, cudaGetLastError());
+        return BC_OK;
+    }
+    const int up = e->rank - 1, dn = e->rank + 1;
+    const int prev = up >= 0 ? up : (periodic ? e->nranks - 1 : -1);
+    const int next = dn < e->nranks ? dn : (periodic ? 0 : -1);
+    BC_NCCL(e, g_nccl.GroupStart());
+    for (int r = 0; r < e->n_rep; ++r) {
+        uint8_t* base = e->d_c[col] + (size_t)r * rep_stride;
+        uint8_t* first_owned = base + Wc;
+        uint8_t* last_owned = base + (size_t)e->Ly * Wc;
+        uint8_t* ghost_top = base;
+        uint8_t* ghost_bot = base + (size_t)(e->Ly + 1) * Wc;
+        // order matters when prev == next (2 ranks): sends (first, last) pair with recvs (bottom, top)
+        if (prev >= 0) BC_NCCL(e, g_nccl.Send(first_owned, Wc, ncclUint8, prev, e->comm, e->stream));
+        if (next >= 0) BC_NCCL(e, g_nccl.Send(last_owned, Wc, ncclUint8, next, e->comm, e->stream));
+        if (next >= 0) BC_NCCL(e, g_nccl.Recv(ghost_bot, Wc, ncclUint8, next, e->comm, e->stream));
+        if (prev >= 0) BC_NCCL(e, g_nccl.Recv(ghost_top, Wc, ncclUint8, prev, e->comm, e->stream));
+    }
+    BC_NCCL(e, g_nccl.GroupEnd());
+    return BC_OK;
+}
+
+static int exchange_both(bc_engine* e) {
+    int rc = exchange_halo(e, 0);
+    if (rc == BC_OK) rc = exchange_halo(e, 1);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // lattice state
 // ---------------------------------------------------------------------------------------------
 static int ensure_stage(bc_engine* e, size_t bytes) {
@@ -229,38 +398,40 @@ extern "C" int bc_init_random(bc_engine* e, int replica) {
     if (replica < -1 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_init_random: replica out of range");
     BC_CUDA(e, cudaSetDevice(e->device));
     const int r0 = replica < 0 ? 0 : replica, n = replica < 0 ? e->n_rep : 1;
-    const long long total = (long long)n * e->L * e->L;
+    const long long total = (long long)n * e->Ly * e->L;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n, (uint32_t)e->seed,
+    init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], geom_of(e), r0, n, (uint32_t)e->seed,
                                                (uint32_t)(e->seed >> 32));
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
-    return BC_OK;
+    return exchange_both(e);
 }
 
 static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins) {
     BC_CUDA(e, cudaSetDevice(e->device));
-    const size_t bytes = (size_t)n * e->L * e->L;
+    const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
-    const long long total = (long long)n * e->L * e->Wc;
+    const long long total = (long long)n * e->Ly * e->Wc;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
+    rc = exchange_both(e);
+    if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
     return BC_OK;
 }
 
 static int download_range(bc_engine* e, int r0, int n, int8_t* spins) {
     BC_CUDA(e, cudaSetDevice(e->device));
-    const size_t bytes = (size_t)n * e->L * e->L;
+    const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
     const long long total = (long long)bytes;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], e->L, e->Wc, r0, n);
+    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
@@ -319,29 +490,29 @@ struct LaunchPlan {
     unsigned grid = 0;
 };
 
-static bool rows_valid(int L, int cpr, int R) {
-    if (R < 1 || L % R) return false;
-    return (((long long)(L / R) * cpr) % 32) == 0;
+static bool rows_valid(int Ly, int cpr, int R) {
+    if (R < 1 || Ly % R) return false;
+    return (((long long)(Ly / R) * cpr) % 32) == 0;
 }
 
 static LaunchPlan make_plan(const bc_engine* e) {
     LaunchPlan p;
-    const int L = e->L;
-    if (L % 32 == 0 && !e->opt_force_generic) {
+    const int L = e->L, Ly = e->Ly;
+    if (L % 32 == 0 && (!e->opt_force_generic || e->ghost)) {
         p.fast = true;
         p.cpr = L / 32;
         int R = 0;
-        if (e->opt_rows > 0 && rows_valid(L, p.cpr, e->opt_rows)) {
+        if (e->opt_rows > 0 && rows_valid(Ly, p.cpr, e->opt_rows)) {
             R = e->opt_rows;
         } else {
             const long long want = 148LL * 1536;  // enough threads to fill the chip
             const int cand[5] = {32, 16, 8, 4, 2};
             for (int i = 0; i < 5 && !R; ++i)
-                if (rows_valid(L, p.cpr, cand[i]) && (long long)e->n_rep * (L / cand[i]) * p.cpr >= want) R = cand[i];
-            if (!R) R = rows_valid(L, p.cpr, 2) ? 2 : 1;
+                if (rows_valid(Ly, p.cpr, cand[i]) && (long long)e->n_rep * (Ly / cand[i]) * p.cpr >= want) R = cand[i];
+            if (!R) R = rows_valid(Ly, p.cpr, 2) ? 2 : 1;
         }
         p.rows = R;
-        p.strips = L / R;
+        p.strips = Ly / R;
         p.small = (R & 1) != 0 || (((long long)p.strips * p.cpr) % FAST_THREADS) != 0;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
@@ -365,6 +536,10 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.t = t;
     P.slot = slot;
     P.L = e->L;
+    P.rows_arr = e->rows_arr;
+    P.row_first = e->row_first;
+    P.rows_per_strip = plan.rows;
+    P.y_rng_off = e->y_glob0 - e->row_first;
     P.Wc = e->Wc;
     P.cpr = plan.cpr;
     P.strips = plan.strips;
@@ -384,7 +559,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
 }
 
 static void raw_to_obs(const bc_engine* e, const unsigned long long* raw, int64_t sweep, bc_obs* o) {
-    const int64_t N = (int64_t)e->L * e->L;
+    const int64_t N = (int64_t)e->L * e->L;  // global lattice (slab sums are all-reduced before this)
     const int64_t N1 = N / 2;  // colour-1 sites ((0,0) is colour 0)
     const int64_t A0 = (int64_t)raw[0], A1 = (int64_t)raw[1], A2 = (int64_t)raw[2], A3 = (int64_t)raw[3];
     const int64_t A4 = (int64_t)raw[4], A5 = (int64_t)raw[5];
@@ -398,6 +573,8 @@ static int fetch_pending(bc_engine* e, bc_obs* out) {
     const int64_t n = e->pending_meas;
     if (n == 0) return BC_OK;
     std::vector<unsigned long long> raw((size_t)n * e->n_rep * OBS_RAW);
+    if (e->comm)  // slab: sum the per-rank partial sums (exact integers, order independent)
+        BC_NCCL(e, g_nccl.AllReduce(e->d_obs, e->d_obs, raw.size(), ncclUint64, ncclSum, e->comm, e->stream));
     BC_CUDA(e, cudaMemcpyAsync(raw.data(), e->d_obs, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
     for (int64_t m = 0; m < n; ++m)
@@ -438,7 +615,9 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
         const int64_t t = e->t + s;
         const bool measure = measure_every > 0 && ((t + 1) % measure_every == 0);
         launch_half(e, plan, 0, measure, t, slot);
+        if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
         launch_half(e, plan, 1, measure, t, slot);
+        if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
         if (measure) ++slot;
     }
     BC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
@@ -449,6 +628,7 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
     if (out && n_meas > 0) {
         int rc = fetch_pending(e, out);
         if (rc != BC_OK) return rc;
+        e->pending_meas = 0;  // fetched (and, for slabs, already all-reduced in place)
         return n_meas * e->n_rep;
     }
     return 0;
@@ -461,6 +641,7 @@ extern "C" int64_t bc_read_obs(bc_engine* e, bc_obs* out, int64_t max_records) {
     BC_CUDA(e, cudaSetDevice(e->device));
     int rc = fetch_pending(e, out);
     if (rc != BC_OK) return rc;
+    e->pending_meas = 0;
     return n;
 }
 
@@ -471,12 +652,16 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
     const size_t bytes = (size_t)e->n_rep * OBS_RAW * sizeof(unsigned long long);
     BC_CUDA(e, cudaMalloc(&d_raw, bytes));
     cudaError_t st = cudaMemsetAsync(d_raw, 0, bytes, e->stream);
-    const long long total = (long long)e->n_rep * e->L * e->L;
+    const long long total = (long long)e->n_rep * e->Ly * e->L;
     const unsigned blocks = (unsigned)((total + 255) / 256);
     if (st == cudaSuccess) {
-        measure_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], e->L, e->Wc, e->n_rep, e->boundary == BC_OPEN, d_raw);
+        measure_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], geom_of(e), e->n_rep, d_raw);
         ++e->launches;
         st = cudaGetLastError();
+    }
+    if (st == cudaSuccess && e->comm) {
+        ncclResult_t ns = g_nccl.AllReduce(d_raw, d_raw, (size_t)e->n_rep * OBS_RAW, ncclUint64, ncclSum, e->comm, e->stream);
+        if (ns != ncclSuccess) { cudaFree(d_raw); return fail(e, BC_ERR_NCCL, std::string("bc_measure: ") + g_nccl.GetErrorString(ns)); }
     }
     std::vector<unsigned long long> raw((size_t)e->n_rep * OBS_RAW);
     if (st == cudaSuccess) st = cudaMemcpyAsync(raw.data(), d_raw, bytes, cudaMemcpyDeviceToHost, e->stream);

@@ -111,9 +111,9 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     }
     const uint32_t strip = rem / (uint32_t)P.cpr;
     const uint32_t j = rem - strip * (uint32_t)P.cpr;
-    const uint32_t L = (uint32_t)P.L;
-    const uint32_t rows = L / (uint32_t)P.strips;
-    const uint32_t y0 = strip * rows;
+    const uint32_t rows = (uint32_t)P.rows_per_strip;
+    const uint32_t y0 = (uint32_t)P.row_first + strip * rows;  // array row; global row = y0 + y_rng_off
+    const uint32_t yg0 = y0 + (uint32_t)P.y_rng_off;
     const uint32_t Wc = (uint32_t)P.Wc;
     const bool open = P.open != 0;
 
@@ -125,7 +125,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 
     // shared-memory table of this thread's replica: uniform for !SMALL
     const char* tab = reinterpret_cast<const char*>(s_tab) + (SMALL ? (rep - rep0) * (TAB16_WORDS * 4) : 0u);
-    const size_t rep_base = (size_t)rep * (size_t)L * (size_t)Wc;
+    const size_t rep_base = (size_t)rep * (size_t)P.rows_arr * (size_t)Wc;
     uint8_t* own_col = P.own + rep_base + (size_t)j * 16;            // + y*Wc
     const uint8_t* oth_col = P.other + rep_base + (size_t)j * 16;    // + y*Wc
     const uint8_t* oth_rep = P.other + rep_base;
@@ -135,7 +135,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
 
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
-    const uint32_t total = L * Wc;  // bytes of one replica's colour array (< 2^32: L <= 65536)
+    const uint32_t total = (uint32_t)P.rows_arr * Wc;  // bytes of one replica's colour array (< 2^32)
 
     uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
 
@@ -277,7 +277,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
     cp_async16(&s_rows[1][tid], oth_col + off);
     stage_other(2, off + Wc);
-    stage_row_inputs(0, off, (int)((y0 + COL) & 1u));
+    stage_row_inputs(0, off, (int)((yg0 + COL) & 1u));
     cp_async_commit();
 
     // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
@@ -291,14 +291,14 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
         const uint4 ownv = s_own[sl & 1][tid];
         const uint32_t side = s_side[sl & 1][tid];
-        update_row(y0 + r, off, par, upv, midv, dnv, side, ownv);
+        update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
         off += Wc;
     };
 
     if (SMALL || (rows & 3u)) {
-        for (uint32_t r = 0; r < rows; ++r) march(r, (int)((y0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
+        for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
     } else {
-        // y0 and rows are multiples of 4: parities alternate COL, 1-COL statically; static ring slots
+        // yg0 is even and rows is a multiple of 4: parities alternate COL, 1-COL statically; static ring slots
         for (uint32_t r = 0; r < rows; r += 4) {
             march(r, COL, false, 0);
             march(r + 1, 1 - COL, false, 1);
@@ -421,53 +421,69 @@ sweep_generic_kernel(const __grid_constant__ SweepParams P, const int COL, const
 }
 
 // ------------------------------------------------------------------------------------------
-// Layout conversion, init, standalone measurement
+// Layout conversion, init, halo, standalone measurement.  Geometry of one replica's colour array:
+// `rows_arr` rows of Wc bytes; the owned rows are array rows row_first .. row_first+Ly-1 and hold
+// global rows y_glob0 .. y_glob0+Ly-1 (a slab owns a row range; ghost rows, if any, sit at array
+// row 0 and rows_arr-1).
 // ------------------------------------------------------------------------------------------
-// row-major int8 spins [rep][y][x]  ->  compact codes (both colours); pad bytes = code 1 (spin 0)
+struct Geom {
+    int L;          // columns (global linear size)
+    int Wc;         // compact row stride
+    int Ly;         // owned rows
+    int rows_arr;   // array rows (Ly, or Ly + 2 with ghost rows)
+    int row_first;  // array row of the first owned row
+    int y_glob0;    // global row of the first owned row (even)
+    int open;       // open boundary
+    int ghost;      // ghost rows present (vertical neighbours never wrap inside the array)
+};
+
+// row-major int8 spins [rep][Ly][L]  ->  compact codes (both colours); pad bytes = code 1 (spin 0)
 __global__ void pack_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1,
-                            int L, int Wc, int rep_first, int n_rep) {
-    const long long per_rep = (long long)L * Wc;
+                            const Geom g, int rep_first, int n_rep) {
+    const long long per_rep = (long long)g.Ly * g.Wc;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= per_rep * n_rep) return;
     const int r = (int)(gid / per_rep);
     const long long rem = gid - (long long)r * per_rep;
-    const int y = (int)(rem / Wc), k = (int)(rem - (long long)y * Wc);
-    const size_t dst = (size_t)(rep_first + r) * per_rep + (size_t)y * Wc + k;
-    const int8_t* src = spins + (size_t)r * L * L + (size_t)y * L;
-    const int xa = 2 * k + (y & 1), xb = 2 * k + ((y + 1) & 1);
-    c0[dst] = (xa < L) ? (uint8_t)(src[xa] + 1) : (uint8_t)1;
-    c1[dst] = (xb < L) ? (uint8_t)(src[xb] + 1) : (uint8_t)1;
+    const int y = (int)(rem / g.Wc), k = (int)(rem - (long long)y * g.Wc);
+    const size_t dst = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + k;
+    const int8_t* src = spins + (size_t)r * g.Ly * g.L + (size_t)y * g.L;
+    const int yg = y + g.y_glob0;
+    const int xa = 2 * k + (yg & 1), xb = 2 * k + ((yg + 1) & 1);
+    c0[dst] = (xa < g.L) ? (uint8_t)(src[xa] + 1) : (uint8_t)1;
+    c1[dst] = (xb < g.L) ? (uint8_t)(src[xb] + 1) : (uint8_t)1;
 }
 
 __global__ void unpack_kernel(int8_t* __restrict__ spins, const uint8_t* __restrict__ c0,
-                              const uint8_t* __restrict__ c1, int L, int Wc, int rep_first, int n_rep) {
-    const long long per_rep = (long long)L * L;
+                              const uint8_t* __restrict__ c1, const Geom g, int rep_first, int n_rep) {
+    const long long per_rep = (long long)g.Ly * g.L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= per_rep * n_rep) return;
     const int r = (int)(gid / per_rep);
     const long long rem = gid - (long long)r * per_rep;
-    const int y = (int)(rem / L), x = (int)(rem - (long long)y * L);
-    const size_t src = (size_t)(rep_first + r) * L * Wc + (size_t)y * Wc + (x >> 1);
-    const uint8_t code = ((x + y) & 1) ? c1[src] : c0[src];
+    const int y = (int)(rem / g.L), x = (int)(rem - (long long)y * g.L);
+    const size_t src = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (x >> 1);
+    const uint8_t code = ((x + y + g.y_glob0) & 1) ? c1[src] : c0[src];
     spins[gid] = (int8_t)((int)code - 1);
 }
 
-// iid uniform {-1,0,1} (main.cpp:166-171) from Philox stream INIT, indexed by the site index x + y*L
-__global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, int L, int Wc, int rep_first,
+// iid uniform {-1,0,1} (main.cpp:166-171) from Philox stream INIT, indexed by the GLOBAL site index x + y*L
+__global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g, int rep_first,
                             int n_rep, uint32_t key0, uint32_t key1) {
-    const long long per_rep = (long long)L * L;
+    const long long per_rep = (long long)g.Ly * g.L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= per_rep * n_rep) return;
     const int r = (int)(gid / per_rep);
     const int rep = rep_first + r;
-    const long long i = gid - (long long)r * per_rep;
-    const int y = (int)(i / L), x = (int)(i - (long long)y * L);
+    const long long li = gid - (long long)r * per_rep;
+    const int y = (int)(li / g.L), x = (int)(li - (long long)y * g.L);
+    const long long i = (long long)(y + g.y_glob0) * g.L + x;
     uint32_t w[4];
     philox4x32_10((uint32_t)(i >> 2), (uint32_t)((unsigned long long)i >> 34), 0u, STREAM_INIT << 1, key0,
                   key1 ^ (uint32_t)rep, w);
     const uint32_t code = (uint32_t)(((unsigned long long)w[i & 3] * 3ull) >> 32);
-    const size_t dst = (size_t)rep * L * Wc + (size_t)y * Wc + (x >> 1);
-    if ((x + y) & 1) c1[dst] = (uint8_t)code; else c0[dst] = (uint8_t)code;
+    const size_t dst = ((size_t)rep * g.rows_arr + g.row_first + y) * g.Wc + (x >> 1);
+    if ((x + y + g.y_glob0) & 1) c1[dst] = (uint8_t)code; else c0[dst] = (uint8_t)code;
 }
 
 __global__ void fill_kernel(uint8_t* __restrict__ p, size_t n, uint8_t v) {
@@ -475,25 +491,49 @@ __global__ void fill_kernel(uint8_t* __restrict__ p, size_t n, uint8_t v) {
     if (gid < n) p[gid] = v;
 }
 
+// single-rank periodic slab: ghost rows <- opposite owned rows of the same array (all replicas)
+__global__ void halo_self_kernel(uint8_t* __restrict__ c, const Geom g, int n_rep) {
+    const long long per_rep = 2LL * g.Wc;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_rep * n_rep) return;
+    const int r = (int)(gid / per_rep);
+    const int rem = (int)(gid - (long long)r * per_rep);
+    const int which = rem / g.Wc, k = rem - which * g.Wc;
+    uint8_t* base = c + (size_t)r * g.rows_arr * g.Wc;
+    if (which == 0) base[k] = base[(size_t)g.Ly * g.Wc + k];                              // top ghost <- last owned row
+    else base[(size_t)(g.Ly + 1) * g.Wc + k] = base[(size_t)g.Wc + k];                    // bottom ghost <- first owned row
+}
+
+// code of the neighbour (nx, ny) [ny = owned-row index, may be -1 or Ly] in the other colour's array
+__device__ __forceinline__ uint32_t geom_other_code(const uint8_t* oth_rep, const Geom& g, int nx, int ny) {
+    if (g.open) { if (nx < 0 || nx >= g.L) return 1u; }
+    else nx = (nx < 0) ? nx + g.L : (nx >= g.L ? nx - g.L : nx);
+    if (!g.ghost) {
+        if (g.open) { if (ny < 0 || ny >= g.Ly) return 1u; }
+        else ny = (ny < 0) ? ny + g.Ly : (ny >= g.Ly ? ny - g.Ly : ny);
+    }
+    return oth_rep[(size_t)(g.row_first + ny) * g.Wc + (nx >> 1)];
+}
+
 // standalone observables of the current configuration into raw accumulators [rep][OBS_RAW]
-__global__ void measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, int L, int Wc,
-                               int n_rep, int open, unsigned long long* __restrict__ obs) {
-    const long long per_rep = (long long)L * L;
+__global__ void measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, const Geom g,
+                               int n_rep, unsigned long long* __restrict__ obs) {
+    const long long per_rep = (long long)g.Ly * g.L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= per_rep * n_rep) return;
     const int rep = (int)(gid / per_rep);
     const long long i = gid - (long long)rep * per_rep;
-    const int y = (int)(i / L), x = (int)(i - (long long)y * L);
-    const size_t rb = (size_t)rep * L * Wc;
-    const int col = (x + y) & 1;
-    const uint32_t c = (col ? c1 : c0)[rb + (size_t)y * Wc + (x >> 1)];
+    const int y = (int)(i / g.L), x = (int)(i - (long long)y * g.L);
+    const size_t rb = (size_t)rep * g.rows_arr * g.Wc;
+    const int col = (x + y + g.y_glob0) & 1;
+    const uint32_t c = (col ? c1 : c0)[rb + (size_t)(g.row_first + y) * g.Wc + (x >> 1)];
     uint32_t v[OBS_RAW] = {0, 0, 0, 0, 0, 0};
     v[2 * col + 0] = c;
     v[2 * col + 1] = c * c;
     if (col == 1) {
         const uint8_t* oth = c0 + rb;
-        const uint32_t S = other_code(oth, L, Wc, x + 1, y, open) + other_code(oth, L, Wc, x - 1, y, open) +
-                           other_code(oth, L, Wc, x, y + 1, open) + other_code(oth, L, Wc, x, y - 1, open);
+        const uint32_t S = geom_other_code(oth, g, x + 1, y) + geom_other_code(oth, g, x - 1, y) +
+                           geom_other_code(oth, g, x, y + 1) + geom_other_code(oth, g, x, y - 1);
         v[4] = c * S;
         v[5] = S;
     }
@@ -503,12 +543,12 @@ __global__ void measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __
     const bool uniform = __all_sync(mask, rep == rep_lo);
     unsigned long long* dst = obs + (size_t)rep * OBS_RAW;
 #pragma unroll
-    for (int i = 0; i < OBS_RAW; ++i) {
+    for (int k = 0; k < OBS_RAW; ++k) {
         if (uniform) {
-            const uint32_t sum = __reduce_add_sync(mask, v[i]);
-            if ((int)(threadIdx.x & 31) == leader && sum) atomicAdd(dst + i, (unsigned long long)sum);
-        } else if (v[i]) {
-            atomicAdd(dst + i, (unsigned long long)v[i]);
+            const uint32_t sum = __reduce_add_sync(mask, v[k]);
+            if ((int)(threadIdx.x & 31) == leader && sum) atomicAdd(dst + k, (unsigned long long)sum);
+        } else if (v[k]) {
+            atomicAdd(dst + k, (unsigned long long)v[k]);
         }
     }
 }

@@ -36,6 +36,9 @@ _lib = None
 _P = C.c_void_p
 SYMBOLS = {
     "bc_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
+    "bc_slab_unique_id": (C.c_int, [_P]),
+    "bc_create_slab": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _P]),
+    "bc_local_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bc_destroy": (None, [_P]),
     "bc_last_error": (C.c_char_p, [_P]),
     "bc_abi_version": (C.c_int, []),
@@ -82,16 +85,37 @@ def load_library():
     return _lib
 
 
+def slab_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0, broadcast to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.bc_slab_unique_id(buf)
+    if rc != 0:
+        raise BCError(rc, (lib.bc_last_error(None) or b"").decode())
+    return buf.raw
+
+
 class Engine:
     """n_replicas independent L x L spin-1 lattices on one GPU."""
 
-    def __init__(self, L: int, boundary: int = PERIODIC, n_replicas: int = 1, device: int = 0, seed: int = 0):
+    def __init__(self, L: int, boundary: int = PERIODIC, n_replicas: int = 1, device: int = 0, seed: int = 0,
+                 slab: Optional[tuple] = None):
+        """slab = (n_ranks, rank, nccl_id_bytes_or_None): this handle owns one row slab of the lattice."""
         self._lib = load_library()
         self._h = _P()
-        rc = self._lib.bc_create(C.byref(self._h), L, boundary, n_replicas, 0, device, seed & (2**64 - 1))
+        if slab is None:
+            rc = self._lib.bc_create(C.byref(self._h), L, boundary, n_replicas, 0, device, seed & (2**64 - 1))
+        else:
+            n_ranks, rank, nid = slab
+            buf = C.create_string_buffer(bytes(nid), 128) if nid is not None else None
+            rc = self._lib.bc_create_slab(C.byref(self._h), L, boundary, n_replicas, 0, device, seed & (2**64 - 1),
+                                          n_ranks, rank, buf)
         if rc != 0:
             raise BCError(rc, (self._lib.bc_last_error(None) or b"").decode())
         self.L, self.boundary, self.n_replicas, self.device, self.seed = L, boundary, n_replicas, device, seed
+        rows, y0 = C.c_int(), C.c_int()
+        self._lib.bc_local_rows(self._h, C.byref(rows), C.byref(y0))
+        self.rows, self.first_row = rows.value, y0.value
 
     # -- helpers
     def _check(self, rc: int) -> int:
@@ -132,18 +156,18 @@ class Engine:
     def upload(self, spins: np.ndarray, replica: Optional[int] = None):
         a = np.ascontiguousarray(spins, dtype=np.int8)
         if replica is None:
-            assert a.size == self.n_replicas * self.L * self.L
+            assert a.size == self.n_replicas * self.rows * self.L
             self._check(self._lib.bc_upload_all(self._h, a.ctypes.data))
         else:
-            assert a.size == self.L * self.L
+            assert a.size == self.rows * self.L
             self._check(self._lib.bc_upload(self._h, replica, a.ctypes.data))
 
     def download(self, replica: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
         if replica is None:
-            a = out if out is not None else np.empty((self.n_replicas, self.L, self.L), np.int8)
+            a = out if out is not None else np.empty((self.n_replicas, self.rows, self.L), np.int8)
             self._check(self._lib.bc_download_all(self._h, a.ctypes.data))
         else:
-            a = out if out is not None else np.empty((self.L, self.L), np.int8)
+            a = out if out is not None else np.empty((self.rows, self.L), np.int8)
             self._check(self._lib.bc_download(self._h, replica, a.ctypes.data))
         return a
 

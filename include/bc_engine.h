@@ -67,6 +67,20 @@ void bc_destroy(bc_engine* e);
 const char* bc_last_error(const bc_engine* e);
 int bc_abi_version(void);
 
+/* ---- slab decomposition (lattices too large for one GPU; one process per GPU) ---------------------
+ * New relative to the reference, whose only multi-process mode is independent Slurm array tasks
+ * (job_scripts/runner.sh:19).  The L x L lattice is split into n_ranks row slabs of L/n_ranks rows;
+ * after every half-sweep each rank sends the freshly updated colour of its first and last owned row to
+ * its ring neighbours over NCCL (ncclSend/ncclRecv on the engine stream).  Results are bit-identical
+ * to a single-GPU run because the RNG counter is a function of global site coordinates.
+ * bc_slab_unique_id: rank 0 fills 128 bytes (an ncclUniqueId) that the caller distributes to all ranks
+ * (bench.py broadcasts it through its process group).  n_ranks == 1 needs no id and exchanges with itself.
+ * On a slab handle bc_upload/bc_download move the LOCAL rows (bc_local_rows), observables are global. */
+int bc_slab_unique_id(void* id128);
+int bc_create_slab(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device, uint64_t seed,
+                   int n_ranks, int rank, const void* nccl_id128);
+int bc_local_rows(const bc_engine* e, int* rows, int* first_global_row);
+
 /* ---- parameters -------------------------------------------------------------------- */
 
 /* Replaces: B = 1/atof(argv[5]); D = atof(argv[6]); J = atof(argv[7]) (main.cpp:321-323).

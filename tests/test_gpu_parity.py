@@ -193,3 +193,26 @@ def test_committed_golden_trajectories(bc):
         assert np.array_equal(e.download(m["replica"]), d[f"final_{i}"]), i
         assert np.array_equal(np.stack([obs["M"], obs["Q"], obs["B"]]), d[f"obs_{i}"]), i
         e.close()
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_single_rank_slab_equals_plain_engine(bc, oracle, boundary):
+    """The slab code path (ghost rows + halo exchange, here with itself) is bit-identical to the
+    wrap-around path and to the oracle; exercises bc_create_slab with n_ranks = 1 on one GPU."""
+    L, n, seed = 128, 10, 0x51AB
+    e = bc.Engine(L, boundary, 2, 0, seed, slab=(1, 0, None))
+    assert (e.rows, e.first_row) == (L, 0)
+    e.set_params(*TC)
+    e.init_random()
+    obs = e.sweep(n, 1)
+    got = e.download()
+    m = e.measure()
+    e.close()
+    tab = oracle.build_table(*TC)
+    for r in range(2):
+        ref = oracle.init_random(L, seed, r)
+        ro = oracle.sweep(ref, tab, seed, r, 0, n, 1, boundary)
+        assert np.array_equal(got[r], ref)
+        for f in ("M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ro[f]), f
+        assert (m[r]["M"], m[r]["Q"], m[r]["B"]) == oracle.observables(ref, boundary)
