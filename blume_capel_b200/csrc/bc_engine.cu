@@ -152,11 +152,11 @@ static void build_table(double T, double D, double J, uint32_t thr31[TABLE_ENTRI
                 }
                 const int i = 18 * c + 9 * f + S;
                 thr31[i] = thr;
-                // coarse 16-bit key compared against h16 = flip<<15 | u15: accept iff h16 < E, tie iff ==.
-                // E = flip<<15 + (thr31>>16), clamped to 65535 (the clamp only turns the single value
-                // h16 = 65535 of an always-accept entry into a tie, which the exact path then accepts).
-                uint32_t E = ((uint32_t)f << 15) + (thr >> 16);
-                if (E > 65535u) E = 65535u;
+                // coarse 15-bit threshold compared against u15 (bits 0..14 of the draw): accept iff u15 < E,
+                // tie iff u15 == E.  Clamped to 32767: the clamp only turns the single value u15 = 32767 of an
+                // always-accept entry into a tie, which the exact path then accepts.
+                uint32_t E = thr >> 16;
+                if (E > 32767u) E = 32767u;
                 tab16[i] = (uint16_t)E;
             }
 }
@@ -545,6 +545,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.strips = plan.strips;
     P.n_replicas = e->n_rep;
     P.open = e->boundary == BC_OPEN;
+    P.one = 1;
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {

@@ -73,15 +73,21 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #ifndef BC_NDP4A
 #define BC_NDP4A 4   // how many of the 4 per-word table-offset extractions run on the FMA-heavy pipe
 #endif
-#ifndef BC_SHL_PRMT
-#define BC_SHL_PRMT 1
+#ifndef BC_CMP_MODE
+#define BC_CMP_MODE 1    // 0: per-site IMAD difference (FMA-heavy pipe), 1: packed 2-site subtract (ALU pipe)
+#endif
+#ifndef BC_S4_HEAVY
+#define BC_S4_HEAVY 0    // neighbour-sum add on the FMA-heavy pipe
+#endif
+#ifndef BC_TIE_HEAVY
+#define BC_TIE_HEAVY 1   // tie-test decrement on the FMA-heavy pipe
 #endif
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
 
 template <int COL, bool SMALL, bool MEASURE>
-__global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
+__global__ void __launch_bounds__(FAST_THREADS, (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
@@ -135,6 +141,9 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
 
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
+    // A multiplier the compiler cannot see through (kernel parameter, always 1): imad(x, one, y) stays an
+    // IMAD on the FMA-heavy pipe instead of being folded into an ALU-pipe IADD3.
+    const uint32_t one = (uint32_t)P.one;
     const uint32_t total = (uint32_t)P.rows_arr * Wc;  // bytes of one replica's colour array (< 2^32)
 
     uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
@@ -156,7 +165,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
             // coarse randoms: one Philox call per 8 sites, 16 bits per site
             uint32_t q[4];
             philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
-            uint32_t idx[2], xr[2], msk[2], Ssave[2];
+            uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
             uint32_t tieacc = 0;
 #pragma unroll
             for (int w2 = 0; w2 < 2; ++w2) {
@@ -165,7 +174,11 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
                 const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
                 const uint32_t sh = par ? sr : sl;
+#if BC_S4_HEAVY
+                const uint32_t S4 = imad(u[wi] + d[wi], one, m[wi] + sh);  // bytes 0..8, no carries (main.cpp:97-103)
+#else
                 const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
+#endif
                 const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
                 const uint32_t c4 = o[wi];
                 // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
@@ -195,22 +208,31 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
                 const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
                 const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
-                // d = (h - E) * 65536 + (noise < 65536): sign(d) <=> h < E, top half zero <=> h == E.
-                // h - E lies in [-32768, 32767], so the 32-bit difference cannot wrap.
-#if BC_SHL_PRMT
-                const uint32_t ral = __byte_perm(ra, 0u, 0x1044), rbl = __byte_perm(rb, 0u, 0x1044);
+#if BC_CMP_MODE == 1
+                // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
+                // in [1, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
+                // tie.  E15 = min(thr31 >> 16, 32767).
+                const uint32_t Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
+                const uint32_t Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
 #else
-                const uint32_t ral = ra << 16, rbl = rb << 16;
+                // Per-site difference on the FMA-heavy pipe: d = ((u15 | 0x8000) - E15) << 16 (+ noise < 65536
+                // for the odd sites); bit 31 clear <=> u15 < E15 (accept), top half == 0x8000 <=> tie.
+                const uint32_t ga = ra | 0x80008000u, gb = rb | 0x80008000u;
+                const uint32_t d0 = imad(E0, 0xFFFF0000u, __byte_perm(ga, 0u, 0x1044));
+                const uint32_t d1 = imad(E1, 0xFFFF0000u, ga);
+                const uint32_t d2 = imad(E2, 0xFFFF0000u, __byte_perm(gb, 0u, 0x1044));
+                const uint32_t d3 = imad(E3, 0xFFFF0000u, gb);
+                const uint32_t Z01 = __byte_perm(d0, d1, 0x7632);  // [d0.hi16, d1.hi16]
+                const uint32_t Z23 = __byte_perm(d2, d3, 0x7632);
 #endif
-                const uint32_t d0 = imad(E0, 0xFFFF0000u, ral);
-                const uint32_t d1 = imad(E1, 0xFFFF0000u, ra);
-                const uint32_t d2 = imad(E2, 0xFFFF0000u, rbl);
-                const uint32_t d3 = imad(E3, 0xFFFF0000u, rb);
-                const uint32_t H01 = __byte_perm(d0, d1, 0x7632);  // [d0.hi16, d1.hi16]
-                const uint32_t H23 = __byte_perm(d2, d3, 0x7632);
-                msk[w2] = prmt(H01, H23, 0xFDB9u);                  // 0xFF where d < 0
-                tieacc |= imad(H01, 1u, 0xFFFEFFFFu) & ~H01;        // has-zero-halfword test (bits 15, 31)
-                tieacc |= imad(H23, 1u, 0xFFFEFFFFu) & ~H23;
+                msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
+#if BC_TIE_HEAVY
+                tieacc |= Z01 & ~imad(Z01, one, 0xFFFEFFFFu);       // lane == 0x8000 -> bit 15 / 31
+                tieacc |= Z23 & ~imad(Z23, one, 0xFFFEFFFFu);
+#else
+                tieacc |= Z01 & ~(Z01 - 0x00010001u);               // lane == 0x8000 -> bit 15 / 31
+                tieacc |= Z23 & ~(Z23 - 0x00010001u);
+#endif
                 idx[w2] = idx4;
                 Ssave[w2] = S4;
             }
@@ -226,10 +248,10 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                     const uint32_t rw = q[s >> 1];
                     const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
                     const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
-                    if (h == E) {
+                    if ((h & 0x7FFFu) == E) {
                         const uint32_t fw = f[s >> 1];
                         const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
-                        if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] |= (0xFFu << (8 * b));
+                        if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] &= ~(0xFFu << (8 * b));
                         ++n_ties;
                     }
                 }
@@ -237,7 +259,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 #pragma unroll
             for (int w2 = 0; w2 < 2; ++w2) {
                 const int wi = 2 * half + w2;
-                const uint32_t v = o[wi] ^ (xr[w2] & msk[w2]);
+                const uint32_t v = o[wi] ^ (xr[w2] & ~msk[w2]);
                 if (MEASURE) {
                     a_c = __dp4a(v, ONES, a_c);
                     a_c2 = __dp4a(v, v, a_c2);
@@ -376,8 +398,8 @@ sweep_generic_kernel(const __grid_constant__ SweepParams P, const int COL, const
             const uint32_t flip = h >> 15;
             const uint32_t e = 18u * c + 9u * flip + S;
             const uint32_t E = P.tab16[(size_t)rep * TABLE_ENTRIES + e];
-            bool accept = h < E;
-            if (h == E) {
+            bool accept = (h & 0x7FFFu) < E;
+            if ((h & 0x7FFFu) == E) {
                 philox4x32_10((uint32_t)(k >> 3), (uint32_t)y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, w);
                 const uint32_t f16 = (jj & 1) ? (w[jj >> 1] >> 16) : (w[jj >> 1] & 0xFFFFu);
                 accept = exact_accept(h, f16, P.tab31[(size_t)rep * TABLE_ENTRIES + e]);
