@@ -94,7 +94,14 @@ struct bc_engine {
     // pending (not yet fetched) measurements of the last bc_sweep
     int64_t pending_meas = 0;
     std::vector<int64_t> pending_sweeps;
+    // CUDA-graph replay of blocks of unmeasured sweeps (cuts per-launch CPU cost and launch gaps)
+    int64_t* d_clock = nullptr;      // device-resident sweep counter read by graph-captured kernels
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_rows = -1, graph_block = 0;  // plan signature the graph was captured for
+    unsigned graph_grid = 0;
     // options
+    int opt_use_graph = 1;
+    int opt_graph_block = 16;  // sweeps per graph launch
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_force_generic = 0;
     std::string err;
@@ -173,6 +180,8 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    cudaFree(e->d_clock);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31);
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
@@ -244,6 +253,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc ties", st);
+    if ((st = cudaMalloc(&e->d_clock, sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc clock", st);
     if ((st = cudaMemsetAsync(e->d_ties, 0, sizeof(unsigned long long), e->stream)) != cudaSuccess) return bail("memset", st);
     // all spins 0 (code 1), including the pad bytes of each compact row and the ghost rows
     if (launch_fill(e, e->d_c[0], e->colour_bytes, 1) != BC_OK || launch_fill(e, e->d_c[1], e->colour_bytes, 1) != BC_OK) {
@@ -523,7 +533,8 @@ static LaunchPlan make_plan(const bc_engine* e) {
     return p;
 }
 
-static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot) {
+static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
+                       const int64_t* t_ptr = nullptr) {
     SweepParams P;
     P.own = e->d_c[col];
     P.other = e->d_c[1 - col];
@@ -531,7 +542,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.tab31 = e->d_tab31;
     P.obs = e->d_obs;
     P.ties = e->d_ties;
-    P.t_ptr = nullptr;
+    P.t_ptr = t_ptr;  // graph replay: t = *t_ptr + t
     P.slot_ptr = nullptr;
     P.t = t;
     P.slot = slot;
@@ -584,6 +595,52 @@ static int fetch_pending(bc_engine* e, bc_obs* out) {
     return BC_OK;
 }
 
+// (Re)capture the graph of `block` unmeasured sweeps for the current plan: 2*block kernels reading the
+// device clock plus one node that advances it.
+static int ensure_graph(bc_engine* e, const LaunchPlan& plan, int block) {
+    if (e->graph_exec && e->graph_rows == plan.rows && e->graph_grid == plan.grid && e->graph_block == block) return BC_OK;
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    BC_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t launches_before = e->launches;
+    for (int s = 0; s < block; ++s) {
+        launch_half(e, plan, 0, false, s, 0, e->d_clock);
+        launch_half(e, plan, 1, false, s, 0, e->d_clock);
+    }
+    clock_add_kernel<<<1, 1, 0, e->stream>>>(e->d_clock, (int64_t)block);
+    e->launches = launches_before;  // capturing is not launching
+    cudaError_t st = cudaStreamEndCapture(e->stream, &graph);
+    if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(st));
+    st = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (st != cudaSuccess) { e->graph_exec = nullptr; return fail(e, BC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(st)); }
+    e->graph_rows = plan.rows; e->graph_grid = plan.grid; e->graph_block = block;
+    return BC_OK;
+}
+
+// n unmeasured sweeps starting at sweep index t0
+static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n) {
+    int64_t done = 0;
+    const int block = e->opt_graph_block;
+    if (e->opt_use_graph && !e->ghost && block > 0 && n >= block) {
+        int rc = ensure_graph(e, plan, block);
+        if (rc != BC_OK) return rc;
+        clock_set_kernel<<<1, 1, 0, e->stream>>>(e->d_clock, t0);
+        ++e->launches;
+        for (; done + block <= n; done += block) {
+            BC_CUDA(e, cudaGraphLaunch(e->graph_exec, e->stream));
+            e->launches += 2 * block + 1;
+        }
+    }
+    for (; done < n; ++done) {
+        launch_half(e, plan, 0, false, t0 + done, 0);
+        if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
+        launch_half(e, plan, 1, false, t0 + done, 0);
+        if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
+    }
+    return BC_OK;
+}
+
 extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out) {
     if (!e) return BC_ERR_ARG;
     if (n_sweeps < 0 || measure_every < 0) return fail(e, BC_ERR_ARG, "bc_sweep: negative count");
@@ -611,15 +668,23 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
     }
 
     BC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
-    int64_t slot = 0;
-    for (int64_t s = 0; s < n_sweeps; ++s) {
-        const int64_t t = e->t + s;
-        const bool measure = measure_every > 0 && ((t + 1) % measure_every == 0);
-        launch_half(e, plan, 0, measure, t, slot);
-        if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
-        launch_half(e, plan, 1, measure, t, slot);
-        if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
-        if (measure) ++slot;
+    // runs of unmeasured sweeps (graph replay where possible), each followed by one measured sweep
+    int64_t t = e->t;
+    const int64_t t_end = e->t + n_sweeps;
+    for (int64_t slot = 0; slot <= n_meas; ++slot) {
+        const int64_t t_meas = slot < n_meas ? e->pending_sweeps[(size_t)slot] : t_end;
+        if (t_meas > t) {
+            int rc = run_plain_sweeps(e, plan, t, t_meas - t);
+            if (rc != BC_OK) return rc;
+            t = t_meas;
+        }
+        if (slot < n_meas) {
+            launch_half(e, plan, 0, true, t, slot);
+            if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
+            launch_half(e, plan, 1, true, t, slot);
+            if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
+            ++t;
+        }
     }
     BC_CUDA(e, cudaEventRecord(e->ev1, e->stream));
     e->have_timing = true;
@@ -714,6 +779,8 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
+    if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }
     return fail(e, BC_ERR_ARG, "bc_set_option: unknown option " + n);
 }

@@ -508,6 +508,10 @@ __global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, 
     if ((x + y + g.y_glob0) & 1) c1[dst] = (uint8_t)code; else c0[dst] = (uint8_t)code;
 }
 
+// device-resident sweep counter used by CUDA-graph replay: kernels read t = *clock + offset
+__global__ void clock_set_kernel(int64_t* clock, int64_t value) { *clock = value; }
+__global__ void clock_add_kernel(int64_t* clock, int64_t delta) { *clock += delta; }
+
 __global__ void fill_kernel(uint8_t* __restrict__ p, size_t n, uint8_t v) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < n) p[gid] = v;

@@ -216,3 +216,23 @@ def test_single_rank_slab_equals_plain_engine(bc, oracle, boundary):
         for f in ("M", "Q", "B"):
             assert np.array_equal(obs[:, r][f], ro[f]), f
         assert (m[r]["M"], m[r]["Q"], m[r]["B"]) == oracle.observables(ref, boundary)
+
+
+@pytest.mark.parametrize("L,n_rep", [(64, 3), (128, 1), (24, 2)])
+def test_graph_replay_equals_direct_launches(bc, L, n_rep):
+    """Blocks of unmeasured sweeps are replayed from a CUDA graph with a device-resident sweep
+    counter; results must not depend on it (nor on how a run is split into bc_sweep calls)."""
+    outs = []
+    for use_graph, block, chunks in ((0, 16, (50,)), (1, 16, (50,)), (1, 4, (7, 20, 23)), (1, 16, (33, 17))):
+        e = bc.Engine(L, 0, n_rep, 0, 2718)
+        e.set_option("use_graph", use_graph)
+        e.set_option("graph_block", block)
+        e.set_params(*TC)
+        e.init_random()
+        obs = [e.sweep(c, 10) for c in chunks]
+        outs.append((e.download(), np.concatenate([o["B"] for o in obs])))
+        assert e.sweep_counter == 50
+        e.close()
+    for lat, b in outs[1:]:
+        assert np.array_equal(lat, outs[0][0])
+        assert np.array_equal(b, outs[0][1])
