@@ -484,13 +484,18 @@ extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
 // ---------------------------------------------------------------------------------------------
 typedef void (*fast_fn)(const SweepParams);
 
-static fast_fn pick_fast(int col, bool small, bool meas) {
-    static const fast_fn tbl[2][2][2] = {
-        {{sweep_fast_kernel<0, false, false>, sweep_fast_kernel<0, false, true>},
-         {sweep_fast_kernel<0, true, false>, sweep_fast_kernel<0, true, true>}},
-        {{sweep_fast_kernel<1, false, false>, sweep_fast_kernel<1, false, true>},
-         {sweep_fast_kernel<1, true, false>, sweep_fast_kernel<1, true, true>}}};
-    return tbl[col][small ? 1 : 0][meas ? 1 : 0];
+template <int COL, bool SMALL, bool MEAS>
+static fast_fn fast_open(bool open) {
+    return open ? (fast_fn)sweep_fast_kernel<COL, SMALL, MEAS, true> : (fast_fn)sweep_fast_kernel<COL, SMALL, MEAS, false>;
+}
+
+static fast_fn pick_fast(int col, bool small, bool meas, bool open) {
+    if (col == 0) {
+        if (!small) return meas ? fast_open<0, false, true>(open) : fast_open<0, false, false>(open);
+        return meas ? fast_open<0, true, true>(open) : fast_open<0, true, false>(open);
+    }
+    if (!small) return meas ? fast_open<1, false, true>(open) : fast_open<1, false, false>(open);
+    return meas ? fast_open<1, true, true>(open) : fast_open<1, true, false>(open);
 }
 
 struct LaunchPlan {
@@ -560,7 +565,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
-        fast_fn fn = pick_fast(col, plan.small, measure);
+        fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN);
         fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);

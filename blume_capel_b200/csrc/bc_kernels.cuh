@@ -47,6 +47,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// packed signed 16-bit minimum (VIMNMX.S16x2): 0x8000 is the most negative lane value
+__device__ __forceinline__ uint32_t min_s16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("min.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
 // Exact rule for a site whose coarse compare tied: u31 = (u15 << 16 | f16) < thr31.
 __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_t thr31) {
     return (((h16 & 0x7FFFu) << 16) | f16) < thr31;
@@ -86,7 +93,7 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #define BC_FAST_MIN_BLOCKS 6
 #endif
 
-template <int COL, bool SMALL, bool MEASURE>
+template <int COL, bool SMALL, bool MEASURE, bool OPEN>
 __global__ void __launch_bounds__(FAST_THREADS, (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
@@ -121,7 +128,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const uint32_t y0 = (uint32_t)P.row_first + strip * rows;  // array row; global row = y0 + y_rng_off
     const uint32_t yg0 = y0 + (uint32_t)P.y_rng_off;
     const uint32_t Wc = (uint32_t)P.Wc;
-    const bool open = P.open != 0;
+    constexpr bool open = OPEN;
 
     int64_t t = P.t;
     if (P.t_ptr) t += *P.t_ptr;
@@ -166,7 +173,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
             uint32_t q[4];
             philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
             uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
-            uint32_t tieacc = 0;
+            uint32_t tiemin = 0x7FFF7FFFu;
 #pragma unroll
             for (int w2 = 0; w2 < 2; ++w2) {
                 const int wi = 2 * half + w2;
@@ -183,26 +190,27 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 const uint32_t c4 = o[wi];
                 // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
                 const uint32_t fO = (prmt(ra, rb, 0xFDB9u) & 0x03030303u) ^ ONES;
-                // byte offsets into the u16 table (base biased by -18): 36c + 18(f+1) + 2S <= 124
-                const uint32_t idx4 = imad(S4, 2u, imad(fO, 18u, c4 * 36u));
+                // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
+                // u16 byte offset is applied by the IDP.4A that extracts each byte
+                const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
                 // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
                 const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
                 const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
                 xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
                 // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
 #if BC_NDP4A >= 4
-                const uint32_t a0 = __dp4a(idx4, 0x00000001u, 0u);
-                const uint32_t a3 = __dp4a(idx4, 0x01000000u, 0u);
+                const uint32_t a0 = __dp4a(idx4, 0x00000002u, 0u);
+                const uint32_t a3 = __dp4a(idx4, 0x02000000u, 0u);
 #else
-                const uint32_t a0 = idx4 & 0xFFu;
-                const uint32_t a3 = idx4 >> 24;
+                const uint32_t a0 = (idx4 & 0xFFu) * 2u;
+                const uint32_t a3 = (idx4 >> 24) * 2u;
 #endif
 #if BC_NDP4A >= 2
-                const uint32_t a1 = __dp4a(idx4, 0x00000100u, 0u);
-                const uint32_t a2 = __dp4a(idx4, 0x00010000u, 0u);
+                const uint32_t a1 = __dp4a(idx4, 0x00000200u, 0u);
+                const uint32_t a2 = __dp4a(idx4, 0x00020000u, 0u);
 #else
-                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441);
-                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442);
+                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441) * 2u;
+                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442) * 2u;
 #endif
                 const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tabm + a0);
                 const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
@@ -226,17 +234,12 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 const uint32_t Z23 = __byte_perm(d2, d3, 0x7632);
 #endif
                 msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
-#if BC_TIE_HEAVY
-                tieacc |= Z01 & ~imad(Z01, one, 0xFFFEFFFFu);       // lane == 0x8000 -> bit 15 / 31
-                tieacc |= Z23 & ~imad(Z23, one, 0xFFFEFFFFu);
-#else
-                tieacc |= Z01 & ~(Z01 - 0x00010001u);               // lane == 0x8000 -> bit 15 / 31
-                tieacc |= Z23 & ~(Z23 - 0x00010001u);
-#endif
+                // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
+                tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
                 idx[w2] = idx4;
                 Ssave[w2] = S4;
             }
-            if ((tieacc & 0x80008000u) != 0u) {
+            if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
                 // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
                 uint32_t f[4];
                 philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
@@ -244,7 +247,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int w2 = s >> 2, b = s & 3;
-                    const uint32_t a = (idx[w2] >> (8 * b)) & 0xFFu;
+                    const uint32_t a = ((idx[w2] >> (8 * b)) & 0xFFu) * 2u;
                     const uint32_t rw = q[s >> 1];
                     const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
                     const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
