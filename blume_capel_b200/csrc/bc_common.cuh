@@ -69,7 +69,6 @@ struct SweepParams {
     int cpr;                 // 16-byte chunks per compact row (fast kernel)
     int strips;              // row strips per replica (fast kernel), rows per strip = L / strips
     int n_replicas;
-    int one;                 // always 1 (opaque multiplier, see sweep_fast_kernel)
     int open;                // 1 = open boundary (off-lattice neighbours are spin 0)
     uint32_t key0, key1;     // Philox key of replica 0; replica r uses (key0, key1 ^ r)
 };

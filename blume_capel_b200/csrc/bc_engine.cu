@@ -102,6 +102,8 @@ struct bc_engine {
     // options
     int opt_use_graph = 1;
     int opt_graph_block = 16;  // sweeps per graph launch
+    int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
+    bool resident_attr_set[2] = {false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_force_generic = 0;
     std::string err;
@@ -561,7 +563,6 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.strips = plan.strips;
     P.n_replicas = e->n_rep;
     P.open = e->boundary == BC_OPEN;
-    P.one = 1;
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
@@ -646,6 +647,52 @@ static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, in
     return BC_OK;
 }
 
+// ---- resident (shared-memory) path for small lattices -----------------------------------------------
+struct ResidentPlan {
+    bool ok = false;
+    int T = 0, reps_per_cta = 0;
+    size_t smem = 0;
+    unsigned grid = 0;
+};
+
+static ResidentPlan resident_plan(const bc_engine* e) {
+    ResidentPlan r;
+    const int L = e->L;
+    if (L % 32 || e->ghost || e->opt_resident == 0 || e->opt_force_generic) return r;
+    const int items = L * (L / 32);
+    r.T = items <= 32 ? 32 : (items <= 128 ? 128 : 256);
+    r.reps_per_cta = r.T < 128 ? 128 / r.T : 1;
+    r.smem = (size_t)r.reps_per_cta * (2 * (size_t)L * e->Wc + 128) + (size_t)r.reps_per_cta * 32;
+    if (r.smem > 227 * 1024) return r;
+    // auto: always for the reference's sizes (L <= 128); for larger resident sizes only when there are
+    // enough replicas to keep every SM busy with one CTA per replica
+    if (e->opt_resident < 0 && L > 128 && e->n_rep < 64) return r;
+    r.grid = (unsigned)((e->n_rep + r.reps_per_cta - 1) / r.reps_per_cta);
+    r.ok = true;
+    return r;
+}
+
+static int launch_resident(bc_engine* e, const ResidentPlan& rp, int64_t t0, int64_t n, int64_t measure_every) {
+    const bool open = e->boundary == BC_OPEN;
+    auto fn = open ? sweep_resident_kernel<true> : sweep_resident_kernel<false>;
+    if (!e->resident_attr_set[open]) {
+        BC_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        e->resident_attr_set[open] = true;
+    }
+    ResidentParams P;
+    P.c0 = e->d_c[0]; P.c1 = e->d_c[1];
+    P.tab16 = e->d_tab16; P.tab31 = e->d_tab31;
+    P.obs = e->d_obs; P.ties = e->d_ties;
+    P.t0 = t0; P.n_sweeps = n; P.measure_every = measure_every;
+    P.L = e->L; P.Wc = e->Wc; P.cpr = e->L / 32; P.n_replicas = e->n_rep;
+    P.threads_per_rep = rp.T; P.reps_per_cta = rp.reps_per_cta;
+    P.key0 = (uint32_t)e->seed; P.key1 = (uint32_t)(e->seed >> 32);
+    fn<<<rp.grid, rp.T * rp.reps_per_cta, rp.smem, e->stream>>>(P);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
 extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out) {
     if (!e) return BC_ERR_ARG;
     if (n_sweeps < 0 || measure_every < 0) return fail(e, BC_ERR_ARG, "bc_sweep: negative count");
@@ -673,10 +720,16 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
     }
 
     BC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
+    const ResidentPlan rp = resident_plan(e);
+    if (rp.ok && n_sweeps > 0) {
+        // whole call in one launch: lattices stay in shared memory, observables written per measured sweep
+        int rc = launch_resident(e, rp, e->t, n_sweeps, measure_every);
+        if (rc != BC_OK) return rc;
+    }
     // runs of unmeasured sweeps (graph replay where possible), each followed by one measured sweep
-    int64_t t = e->t;
+    int64_t t = rp.ok ? e->t + n_sweeps : e->t;
     const int64_t t_end = e->t + n_sweeps;
-    for (int64_t slot = 0; slot <= n_meas; ++slot) {
+    for (int64_t slot = 0; slot <= n_meas && !rp.ok; ++slot) {
         const int64_t t_meas = slot < n_meas ? e->pending_sweeps[(size_t)slot] : t_end;
         if (t_meas > t) {
             int rc = run_plain_sweeps(e, plan, t, t_meas - t);
@@ -784,6 +837,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
     if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }
@@ -803,6 +857,14 @@ extern "C" int bc_tie_count(bc_engine* e, int64_t* ties) {
 extern "C" int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, int* grid, int* block) {
     if (!e) return BC_ERR_ARG;
     const LaunchPlan p = make_plan(e);
+    if (resident_plan(e).ok) {  // 2 = shared-memory-resident kernel
+        const ResidentPlan r = resident_plan(e);
+        if (fast) *fast = 2;
+        if (rows_per_thread) *rows_per_thread = 0;
+        if (grid) *grid = (int)r.grid;
+        if (block) *block = r.T * r.reps_per_cta;
+        return BC_OK;
+    }
     if (fast) *fast = p.fast;
     if (rows_per_thread) *rows_per_thread = p.rows;
     if (grid) *grid = (int)p.grid;

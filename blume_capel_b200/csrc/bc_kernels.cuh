@@ -60,6 +60,118 @@ __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_
 }
 
 // ------------------------------------------------------------------------------------------
+// The per-row update shared by the streaming kernel and the resident (small-lattice) kernel:
+// 16 same-colour sites of row y, chunk j.  Inputs: the other colour's rows y-1, y, y+1 (upv, midv,
+// dnv), the word holding the horizontal neighbour that lives in the adjacent chunk (`side`), the
+// own chunk; par = (y+COL)&1; tabm = shared-memory coarse table biased by -18 bytes; t31_rep = the
+// replica's exact thresholds.  Returns the new chunk; accumulates the raw observables.
+// ------------------------------------------------------------------------------------------
+struct RowCtx {
+    uint32_t j, ctr2, ctr3, k0, k1;
+    int64_t t;
+    const char* tabm;
+    const uint32_t* t31_rep;
+};
+
+template <int COL, bool MEASURE>
+__device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t y, const int par, const uint4& upv,
+                                                const uint4& midv, const uint4& dnv, const uint32_t side,
+                                                const uint4& ownv, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
+                                                uint32_t& a_S, uint32_t& n_ties) {
+    const uint32_t j = C.j, ctr2 = C.ctr2, ctr3 = C.ctr3, k0 = C.k0, k1 = C.k1;
+    const int64_t t = C.t;
+    const char* tabm = C.tabm;
+    const uint32_t* t31_rep = C.t31_rep;
+    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
+    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
+    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
+    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
+    uint32_t nw[4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        // coarse randoms: one Philox call per 8 sites, 16 bits per site
+        uint32_t q[4];
+        philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
+        uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
+        uint32_t tiemin = 0x7FFF7FFFu;
+#pragma unroll
+        for (int w2 = 0; w2 < 2; ++w2) {
+            const int wi = 2 * half + w2;
+            // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
+            const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
+            const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
+            const uint32_t sh = par ? sr : sl;
+            const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
+            const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
+            const uint32_t c4 = o[wi];
+            // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
+            const uint32_t fO = (prmt(ra, rb, 0xFDB9u) & 0x03030303u) ^ ONES;
+            // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
+            // u16 byte offset is applied by the IDP.4A that extracts each byte
+            const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
+            // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
+            const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
+            const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
+            xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
+            // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
+            const uint32_t a0 = __dp4a(idx4, 0x00000002u, 0u);
+            const uint32_t a3 = __dp4a(idx4, 0x02000000u, 0u);
+            const uint32_t a1 = __dp4a(idx4, 0x00000200u, 0u);
+            const uint32_t a2 = __dp4a(idx4, 0x00020000u, 0u);
+            const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tabm + a0);
+            const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
+            const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
+            const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
+            // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
+            // in [1, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
+            // tie.  E15 = min(thr31 >> 16, 32767).
+            const uint32_t Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
+            const uint32_t Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
+            msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
+            // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
+            tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
+            idx[w2] = idx4;
+            Ssave[w2] = S4;
+        }
+        if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
+            // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
+            uint32_t f[4];
+            philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
+            const uint32_t* t31 = t31_rep;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int w2 = s >> 2, b = s & 3;
+                const uint32_t a = ((idx[w2] >> (8 * b)) & 0xFFu) * 2u;
+                const uint32_t rw = q[s >> 1];
+                const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
+                const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
+                if ((h & 0x7FFFu) == E) {
+                    const uint32_t fw = f[s >> 1];
+                    const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
+                    if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] &= ~(0xFFu << (8 * b));
+                    ++n_ties;
+                }
+            }
+        }
+#pragma unroll
+        for (int w2 = 0; w2 < 2; ++w2) {
+            const int wi = 2 * half + w2;
+            const uint32_t v = o[wi] ^ (xr[w2] & ~msk[w2]);
+            if (MEASURE) {
+                a_c = __dp4a(v, ONES, a_c);
+                a_c2 = __dp4a(v, v, a_c2);
+                if (COL == 1) {
+                    a_cS = __dp4a(v, Ssave[w2], a_cS);
+                    a_S = __dp4a(Ssave[w2], ONES, a_S);
+                }
+            }
+            nw[wi] = v;
+        }
+    }
+    return make_uint4(nw[0], nw[1], nw[2], nw[3]);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fast kernel: L % 32 == 0.  One thread = one 16-byte chunk column j, marching down the
 // L/strips rows of its strip with the three rows of the other colour held in registers and the
 // loads of the NEXT row (other-colour row y+2, side word, own chunk) issued before the current
@@ -71,24 +183,14 @@ __device__ __forceinline__ bool exact_accept(uint32_t h16, uint32_t f16, uint32_
 //   SMALL = false: rows per strip is even (row parity static per unrolled row) and
 //                  items/replica is a multiple of 128 (one replica, one table per CTA).
 //   SMALL = true : any strip height, up to 4 replicas per CTA (small lattices).
-// Per-site compare: d = r - E*65536 on the FMA pipe (IMAD), accept masks
-// from the sign bytes with PRMT sign replication, ties (coarse draw == coarse threshold) from a
-// SWAR has-zero-halfword test; the ALU pipe (LOP3/PRMT/SHF/ISETP) is the scarce resource.
+// Per-site compare: table offsets extracted with IDP.4A (FMA-heavy pipe), LDS.U16
+// from a 27-word conflict-free table, two sites per packed 16-bit subtract, reject masks by PRMT sign
+// replication, ties (coarse draw == coarse threshold) by a packed signed minimum (VIMNMX3.S16x2).  The
+// two half-rate integer pipes (ALU: LOP3/PRMT/SHF, FMA-heavy: IMAD/IDP, quarter-rate IMAD.WIDE) bound
+// this kernel, not HBM; the instruction mix is balanced between them (tools/microbench/pipes.cu).
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
-#ifndef BC_NDP4A
-#define BC_NDP4A 4   // how many of the 4 per-word table-offset extractions run on the FMA-heavy pipe
-#endif
-#ifndef BC_CMP_MODE
-#define BC_CMP_MODE 1    // 0: per-site IMAD difference (FMA-heavy pipe), 1: packed 2-site subtract (ALU pipe)
-#endif
-#ifndef BC_S4_HEAVY
-#define BC_S4_HEAVY 0    // neighbour-sum add on the FMA-heavy pipe
-#endif
-#ifndef BC_TIE_HEAVY
-#define BC_TIE_HEAVY 1   // tie-test decrement on the FMA-heavy pipe
-#endif
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
@@ -148,9 +250,6 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
 
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
-    // A multiplier the compiler cannot see through (kernel parameter, always 1): imad(x, one, y) stays an
-    // IMAD on the FMA-heavy pipe instead of being folded into an ALU-pipe IADD3.
-    const uint32_t one = (uint32_t)P.one;
     const uint32_t total = (uint32_t)P.rows_arr * Wc;  // bytes of one replica's colour array (< 2^32)
 
     uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
@@ -158,123 +257,13 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     // The 18*(f+1) term of the table offset is computed with f+1 instead of f: bias the base by -18.
     const char* tabm = tab - 18;
 
-    // Update the 16 sites of row y (byte offset `off`) given the other colour's rows y-1, y, y+1
-    // (upv, midv, dnv), the side word and the own chunk.  PAR = (y+COL)&1.
+    RowCtx ctx;
+    ctx.j = j; ctx.ctr2 = ctr2; ctx.ctr3 = ctr3; ctx.k0 = k0; ctx.k1 = k1; ctx.t = t; ctx.tabm = tabm;
+    ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
-        const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
-        const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
-        const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
-        const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-        uint32_t nw[4];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            // coarse randoms: one Philox call per 8 sites, 16 bits per site
-            uint32_t q[4];
-            philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
-            uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
-            uint32_t tiemin = 0x7FFF7FFFu;
-#pragma unroll
-            for (int w2 = 0; w2 < 2; ++w2) {
-                const int wi = 2 * half + w2;
-                // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
-                const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
-                const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
-                const uint32_t sh = par ? sr : sl;
-#if BC_S4_HEAVY
-                const uint32_t S4 = imad(u[wi] + d[wi], one, m[wi] + sh);  // bytes 0..8, no carries (main.cpp:97-103)
-#else
-                const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
-#endif
-                const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
-                const uint32_t c4 = o[wi];
-                // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
-                const uint32_t fO = (prmt(ra, rb, 0xFDB9u) & 0x03030303u) ^ ONES;
-                // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
-                // u16 byte offset is applied by the IDP.4A that extracts each byte
-                const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
-                // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
-                const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
-                const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
-                xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
-                // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
-#if BC_NDP4A >= 4
-                const uint32_t a0 = __dp4a(idx4, 0x00000002u, 0u);
-                const uint32_t a3 = __dp4a(idx4, 0x02000000u, 0u);
-#else
-                const uint32_t a0 = (idx4 & 0xFFu) * 2u;
-                const uint32_t a3 = (idx4 >> 24) * 2u;
-#endif
-#if BC_NDP4A >= 2
-                const uint32_t a1 = __dp4a(idx4, 0x00000200u, 0u);
-                const uint32_t a2 = __dp4a(idx4, 0x00020000u, 0u);
-#else
-                const uint32_t a1 = __byte_perm(idx4, 0u, 0x4441) * 2u;
-                const uint32_t a2 = __byte_perm(idx4, 0u, 0x4442) * 2u;
-#endif
-                const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tabm + a0);
-                const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
-                const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
-                const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
-#if BC_CMP_MODE == 1
-                // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
-                // in [1, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
-                // tie.  E15 = min(thr31 >> 16, 32767).
-                const uint32_t Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
-                const uint32_t Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
-#else
-                // Per-site difference on the FMA-heavy pipe: d = ((u15 | 0x8000) - E15) << 16 (+ noise < 65536
-                // for the odd sites); bit 31 clear <=> u15 < E15 (accept), top half == 0x8000 <=> tie.
-                const uint32_t ga = ra | 0x80008000u, gb = rb | 0x80008000u;
-                const uint32_t d0 = imad(E0, 0xFFFF0000u, __byte_perm(ga, 0u, 0x1044));
-                const uint32_t d1 = imad(E1, 0xFFFF0000u, ga);
-                const uint32_t d2 = imad(E2, 0xFFFF0000u, __byte_perm(gb, 0u, 0x1044));
-                const uint32_t d3 = imad(E3, 0xFFFF0000u, gb);
-                const uint32_t Z01 = __byte_perm(d0, d1, 0x7632);  // [d0.hi16, d1.hi16]
-                const uint32_t Z23 = __byte_perm(d2, d3, 0x7632);
-#endif
-                msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
-                // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
-                tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
-                idx[w2] = idx4;
-                Ssave[w2] = S4;
-            }
-            if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
-                // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
-                uint32_t f[4];
-                philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
-                const uint32_t* t31 = P.tab31 + (size_t)rep * TABLE_ENTRIES;
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int w2 = s >> 2, b = s & 3;
-                    const uint32_t a = ((idx[w2] >> (8 * b)) & 0xFFu) * 2u;
-                    const uint32_t rw = q[s >> 1];
-                    const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
-                    const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
-                    if ((h & 0x7FFFu) == E) {
-                        const uint32_t fw = f[s >> 1];
-                        const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
-                        if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] &= ~(0xFFu << (8 * b));
-                        ++n_ties;
-                    }
-                }
-            }
-#pragma unroll
-            for (int w2 = 0; w2 < 2; ++w2) {
-                const int wi = 2 * half + w2;
-                const uint32_t v = o[wi] ^ (xr[w2] & ~msk[w2]);
-                if (MEASURE) {
-                    a_c = __dp4a(v, ONES, a_c);
-                    a_c2 = __dp4a(v, v, a_c2);
-                    if (COL == 1) {
-                        a_cS = __dp4a(v, Ssave[w2], a_cS);
-                        a_S = __dp4a(Ssave[w2], ONES, a_S);
-                    }
-                }
-                nw[wi] = v;
-            }
-        }
-        *reinterpret_cast<uint4*>(own_col + off) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+        *reinterpret_cast<uint4*>(own_col + off) =
+            update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
     };
 
     // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour
@@ -345,6 +334,144 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
                 atomicAdd(dst + 4, (unsigned long long)s_cS);
                 atomicAdd(dst + 5, (unsigned long long)s_S);
             }
+        }
+    }
+    if (n_ties && P.ties) atomicAdd(P.ties, (unsigned long long)n_ties);
+}
+
+// ------------------------------------------------------------------------------------------
+// Resident kernel: lattices small enough (L % 32 == 0, L <= 448) to stay in shared memory for a whole
+// launch.  One CTA holds both colour arrays of its replica(s) and runs ALL n_sweeps sweeps of the call
+// with __syncthreads() between half-sweeps -- no launch per half-sweep, no HBM traffic inside the loop.
+// This is what the reference's own sizes (L = 8 ... 128, gen_files.py:11) and finite-size-scaling ladders
+// need: at L = 64 a launch-per-half-sweep engine is launch-bound (~3 us per 2048 updates).
+// Same spec, same update_chunk16 -> bit-identical to the streaming kernel and the oracle.
+//   threads_per_rep T (32 / 128 / 256) threads share one replica; reps_per_cta = 128 / T for T < 128.
+// ------------------------------------------------------------------------------------------
+struct ResidentParams {
+    uint8_t* c0;             // colour-0 array [replica][L][Wc]
+    uint8_t* c1;             // colour-1 array
+    const uint16_t* tab16;   // [replica][54]
+    const uint32_t* tab31;   // [replica][54]
+    unsigned long long* obs; // raw accumulators [slot][replica][OBS_RAW]
+    unsigned long long* ties;
+    int64_t t0;              // first sweep index
+    int64_t n_sweeps;
+    int64_t measure_every;   // 0 = never
+    int L, Wc, cpr, n_replicas, threads_per_rep, reps_per_cta;
+    uint32_t key0, key1;
+};
+
+template <bool OPEN>
+__global__ void __launch_bounds__(256)
+sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const int L = P.L, Wc = P.Wc, cpr = P.cpr, T = P.threads_per_rep;
+    const uint32_t arr = (uint32_t)L * (uint32_t)Wc;            // bytes of one colour array
+    const uint32_t rep_stride = 2u * arr + 128u;                 // two colours + coarse table (27 words, padded)
+    const int lr = threadIdx.x / T, ltid = threadIdx.x - lr * T;
+    const int rep = blockIdx.x * P.reps_per_cta + lr;
+    const bool live = rep < P.n_replicas;
+    uint8_t* s_c0 = s_dyn + (size_t)lr * rep_stride;
+    uint8_t* s_c1 = s_c0 + arr;
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_c1 + arr);
+    uint32_t* s_red = reinterpret_cast<uint32_t*>(s_dyn + (size_t)P.reps_per_cta * rep_stride) + lr * 8;
+
+    // ---- load: global -> shared (16-byte vectors), table, zero the reduction scratch
+    if (live) {
+        const uint4* g0 = reinterpret_cast<const uint4*>(P.c0 + (size_t)rep * arr);
+        const uint4* g1 = reinterpret_cast<const uint4*>(P.c1 + (size_t)rep * arr);
+        for (uint32_t i = ltid; i < arr / 16; i += T) {
+            reinterpret_cast<uint4*>(s_c0)[i] = g0[i];
+            reinterpret_cast<uint4*>(s_c1)[i] = g1[i];
+        }
+        for (int i = ltid; i < TAB16_WORDS; i += T)
+            s_tab[i] = reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)rep * TAB16_WORDS + i];
+        if (ltid < 8) s_red[ltid] = 0u;
+    }
+    __syncthreads();
+
+    RowCtx ctx;
+    ctx.k0 = P.key0; ctx.k1 = P.key1 ^ (uint32_t)rep;
+    ctx.tabm = reinterpret_cast<const char*>(s_tab) - 18;
+    ctx.t31_rep = P.tab31 + (size_t)(live ? rep : 0) * TABLE_ENTRIES;
+    const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
+    const int items = L * cpr;
+    uint32_t n_ties = 0;
+    int64_t slot = 0;
+
+    // one half-sweep of colour COL over this replica's rows
+    auto half_sweep = [&](auto colc, auto measc, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S) {
+        constexpr int COL = decltype(colc)::value;
+        constexpr bool MEAS = decltype(measc)::value;
+        uint8_t* own = COL ? s_c1 : s_c0;
+        const uint8_t* oth = COL ? s_c0 : s_c1;
+        for (int item = ltid; item < items; item += T) {
+            const int y = item / cpr, j = item - y * cpr;
+            const int par = (y + COL) & 1;
+            const uint32_t rowo = (uint32_t)y * Wc, co = (uint32_t)j * 16;
+            uint4 upv, dnv;
+            if (y == 0) upv = OPEN ? ones4 : *reinterpret_cast<const uint4*>(oth + (arr - Wc) + co);
+            else upv = *reinterpret_cast<const uint4*>(oth + rowo - Wc + co);
+            if (y == L - 1) dnv = OPEN ? ones4 : *reinterpret_cast<const uint4*>(oth + co);
+            else dnv = *reinterpret_cast<const uint4*>(oth + rowo + Wc + co);
+            const uint4 midv = *reinterpret_cast<const uint4*>(oth + rowo + co);
+            uint32_t side;
+            if (par) {
+                if (j + 1 == cpr) side = OPEN ? 0x00000001u : *reinterpret_cast<const uint32_t*>(oth + rowo);
+                else side = *reinterpret_cast<const uint32_t*>(oth + rowo + co + 16);
+            } else {
+                if (j == 0) side = OPEN ? 0x01000000u : *reinterpret_cast<const uint32_t*>(oth + rowo + (cpr - 1) * 16 + 12);
+                else side = *reinterpret_cast<const uint32_t*>(oth + rowo + co - 4);
+            }
+            const uint4 ownv = *reinterpret_cast<const uint4*>(own + rowo + co);
+            ctx.j = (uint32_t)j;
+            *reinterpret_cast<uint4*>(own + rowo + co) =
+                update_chunk16<COL, MEAS>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+        }
+    };
+
+    for (int64_t s = 0; s < P.n_sweeps; ++s) {
+        const int64_t t = P.t0 + s;
+        const bool measure = P.measure_every > 0 && ((t + 1) % P.measure_every) == 0;
+        ctx.t = t;
+        ctx.ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+        ctx.ctr3 = ctr3_of(t, STREAM_COARSE, 0);
+        if (live) {
+            if (measure) half_sweep(std::integral_constant<int, 0>{}, std::true_type{}, a0, a1, a4, a5);
+            else half_sweep(std::integral_constant<int, 0>{}, std::false_type{}, a0, a1, a4, a5);
+        }
+        __syncthreads();
+        ctx.ctr3 = ctr3_of(t, STREAM_COARSE, 1);
+        if (live) {
+            if (measure) half_sweep(std::integral_constant<int, 1>{}, std::true_type{}, a2, a3, a4, a5);
+            else half_sweep(std::integral_constant<int, 1>{}, std::false_type{}, a2, a3, a4, a5);
+        }
+        if (measure) {
+            // block reduction of the raw sums of this replica, then one plain store per quantity
+            if (live) {
+                const uint32_t v[OBS_RAW] = {warp_sum(a0), warp_sum(a1), warp_sum(a2), warp_sum(a3), warp_sum(a4), warp_sum(a5)};
+                if ((threadIdx.x & 31) == 0)
+                    for (int k = 0; k < OBS_RAW; ++k) atomicAdd(&s_red[k], v[k]);
+            }
+            __syncthreads();
+            if (live && ltid < OBS_RAW) {
+                P.obs[((size_t)slot * P.n_replicas + rep) * OBS_RAW + ltid] = (unsigned long long)s_red[ltid];
+                s_red[ltid] = 0u;
+            }
+            ++slot;
+        }
+        __syncthreads();
+    }
+
+    // ---- store back
+    if (live) {
+        uint4* g0 = reinterpret_cast<uint4*>(P.c0 + (size_t)rep * arr);
+        uint4* g1 = reinterpret_cast<uint4*>(P.c1 + (size_t)rep * arr);
+        for (uint32_t i = ltid; i < arr / 16; i += T) {
+            g0[i] = reinterpret_cast<const uint4*>(s_c0)[i];
+            g1[i] = reinterpret_cast<const uint4*>(s_c1)[i];
         }
     }
     if (n_ties && P.ties) atomicAdd(P.ties, (unsigned long long)n_ties);

@@ -63,8 +63,8 @@ def test_generic_kernel_open(bc, oracle, L):
 def test_fast_kernel(bc, oracle, L, rows, boundary):
     n_rep = 3 if L <= 128 else 1
     got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, 12, 0xFA57 + L + rows,
-                                            opts=(("rows_per_thread", rows),))
-    assert plan["fast"]
+                                            opts=(("rows_per_thread", rows), ("resident", 0)))
+    assert plan["fast"] and not plan["resident"]
     if rows:
         assert plan["rows_per_thread"] == rows
     assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
@@ -236,3 +236,37 @@ def test_graph_replay_equals_direct_launches(bc, L, n_rep):
     for lat, b in outs[1:]:
         assert np.array_equal(lat, outs[0][0])
         assert np.array_equal(b, outs[0][1])
+
+
+@pytest.mark.parametrize("L,n_rep,force", [(32, 1, -1), (32, 7, -1), (64, 1, -1), (64, 3, -1), (96, 2, -1), (128, 2, -1),
+                                           (256, 2, 1), (448, 1, 1)])
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_resident_kernel(bc, oracle, L, n_rep, force, boundary):
+    """Small lattices stay in shared memory for the whole call (one launch for all sweeps)."""
+    n = 9 if L <= 128 else 4
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, n, 0x2E51 + L, measure_every=2,
+                                            opts=(("resident", force),))
+    assert plan["resident"], plan
+    assert np.array_equal(got, ref)
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
+
+
+def test_resident_is_one_launch_and_equals_streaming(bc):
+    res = []
+    for resident in (1, 0):
+        e = bc.Engine(64, 0, 5, 0, 99)
+        e.set_option("resident", resident)
+        e.set_params(*TC)
+        e.init_random()
+        e.sync()
+        l0 = e.launch_count
+        a = e.sweep(40, 4)
+        b = e.sweep(17, 4)
+        n_launch = e.launch_count - l0
+        res.append((e.download(), np.concatenate([a["B"], b["B"]]), n_launch, e.tie_count))
+        e.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][2] == 2 and res[1][2] > 100
+    assert res[0][3] == res[1][3]

@@ -45,8 +45,11 @@ if __name__ == "__main__":
         cases.append((4096, 1, 0, 200, 1))
         cases.append((1024, 64, 0, 50, 0))
         cases.append((256, 512, 0, 50, 0))
-        cases.append((64, 4096, 0, 50, 0))
-        cases.append((32, 8192, 0, 50, 0))
+        for L, nr in ((64, 4096), (32, 8192), (128, 1024), (64, 100), (64, 1), (128, 100), (256, 256)):
+            cases.append((L, nr, 0, 2000 if nr <= 100 else 50, 0, 0, (("resident", 0),)))
+            cases.append((L, nr, 0, 2000 if nr <= 100 else 50, 0, 0, (("resident", 1),)))
+        cases.append((64, 1, 0, 20000, 1, 0, (("resident", 1),)))
+        cases.append((64, 100, 0, 2000, 1, 0, (("resident", 1),)))
     for c in cases:
         ups, ms, plan = run(*c)
         print(json.dumps({"lib": os.path.basename(tag), "L": c[0], "n_rep": c[1], "rows": c[2], "sweeps": c[3],
