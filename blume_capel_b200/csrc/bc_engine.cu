@@ -660,13 +660,14 @@ static ResidentPlan resident_plan(const bc_engine* e) {
     const int L = e->L;
     if (L % 32 || e->ghost || e->opt_resident == 0 || e->opt_force_generic) return r;
     const int items = L * (L / 32);
-    r.T = items <= 32 ? 32 : (items <= 128 ? 128 : 256);
+    // 512 threads per replica shorten a half-sweep when there are too few replicas to fill the chip
+    r.T = items <= 32 ? 32 : (items <= 128 ? 128 : ((items <= 256 || e->n_rep >= 2 * 148) ? 256 : 512));
     r.reps_per_cta = r.T < 128 ? 128 / r.T : 1;
     r.smem = (size_t)r.reps_per_cta * (2 * (size_t)L * e->Wc + 128) + (size_t)r.reps_per_cta * 32;
     if (r.smem > 227 * 1024) return r;
     // auto: always for the reference's sizes (L <= 128); for larger resident sizes only when there are
     // enough replicas to keep every SM busy with one CTA per replica
-    if (e->opt_resident < 0 && L > 128 && e->n_rep < 64) return r;
+    if (e->opt_resident < 0 && L > 128 && e->n_rep < 2 * 148) return r;
     r.grid = (unsigned)((e->n_rep + r.reps_per_cta - 1) / r.reps_per_cta);
     r.ok = true;
     return r;

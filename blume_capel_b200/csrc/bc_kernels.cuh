@@ -346,7 +346,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 // This is what the reference's own sizes (L = 8 ... 128, gen_files.py:11) and finite-size-scaling ladders
 // need: at L = 64 a launch-per-half-sweep engine is launch-bound (~3 us per 2048 updates).
 // Same spec, same update_chunk16 -> bit-identical to the streaming kernel and the oracle.
-//   threads_per_rep T (32 / 128 / 256) threads share one replica; reps_per_cta = 128 / T for T < 128.
+//   threads_per_rep T (32 / 128 / 256 / 512) threads share one replica; reps_per_cta = 128 / T for T < 128.
 // ------------------------------------------------------------------------------------------
 struct ResidentParams {
     uint8_t* c0;             // colour-0 array [replica][L][Wc]
@@ -363,7 +363,7 @@ struct ResidentParams {
 };
 
 template <bool OPEN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int L = P.L, Wc = P.Wc, cpr = P.cpr, T = P.threads_per_rep;
