@@ -195,6 +195,19 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     last_obs = eng.read_obs(n_meas)
 
+    # ---- for the record: ONE L=4096 lattice (16 MiB, L2 resident, launch-bound), not the headline
+    single = None
+    if rank == 0:
+        e1 = bc.Engine(L, bc.PERIODIC, 1, local_rank, SEED)
+        e1.set_params(T, D, J)
+        e1.init_random()
+        e1.sweep(64)
+        e1.sync()
+        e1.timer_start()
+        e1.sweep(1024)
+        single = float(L) * L * 1024 / (e1.timer_stop() * 1e6)
+        e1.close()
+
     # ---- end to end through the C ABI from pinned host buffers
     host = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True)
     host_np = host.numpy()
@@ -258,6 +271,8 @@ def run_ours(args, rank, world, local_rank):
                          "avg_launch_ms": avg_launch_ms, "sweep_launches": sweep_launches},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "single_lattice": {"workload": f"one L={L} lattice (16 MiB, L2-resident; CUDA-graph replay + PDL)",
+                               "updates_per_ns": single},
             "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
                       "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": eng.tie_count},
         }

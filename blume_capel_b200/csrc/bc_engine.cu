@@ -102,6 +102,7 @@ struct bc_engine {
     // options
     int opt_use_graph = 1;
     int opt_graph_block = 16;  // sweeps per graph launch
+    int opt_pdl = 1;  // programmatic dependent launch between consecutive half-sweeps
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
     bool resident_attr_set[2] = {false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
@@ -522,7 +523,7 @@ static LaunchPlan make_plan(const bc_engine* e) {
         if (e->opt_rows > 0 && rows_valid(Ly, p.cpr, e->opt_rows)) {
             R = e->opt_rows;
         } else {
-            const long long want = 148LL * 1536;  // enough threads to fill the chip
+            const long long want = 148LL * 768;  // enough threads to fill the chip (6-7 CTAs of 128 per SM)
             const int cand[5] = {32, 16, 8, 4, 2};
             for (int i = 0; i < 5 && !R; ++i)
                 if (rows_valid(Ly, p.cpr, cand[i]) && (long long)e->n_rep * (Ly / cand[i]) * p.cpr >= want) R = cand[i];
@@ -567,7 +568,17 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
         fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN);
-        fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
+        if (e->opt_pdl) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, fn, P);
+        } else {
+            fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
+        }
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
         else sweep_generic_kernel<false><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
@@ -838,6 +849,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
     if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }

@@ -203,6 +203,11 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ uint4 s_own[2][FAST_THREADS];     // thread-private own chunks (current / next row)
     __shared__ uint32_t s_side[2][FAST_THREADS];  // thread-private side words
 
+    // Programmatic dependent launch: let the next half-sweep's grid be scheduled as soon as SMs free up; its
+    // CTAs run their prologue (table staging, index arithmetic) and then block in griddepcontrol.wait until
+    // this grid has completed and its writes are visible.  Both are no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     const uint32_t ipr = (uint32_t)(P.strips * P.cpr);  // items per replica
     const unsigned long long gid0 = (unsigned long long)blockIdx.x * FAST_THREADS;
     const uint32_t rep0 = (uint32_t)(gid0 / ipr);
@@ -286,6 +291,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         }
     };
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous half-sweep (other colour) is complete
     uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
     if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
     else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));

@@ -31,7 +31,9 @@ if __name__ == "__main__":
     tag = os.environ.get("BC_ENGINE_LIB", "default")
     cases = []
     if mode == "quick":
-        cases.append((4096, 64, 0, 10, 0, 0))
+        for L, nr, sw in ((4096, 1, 200), (2048, 8, 200), (1024, 8, 400), (8192, 1, 100), (16384, 1, 50)):
+            for rows in (0, 2, 4, 8, 16):
+                cases.append((L, nr, rows, sw, 0, 0))
         cases.append((4096, 64, 8, 10, 0, 0))
         cases.append((4096, 64, 32, 10, 0, 0))
         cases.append((4096, 64, 0, 10, 1, 0))
