@@ -208,24 +208,45 @@ def run_ours(args, rank, world, local_rank):
         single = float(L) * L * 1024 / (e1.timer_stop() * 1e6)
         e1.close()
 
-    # ---- end to end through the C ABI from pinned host buffers
-    host = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True)
-    host_np = host.numpy()
-    eng.download(out=host_np)
+    # ---- end to end through the C ABI from pinned host buffers.  Two handles (two streams) are used the
+    # ---- way a caller with many batches would: while one batch is swept, the other batch's lattices are
+    # ---- uploaded / downloaded.  Every step still uploads its 1 GiB of input lattices and reads back its
+    # ---- observables and its 1 GiB of final lattices inside the timed region.
+    eng2 = bc.Engine(L, bc.PERIODIC, N_REPLICAS, local_rank, SEED + (rank << 40) + 1)
+    eng2.set_params(T, D, J)
+    engs = [eng, eng2]
+    hosts = []
+    for k in range(2):
+        h = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True).numpy()
+        eng.download(out=h)
+        hosts.append(h)
     obs_buf = None
-    for _ in range(min(args.warmup, 2)):
-        eng.upload(host_np)
-        obs_buf = eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY)
-        eng.download(out=host_np)
+
+    def e2e_steps(n):
+        nonlocal obs_buf
+        pending = [False, False]
+        for i in range(n):
+            k = i & 1
+            e = engs[k]
+            if pending[k]:
+                obs_buf = e.read_obs(n_meas)                 # waits for step i-2 on this handle (d2h observables)
+            e.upload_async(hosts[k])                          # h2d: the step's input lattices
+            e.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
+            e.download_async(hosts[k])                        # d2h: the step's final lattices (the sample dump)
+            pending[k] = True
+        for k in range(2):
+            if pending[k]:
+                obs_buf = engs[k].read_obs(n_meas)
+                engs[k].sync()
+
+    e2e_steps(min(args.warmup, 2))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.upload(host_np)                                 # h2d: the step's input lattices
-        obs_buf = eng.sweep(SWEEPS_PER_STEP, MEASURE_EVERY)  # d2h: the step's observables
-        eng.download(out=host_np)                           # d2h: the sample for the dump
+    e2e_steps(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    host_np = hosts[0]
 
     ms_t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
@@ -278,6 +299,7 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     eng.close()
+    eng2.close()
     if dist is not None:
         dist.destroy_process_group()
 

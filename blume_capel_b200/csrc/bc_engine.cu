@@ -420,7 +420,7 @@ extern "C" int bc_init_random(bc_engine* e, int replica) {
     return exchange_both(e);
 }
 
-static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins) {
+static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool wait = true) {
     BC_CUDA(e, cudaSetDevice(e->device));
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
@@ -433,11 +433,11 @@ static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins) {
     BC_CUDA(e, cudaGetLastError());
     rc = exchange_both(e);
     if (rc != BC_OK) return rc;
-    BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
+    if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
     return BC_OK;
 }
 
-static int download_range(bc_engine* e, int r0, int n, int8_t* spins) {
+static int download_range(bc_engine* e, int r0, int n, int8_t* spins, bool wait = true) {
     BC_CUDA(e, cudaSetDevice(e->device));
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
@@ -448,7 +448,7 @@ static int download_range(bc_engine* e, int r0, int n, int8_t* spins) {
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
-    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));
     return BC_OK;
 }
 
@@ -469,6 +469,15 @@ extern "C" int bc_upload_all(bc_engine* e, const int8_t* spins) {
 extern "C" int bc_download_all(bc_engine* e, int8_t* spins) {
     if (!e || !spins) return BC_ERR_ARG;
     return download_range(e, 0, e->n_rep, spins);
+}
+
+extern "C" int bc_upload_all_async(bc_engine* e, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return upload_range(e, 0, e->n_rep, spins, false);
+}
+extern "C" int bc_download_all_async(bc_engine* e, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return download_range(e, 0, e->n_rep, spins, false);
 }
 
 extern "C" int bc_get_sweep_counter(const bc_engine* e, int64_t* t) {

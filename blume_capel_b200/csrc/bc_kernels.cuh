@@ -351,7 +351,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 // with __syncthreads() between half-sweeps -- no launch per half-sweep, no HBM traffic inside the loop.
 // This is what the reference's own sizes (L = 8 ... 128, gen_files.py:11) and finite-size-scaling ladders
 // need: at L = 64 a launch-per-half-sweep engine is launch-bound (~3 us per 2048 updates).
-// Same spec, same update_chunk16 -> bit-identical to the streaming kernel and the oracle.
+// Same spec, same update_chunk16 -> bit-identical to the streaming kernel and to the CPU restatement of the spec.
 //   threads_per_rep T (32 / 128 / 256 / 512) threads share one replica; reps_per_cta = 128 / T for T < 128.
 // ------------------------------------------------------------------------------------------
 struct ResidentParams {

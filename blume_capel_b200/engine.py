@@ -49,6 +49,8 @@ SYMBOLS = {
     "bc_download": (C.c_int, [_P, C.c_int, _P]),
     "bc_upload_all": (C.c_int, [_P, _P]),
     "bc_download_all": (C.c_int, [_P, _P]),
+    "bc_upload_all_async": (C.c_int, [_P, _P]),
+    "bc_download_all_async": (C.c_int, [_P, _P]),
     "bc_get_sweep_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_sweep_counter": (C.c_int, [_P, C.c_int64]),
     "bc_sweep": (C.c_int64, [_P, C.c_int64, C.c_int64, _P]),
@@ -170,6 +172,15 @@ class Engine:
             a = out if out is not None else np.empty((self.rows, self.L), np.int8)
             self._check(self._lib.bc_download(self._h, replica, a.ctypes.data))
         return a
+
+    def upload_async(self, spins: np.ndarray):
+        """All replicas, no wait: `spins` (pinned, C-contiguous int8) must stay untouched until sync()."""
+        assert spins.dtype == np.int8 and spins.flags.c_contiguous and spins.size == self.n_replicas * self.rows * self.L
+        self._check(self._lib.bc_upload_all_async(self._h, spins.ctypes.data))
+
+    def download_async(self, out: np.ndarray):
+        assert out.dtype == np.int8 and out.flags.c_contiguous and out.size == self.n_replicas * self.rows * self.L
+        self._check(self._lib.bc_download_all_async(self._h, out.ctypes.data))
 
     @property
     def sweep_counter(self) -> int:

@@ -104,6 +104,11 @@ int bc_download(bc_engine* e, int replica, int8_t* spins);
 /* all replicas at once, spins: n_replicas * L*L int8, replica-major */
 int bc_upload_all(bc_engine* e, const int8_t* spins);
 int bc_download_all(bc_engine* e, int8_t* spins);
+/* Asynchronous variants (enqueue on the engine stream and return): `spins` should be pinned host memory
+ * and must stay valid -- and, for the upload, unmodified -- until the next bc_sync on this handle.  With
+ * two handles a caller overlaps the transfers of one batch with the sweeps of another. */
+int bc_upload_all_async(bc_engine* e, const int8_t* spins);
+int bc_download_all_async(bc_engine* e, int8_t* spins);
 
 /* Sweep counter = the full RNG state besides the seed (Philox is counter based), so
  * (lattice, seed, counter) is an exact checkpoint. */
