@@ -270,3 +270,50 @@ def test_resident_is_one_launch_and_equals_streaming(bc):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert res[0][2] == 2 and res[1][2] > 100
     assert res[0][3] == res[1][3]
+
+
+def test_async_transfers_and_two_handles(bc, oracle):
+    """bc_upload_all_async / bc_download_all_async on two handles (two streams) used ping-pong, as
+    bench.py's end-to-end loop does; every batch must come back exactly as the oracle computes it."""
+    L, n_rep, n = 64, 3, 6
+    tab = oracle.build_table(*TC)
+    engs = [bc.Engine(L, 0, n_rep, 0, 1000 + k) for k in range(2)]
+    for e in engs:
+        e.set_params(*TC)
+    rng = np.random.default_rng(8)
+    bufs = [np.ascontiguousarray(rng.integers(-1, 2, size=(n_rep, L, L), dtype=np.int8)) for _ in range(2)]
+    want = [b.copy() for b in bufs]
+    counters = [0, 0]
+    for step in range(4):
+        k = step & 1
+        e = engs[k]
+        e.sync()
+        e.upload_async(bufs[k])
+        e.sweep(n, 0, fetch=False)
+        e.download_async(bufs[k])
+        for r in range(n_rep):
+            oracle.sweep(want[k][r], tab, 1000 + k, r, counters[k], n, 0)
+        counters[k] += n
+    for k in range(2):
+        engs[k].sync()
+        assert np.array_equal(bufs[k], want[k]), k
+        engs[k].close()
+
+
+def test_resident_per_replica_parameters_and_counter_offset(bc, oracle):
+    L, n_rep, seed = 64, 4, 31
+    e = bc.Engine(L, 1, n_rep, 0, seed)
+    pts = [(0.5 + 0.1 * r, 1.9 + 0.02 * r, 1.0) for r in range(n_rep)]
+    for r, p in enumerate(pts):
+        e.set_params(*p, replica=r)
+    e.init_random()
+    e.sweep_counter = (1 << 33) + 5  # exercises the high word of the Philox counter
+    obs = e.sweep(7, 3)
+    assert e.plan()["resident"]
+    got = e.download()
+    for r, p in enumerate(pts):
+        ref = oracle.init_random(L, seed, r)
+        ro = oracle.sweep(ref, oracle.build_table(*p), seed, r, (1 << 33) + 5, 7, 3, 1)
+        assert np.array_equal(got[r], ref), r
+        assert np.array_equal(obs[:, r]["B"], ro["B"]) and np.array_equal(obs[:, r]["sweep"], ro["sweep"])
+    e.close()
