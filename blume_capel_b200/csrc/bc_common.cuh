@@ -67,7 +67,9 @@ struct SweepParams {
     int y_rng_off;           // global row = array row + y_rng_off (RNG counter and colour parity)
     int Wc;                  // compact row stride in bytes
     int cpr;                 // 16-byte chunks per compact row (fast kernel)
-    int strips;              // row strips per replica (fast kernel), rows per strip = L / strips
+    int strips;              // row strips per replica processed by THIS launch
+    int strip_base;          // actual strip = strip_base + local strip * strip_stride (a slab launches its two
+    int strip_stride;        //   boundary strips first, then the interior, so the halo exchange can overlap)
     int n_replicas;
     int open;                // 1 = open boundary (off-lattice neighbours are spin 0)
     uint32_t key0, key1;     // Philox key of replica 0; replica r uses (key0, key1 ^ r)

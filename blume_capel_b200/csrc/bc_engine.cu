@@ -75,6 +75,9 @@ struct bc_engine {
     bool ghost = false;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    cudaStream_t halo_stream = nullptr;  // high-priority side stream for the slab halo exchange
+    cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
+    int opt_overlap = 1;
     size_t colour_bytes = 0;  // bytes of one colour array (all replicas)
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
@@ -182,7 +185,11 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->halo_stream) cudaStreamSynchronize(e->halo_stream);
     if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
+    if (e->ev_boundary) cudaEventDestroy(e->ev_boundary);
+    if (e->ev_halo) cudaEventDestroy(e->ev_halo);
+    if (e->halo_stream) cudaStreamDestroy(e->halo_stream);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->d_clock);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
@@ -265,6 +272,13 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
         return BC_ERR_CUDA;
     }
     if ((st = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", st);
+    if (slab) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if ((st = cudaStreamCreateWithPriority(&e->halo_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("halo stream", st);
+        if ((st = cudaEventCreateWithFlags(&e->ev_boundary, cudaEventDisableTiming)) != cudaSuccess) return bail("event", st);
+        if ((st = cudaEventCreateWithFlags(&e->ev_halo, cudaEventDisableTiming)) != cudaSuccess) return bail("event", st);
+    }
     if (slab && nranks > 1) {
         if (!g_nccl.load()) {
             g_create_error = "bc_create_slab: " + g_nccl.error;
@@ -355,14 +369,15 @@ extern "C" int bc_get_table(const bc_engine* e, int replica, uint32_t thr31[54])
 // of the rank above and its last owned row to the top ghost row of the rank below (periodic wrap; an
 // open lattice keeps code-1 ghost rows at the global edges).  32 KiB per message at L = 65536.
 // ---------------------------------------------------------------------------------------------
-static int exchange_halo(bc_engine* e, int col) {
+static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr) {
     if (!e->ghost) return BC_OK;
+    if (!stream) stream = e->stream;
     const bool periodic = e->boundary == BC_PERIODIC;
     const size_t Wc = (size_t)e->Wc, rep_stride = (size_t)e->rows_arr * Wc;
     if (e->nranks == 1) {
         if (!periodic) return BC_OK;
         const long long total = 2LL * e->Wc * e->n_rep;
-        halo_self_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(e->d_c[col], geom_of(e), e->n_rep);
+        halo_self_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(e->d_c[col], geom_of(e), e->n_rep);
         ++e->launches;
         BC_CUDA(e, cudaGetLastError());
         return BC_OK;
@@ -378,10 +393,10 @@ static int exchange_halo(bc_engine* e, int col) {
         uint8_t* ghost_top = base;
         uint8_t* ghost_bot = base + (size_t)(e->Ly + 1) * Wc;
         // order matters when prev == next (2 ranks): sends (first, last) pair with recvs (bottom, top)
-        if (prev >= 0) BC_NCCL(e, g_nccl.Send(first_owned, Wc, ncclUint8, prev, e->comm, e->stream));
-        if (next >= 0) BC_NCCL(e, g_nccl.Send(last_owned, Wc, ncclUint8, next, e->comm, e->stream));
-        if (next >= 0) BC_NCCL(e, g_nccl.Recv(ghost_bot, Wc, ncclUint8, next, e->comm, e->stream));
-        if (prev >= 0) BC_NCCL(e, g_nccl.Recv(ghost_top, Wc, ncclUint8, prev, e->comm, e->stream));
+        if (prev >= 0) BC_NCCL(e, g_nccl.Send(first_owned, Wc, ncclUint8, prev, e->comm, stream));
+        if (next >= 0) BC_NCCL(e, g_nccl.Send(last_owned, Wc, ncclUint8, next, e->comm, stream));
+        if (next >= 0) BC_NCCL(e, g_nccl.Recv(ghost_bot, Wc, ncclUint8, next, e->comm, stream));
+        if (prev >= 0) BC_NCCL(e, g_nccl.Recv(ghost_top, Wc, ncclUint8, prev, e->comm, stream));
     }
     BC_NCCL(e, g_nccl.GroupEnd());
     return BC_OK;
@@ -550,8 +565,9 @@ static LaunchPlan make_plan(const bc_engine* e) {
     return p;
 }
 
+// part: 0 = all strips, 1 = the two boundary strips of the slab, 2 = the interior strips
 static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
-                       const int64_t* t_ptr = nullptr) {
+                       const int64_t* t_ptr = nullptr, int part = 0) {
     SweepParams P;
     P.own = e->d_c[col];
     P.other = e->d_c[1 - col];
@@ -571,6 +587,12 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.Wc = e->Wc;
     P.cpr = plan.cpr;
     P.strips = plan.strips;
+    P.strip_base = 0;
+    P.strip_stride = 1;
+    unsigned grid = plan.grid;
+    if (part == 1) { P.strips = 2; P.strip_stride = plan.strips - 1; }
+    if (part == 2) { P.strips = plan.strips - 2; P.strip_base = 1; }
+    if (part != 0) grid = (unsigned)(((long long)e->n_rep * P.strips * plan.cpr + FAST_THREADS - 1) / FAST_THREADS);
     P.n_replicas = e->n_rep;
     P.open = e->boundary == BC_OPEN;
     P.key0 = (uint32_t)e->seed;
@@ -579,14 +601,14 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
         fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN);
         if (e->opt_pdl) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             cudaLaunchKernelEx(&cfg, fn, P);
         } else {
-            fn<<<plan.grid, FAST_THREADS, 0, e->stream>>>(P);
+            fn<<<grid, FAST_THREADS, 0, e->stream>>>(P);
         }
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
@@ -618,6 +640,29 @@ static int fetch_pending(bc_engine* e, bc_obs* out) {
     for (int64_t m = 0; m < n; ++m)
         for (int r = 0; r < e->n_rep; ++r)
             raw_to_obs(e, &raw[((size_t)m * e->n_rep + r) * OBS_RAW], e->pending_sweeps[m], &out[(size_t)m * e->n_rep + r]);
+    return BC_OK;
+}
+
+// One half-sweep of a slab handle.  With overlap: the two boundary strips first, then their halo rows travel
+// on the high-priority side stream while the interior strips are updated on the main stream; the next
+// half-sweep waits for both.  (The boundary strips are whole strips of the ordinary decomposition, so the
+// result is identical to the single-launch order: sites of one colour never read each other.)
+static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot) {
+    const long long ipr_part = (long long)2 * plan.cpr, ipr_int = (long long)(plan.strips - 2) * plan.cpr;
+    const bool can_split = plan.fast && !plan.small && plan.strips >= 4 && (ipr_part % FAST_THREADS) == 0 &&
+                           (ipr_int % FAST_THREADS) == 0 && e->opt_overlap;
+    if (!can_split) {
+        launch_half(e, plan, col, measure, t, slot);
+        return exchange_halo(e, col);
+    }
+    launch_half(e, plan, col, measure, t, slot, nullptr, 1);
+    BC_CUDA(e, cudaEventRecord(e->ev_boundary, e->stream));
+    BC_CUDA(e, cudaStreamWaitEvent(e->halo_stream, e->ev_boundary, 0));
+    int rc = exchange_halo(e, col, e->halo_stream);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaEventRecord(e->ev_halo, e->halo_stream));
+    launch_half(e, plan, col, measure, t, slot, nullptr, 2);
+    BC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_halo, 0));
     return BC_OK;
 }
 
@@ -659,10 +704,14 @@ static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, in
         }
     }
     for (; done < n; ++done) {
-        launch_half(e, plan, 0, false, t0 + done, 0);
-        if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
-        launch_half(e, plan, 1, false, t0 + done, 0);
-        if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
+        if (e->ghost) {
+            int rc = slab_half(e, plan, 0, false, t0 + done, 0);
+            if (rc == BC_OK) rc = slab_half(e, plan, 1, false, t0 + done, 0);
+            if (rc != BC_OK) return rc;
+        } else {
+            launch_half(e, plan, 0, false, t0 + done, 0);
+            launch_half(e, plan, 1, false, t0 + done, 0);
+        }
     }
     return BC_OK;
 }
@@ -758,10 +807,14 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
             t = t_meas;
         }
         if (slot < n_meas) {
-            launch_half(e, plan, 0, true, t, slot);
-            if (e->ghost) { int rc = exchange_halo(e, 0); if (rc != BC_OK) return rc; }
-            launch_half(e, plan, 1, true, t, slot);
-            if (e->ghost) { int rc = exchange_halo(e, 1); if (rc != BC_OK) return rc; }
+            if (e->ghost) {
+                int rc = slab_half(e, plan, 0, true, t, slot);
+                if (rc == BC_OK) rc = slab_half(e, plan, 1, true, t, slot);
+                if (rc != BC_OK) return rc;
+            } else {
+                launch_half(e, plan, 0, true, t, slot);
+                launch_half(e, plan, 1, true, t, slot);
+            }
             ++t;
         }
     }
@@ -859,6 +912,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
+    if (n == "overlap") { e->opt_overlap = value != 0; return BC_OK; }
     if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
     if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }

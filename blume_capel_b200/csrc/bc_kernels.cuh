@@ -232,7 +232,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     const uint32_t strip = rem / (uint32_t)P.cpr;
     const uint32_t j = rem - strip * (uint32_t)P.cpr;
     const uint32_t rows = (uint32_t)P.rows_per_strip;
-    const uint32_t y0 = (uint32_t)P.row_first + strip * rows;  // array row; global row = y0 + y_rng_off
+    const uint32_t y0 = (uint32_t)P.row_first + ((uint32_t)P.strip_base + strip * (uint32_t)P.strip_stride) * rows;  // array row
     const uint32_t yg0 = y0 + (uint32_t)P.y_rng_off;
     const uint32_t Wc = (uint32_t)P.Wc;
     constexpr bool open = OPEN;

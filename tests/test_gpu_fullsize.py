@@ -102,3 +102,24 @@ def test_J0_limit_statistics(bc):
     assert abs(q - q_exact) < 6e-4, (q, q_exact)
     assert abs(obs[:, 0]["M"].mean() / N) < 2e-3
     assert np.all(obs[:, 0]["B"] * 0 == 0)
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_slab_overlap_path_equals_plain_engine_L2048(bc, boundary):
+    """Slab handle (ghost rows, boundary strips first, halo exchange on the side stream overlapped with
+    the interior) against the ordinary engine at a size where the split launch is active."""
+    L, n = 2048, 6
+    out = []
+    for mode in ("plain", "slab", "slab_no_overlap"):
+        e = bc.Engine(L, boundary, 1, 0, 0xC0FFEE) if mode == "plain" else bc.Engine(L, boundary, 1, 0, 0xC0FFEE, slab=(1, 0, None))
+        if mode == "slab_no_overlap":
+            e.set_option("overlap", 0)
+        e.set_params(*TC)
+        e.init_random()
+        obs = e.sweep(n, 2)
+        out.append((e.download(0), obs))
+        e.close()
+    for lat, obs in out[1:]:
+        assert np.array_equal(lat, out[0][0])
+        for f in ("M", "Q", "B"):
+            assert np.array_equal(obs[f], out[0][1][f])
