@@ -47,6 +47,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// (a & b) ^ c as ONE LOP3 (immLut 0x6A); c must live in a register, a LOP3 has room for one immediate only
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // packed signed 16-bit minimum (VIMNMX.S16x2): 0x8000 is the most negative lane value
 __device__ __forceinline__ uint32_t min_s16x2(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -82,6 +89,8 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
     const int64_t t = C.t;
     const char* tabm = C.tabm;
     const uint32_t* t31_rep = C.t31_rep;
+    uint32_t ones_r;  // ONES held in a register the compiler cannot fold back into an immediate
+    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
     const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
     const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
     const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
@@ -105,7 +114,7 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
             const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
             const uint32_t c4 = o[wi];
             // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
-            const uint32_t fO = (prmt(ra, rb, 0xFDB9u) & 0x03030303u) ^ ONES;
+            const uint32_t fO = and_xor(prmt(ra, rb, 0xFDB9u), 0x03030303u, ones_r);  // one LOP3
             // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
             // u16 byte offset is applied by the IDP.4A that extracts each byte
             const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
