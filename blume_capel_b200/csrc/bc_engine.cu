@@ -75,6 +75,17 @@ struct bc_engine {
     bool ghost = false;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    // P2P halo exchange (peer pointers opened from the neighbours' CUDA IPC handles)
+    bool p2p = false;
+    long long* d_flags = nullptr;      // [0] top ghost epoch, [1] bottom ghost epoch (written by the neighbours)
+    int* d_halo_err = nullptr;
+    uint8_t* peer_prev_c[2] = {nullptr, nullptr};
+    uint8_t* peer_next_c[2] = {nullptr, nullptr};
+    long long* peer_prev_flags = nullptr;
+    long long* peer_next_flags = nullptr;
+    void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    long long halo_epoch = 0;          // exchanges issued so far (identical on every rank)
+    long long halo_waited = 0;         // last epoch a wait was enqueued for
     cudaStream_t halo_stream = nullptr;  // high-priority side stream for the slab halo exchange
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
     int opt_overlap = 1;
@@ -186,6 +197,8 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->halo_stream) cudaStreamSynchronize(e->halo_stream);
+    for (void* p : e->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
+    cudaFree(e->d_flags); cudaFree(e->d_halo_err);
     if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
     if (e->ev_boundary) cudaEventDestroy(e->ev_boundary);
     if (e->ev_halo) cudaEventDestroy(e->ev_halo);
@@ -273,6 +286,10 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     }
     if ((st = cudaStreamSynchronize(e->stream)) != cudaSuccess) return bail("sync", st);
     if (slab) {
+        if ((st = cudaMalloc(&e->d_flags, 2 * sizeof(long long))) != cudaSuccess) return bail("cudaMalloc flags", st);
+        if ((st = cudaMemset(e->d_flags, 0, 2 * sizeof(long long))) != cudaSuccess) return bail("memset", st);
+        if ((st = cudaMalloc(&e->d_halo_err, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", st);
+        if ((st = cudaMemset(e->d_halo_err, 0, sizeof(int))) != cudaSuccess) return bail("memset", st);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((st = cudaStreamCreateWithPriority(&e->halo_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("halo stream", st);
@@ -385,6 +402,19 @@ static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr) {
     const int up = e->rank - 1, dn = e->rank + 1;
     const int prev = up >= 0 ? up : (periodic ? e->nranks - 1 : -1);
     const int next = dn < e->nranks ? dn : (periodic ? 0 : -1);
+    if (e->p2p) {
+        // direct stores into the neighbours' ghost rows over NVLink, then publish the epoch in their flags
+        const long long total = 2LL * (e->Wc / 16) * e->n_rep;
+        halo_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            e->d_c[col], prev >= 0 ? e->peer_prev_c[col] : nullptr, next >= 0 ? e->peer_next_c[col] : nullptr,
+            geom_of(e), e->n_rep);
+        ++e->halo_epoch;
+        halo_signal_kernel<<<1, 1, 0, stream>>>(prev >= 0 ? e->peer_prev_flags : nullptr,
+                                                next >= 0 ? e->peer_next_flags : nullptr, e->halo_epoch);
+        e->launches += 2;
+        BC_CUDA(e, cudaGetLastError());
+        return BC_OK;
+    }
     BC_NCCL(e, g_nccl.GroupStart());
     for (int r = 0; r < e->n_rep; ++r) {
         uint8_t* base = e->d_c[col] + (size_t)r * rep_stride;
@@ -402,7 +432,22 @@ static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr) {
     return BC_OK;
 }
 
+// P2P mode: before a kernel reads ghost rows, wait (on the GPU) for the neighbours' latest epoch
+static int halo_wait(bc_engine* e, cudaStream_t stream) {
+    if (!e->p2p || e->halo_waited == e->halo_epoch) return BC_OK;
+    const bool periodic = e->boundary == BC_PERIODIC;
+    const int need_top = (e->rank > 0 || periodic) ? 1 : 0, need_bottom = (e->rank + 1 < e->nranks || periodic) ? 1 : 0;
+    halo_wait_kernel<<<1, 1, 0, stream>>>(e->d_flags, need_top, need_bottom, e->halo_epoch, e->d_halo_err);
+    ++e->launches;
+    e->halo_waited = e->halo_epoch;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
 static int exchange_both(bc_engine* e) {
+    // P2P: the neighbours must have finished reading their ghost rows (their last boundary kernel precedes
+    // their last signal) before this rank overwrites them outside the half-sweep cadence (init / upload)
+    if (e->p2p) { int rc0 = halo_wait(e, e->stream); if (rc0 != BC_OK) return rc0; }
     int rc = exchange_halo(e, 0);
     if (rc == BC_OK) rc = exchange_halo(e, 1);
     return rc;
@@ -651,6 +696,21 @@ static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure
     const long long ipr_part = (long long)2 * plan.cpr, ipr_int = (long long)(plan.strips - 2) * plan.cpr;
     const bool can_split = plan.fast && !plan.small && plan.strips >= 4 && (ipr_part % FAST_THREADS) == 0 &&
                            (ipr_int % FAST_THREADS) == 0 && e->opt_overlap;
+    if (e->p2p) {
+        // wait for the ghost rows of the other colour (pushed by the neighbours one half-sweep ago), update the
+        // boundary strips, push + signal, then the interior: everything on the main stream, no NCCL kernels
+        int rc = halo_wait(e, e->stream);
+        if (rc != BC_OK) return rc;
+        if (!can_split) {
+            launch_half(e, plan, col, measure, t, slot);
+            return exchange_halo(e, col);
+        }
+        launch_half(e, plan, col, measure, t, slot, nullptr, 1);
+        rc = exchange_halo(e, col);
+        if (rc != BC_OK) return rc;
+        launch_half(e, plan, col, measure, t, slot, nullptr, 2);
+        return BC_OK;
+    }
     if (!can_split) {
         launch_half(e, plan, col, measure, t, slot);
         return exchange_halo(e, col);
@@ -852,6 +912,7 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
     cudaError_t st = cudaMemsetAsync(d_raw, 0, bytes, e->stream);
     const long long total = (long long)e->n_rep * e->Ly * e->L;
     const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (st == cudaSuccess && halo_wait(e, e->stream) != BC_OK) st = cudaErrorUnknown;
     if (st == cudaSuccess) {
         measure_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], geom_of(e), e->n_rep, d_raw);
         ++e->launches;
@@ -874,6 +935,56 @@ extern "C" int bc_sync(bc_engine* e) {
     if (!e) return BC_ERR_ARG;
     BC_CUDA(e, cudaSetDevice(e->device));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->d_halo_err) {
+        int err = 0;
+        BC_CUDA(e, cudaMemcpy(&err, e->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(e, BC_ERR_STATE, "bc_sync: a slab neighbour did not deliver its halo rows in time");
+    }
+    return BC_OK;
+}
+
+// ---- P2P halo: export / connect CUDA IPC handles -----------------------------------------------------
+struct IpcBlob {
+    cudaIpcMemHandle_t c[2];
+    cudaIpcMemHandle_t flags;
+};
+static_assert(sizeof(IpcBlob) == 192, "three 64-byte CUDA IPC handles");
+
+extern "C" int bc_slab_ipc_export(bc_engine* e, void* blob192) {
+    if (!e || !blob192) return BC_ERR_ARG;
+    if (!e->ghost) return fail(e, BC_ERR_STATE, "bc_slab_ipc_export: not a slab handle");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    IpcBlob b;
+    BC_CUDA(e, cudaIpcGetMemHandle(&b.c[0], e->d_c[0]));
+    BC_CUDA(e, cudaIpcGetMemHandle(&b.c[1], e->d_c[1]));
+    BC_CUDA(e, cudaIpcGetMemHandle(&b.flags, e->d_flags));
+    std::memcpy(blob192, &b, sizeof(b));
+    return BC_OK;
+}
+
+extern "C" int bc_slab_ipc_connect(bc_engine* e, const void* prev_blob192, const void* next_blob192) {
+    if (!e) return BC_ERR_ARG;
+    if (!e->ghost || e->nranks < 2) return fail(e, BC_ERR_STATE, "bc_slab_ipc_connect: needs a slab handle with n_ranks >= 2");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    const bool same = prev_blob192 && next_blob192 && std::memcmp(prev_blob192, next_blob192, sizeof(IpcBlob)) == 0;
+    auto open3 = [&](const void* blob, uint8_t* (&c)[2], long long*& flags, int slot) -> int {
+        IpcBlob b;
+        std::memcpy(&b, blob, sizeof(b));
+        void* p[3] = {nullptr, nullptr, nullptr};
+        BC_CUDA(e, cudaIpcOpenMemHandle(&p[0], b.c[0], cudaIpcMemLazyEnablePeerAccess));
+        BC_CUDA(e, cudaIpcOpenMemHandle(&p[1], b.c[1], cudaIpcMemLazyEnablePeerAccess));
+        BC_CUDA(e, cudaIpcOpenMemHandle(&p[2], b.flags, cudaIpcMemLazyEnablePeerAccess));
+        c[0] = (uint8_t*)p[0]; c[1] = (uint8_t*)p[1]; flags = (long long*)p[2];
+        for (int i = 0; i < 3; ++i) e->ipc_opened[slot * 3 + i] = p[i];
+        return BC_OK;
+    };
+    if (prev_blob192) { int rc = open3(prev_blob192, e->peer_prev_c, e->peer_prev_flags, 0); if (rc != BC_OK) return rc; }
+    if (next_blob192) {
+        if (same) { e->peer_next_c[0] = e->peer_prev_c[0]; e->peer_next_c[1] = e->peer_prev_c[1]; e->peer_next_flags = e->peer_prev_flags; }
+        else { int rc = open3(next_blob192, e->peer_next_c, e->peer_next_flags, 1); if (rc != BC_OK) return rc; }
+    }
+    e->p2p = true;
     return BC_OK;
 }
 

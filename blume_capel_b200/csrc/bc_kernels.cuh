@@ -675,6 +675,53 @@ __global__ void halo_self_kernel(uint8_t* __restrict__ c, const Geom g, int n_re
     else base[(size_t)(g.Ly + 1) * g.Wc + k] = base[(size_t)g.Wc + k];                    // bottom ghost <- first owned row
 }
 
+// ---- slab halo over peer memory (NVLink P2P, one process per GPU, pointers from cudaIpcOpenMemHandle) --------
+// Copies this rank's first / last owned row of one colour array into the bottom / top ghost row of the
+// ring neighbour above / below, for every replica, with plain 16-byte stores to the peer's memory.
+__global__ void halo_push_kernel(const uint8_t* __restrict__ c, uint8_t* __restrict__ peer_prev,
+                                 uint8_t* __restrict__ peer_next, const Geom g, int n_rep) {
+    const int vec_per_row = g.Wc / 16;
+    const long long per_rep = 2LL * vec_per_row;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_rep * n_rep) return;
+    const int r = (int)(gid / per_rep);
+    const int rem = (int)(gid - (long long)r * per_rep);
+    const int which = rem / vec_per_row, v = rem - which * vec_per_row;
+    const size_t rep_off = (size_t)r * g.rows_arr * g.Wc;
+    if (which == 0) {
+        if (peer_prev)  // my first owned row -> bottom ghost row of the rank above
+            reinterpret_cast<uint4*>(peer_prev + rep_off + (size_t)(g.Ly + 1) * g.Wc)[v] =
+                reinterpret_cast<const uint4*>(c + rep_off + (size_t)g.Wc)[v];
+    } else {
+        if (peer_next)  // my last owned row -> top ghost row of the rank below
+            reinterpret_cast<uint4*>(peer_next + rep_off)[v] =
+                reinterpret_cast<const uint4*>(c + rep_off + (size_t)g.Ly * g.Wc)[v];
+    }
+}
+
+// After the pushes of an exchange have completed (stream order): publish the epoch in the neighbours' flags.
+// flags[0] of a rank = "top ghost rows valid through epoch" (written by the rank above),
+// flags[1]           = "bottom ghost rows valid through epoch" (written by the rank below).
+__global__ void halo_signal_kernel(long long* peer_prev_flags, long long* peer_next_flags, long long epoch) {
+    __threadfence_system();
+    if (peer_prev_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_prev_flags + 1), "l"(epoch) : "memory");
+    if (peer_next_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_next_flags + 0), "l"(epoch) : "memory");
+}
+
+// Before ghost rows are read: wait until both neighbours have published `epoch`.  One thread, one GPU per
+// rank (never two ranks on one GPU), bounded: gives up after ~4 s and raises *err instead of hanging the GPU.
+__global__ void halo_wait_kernel(const long long* my_flags, int need_top, int need_bottom, long long epoch, int* err) {
+    const long long t0 = clock64();
+    for (int k = 0; k < 2; ++k) {
+        if (!(k == 0 ? need_top : need_bottom)) continue;
+        long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(my_flags + k) : "memory");
+            if (v < epoch && clock64() - t0 > 8000000000LL) { *err = 1; return; }
+        } while (v < epoch);
+    }
+}
+
 // code of the neighbour (nx, ny) [ny = owned-row index, may be -1 or Ly] in the other colour's array
 __device__ __forceinline__ uint32_t geom_other_code(const uint8_t* oth_rep, const Geom& g, int nx, int ny) {
     if (g.open) { if (nx < 0 || nx >= g.L) return 1u; }

@@ -38,6 +38,8 @@ SYMBOLS = {
     "bc_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64]),
     "bc_slab_unique_id": (C.c_int, [_P]),
     "bc_create_slab": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _P]),
+    "bc_slab_ipc_export": (C.c_int, [_P, _P]),
+    "bc_slab_ipc_connect": (C.c_int, [_P, _P, _P]),
     "bc_local_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bc_destroy": (None, [_P]),
     "bc_last_error": (C.c_char_p, [_P]),
@@ -172,6 +174,17 @@ class Engine:
             a = out if out is not None else np.empty((self.rows, self.L), np.int8)
             self._check(self._lib.bc_download(self._h, replica, a.ctypes.data))
         return a
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(192)
+        self._check(self._lib.bc_slab_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_connect(self, prev_blob: Optional[bytes], next_blob: Optional[bytes]):
+        """Switch the slab halo exchange to direct peer stores (blobs of the ranks above / below, None at an open edge)."""
+        p = C.create_string_buffer(prev_blob, 192) if prev_blob is not None else None
+        n = C.create_string_buffer(next_blob, 192) if next_blob is not None else None
+        self._check(self._lib.bc_slab_ipc_connect(self._h, p, n))
 
     def upload_async(self, spins: np.ndarray):
         """All replicas, no wait: `spins` (pinned, C-contiguous int8) must stay untouched until sync()."""

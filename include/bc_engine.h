@@ -80,6 +80,13 @@ int bc_slab_unique_id(void* id128);
 int bc_create_slab(bc_engine** out, int L, int boundary, int n_replicas, int storage, int device, uint64_t seed,
                    int n_ranks, int rank, const void* nccl_id128);
 int bc_local_rows(const bc_engine* e, int* rows, int* first_global_row);
+/* Halo exchange over peer memory instead of NCCL send/recv: every rank exports 192 bytes (CUDA IPC handles of
+ * its two colour arrays and its flag words), the caller hands each rank the blobs of its ring neighbours
+ * (NULL at an open edge), and from then on a half-sweep stores its boundary rows straight into the
+ * neighbours' ghost rows over NVLink and publishes an epoch flag; the consumer waits on the GPU.  One
+ * process per GPU, never two ranks on one GPU.  Collective: all ranks connect at the same point. */
+int bc_slab_ipc_export(bc_engine* e, void* blob192);
+int bc_slab_ipc_connect(bc_engine* e, const void* prev_blob192, const void* next_blob192);
 
 /* ---- parameters -------------------------------------------------------------------- */
 

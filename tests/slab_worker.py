@@ -62,22 +62,39 @@ def cpu_slab(boundary):
     return 0 if flag.item() == 1 else 1
 
 
-def gpu_slab(boundary):
-    """bc_create_slab over NCCL == single-GPU engine, lattice and fused observables."""
+def connect_p2p(bc, e, rank, world, periodic):
+    """All-gather the 192-byte IPC blobs and hand each rank its ring neighbours'."""
+    mine = torch.frombuffer(bytearray(e.ipc_export()), dtype=torch.uint8).cuda()
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    blobs = [bytes(t.cpu().numpy().tobytes()) for t in allb]
+    prev = blobs[(rank - 1) % world] if (periodic or rank > 0) else None
+    nxt = blobs[(rank + 1) % world] if (periodic or rank + 1 < world) else None
+    e.ipc_connect(prev, nxt)
+    dist.barrier()
+
+
+def gpu_slab(boundary, p2p=False):
+    """bc_create_slab over NCCL (or peer stores) == single-GPU engine, lattice and fused observables."""
     import blume_capel_b200 as bc
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L, n, seed = 256, 8, 4321
+    L, n, seed = (2048 if p2p else 256), 8, 4321
     b = bc.PERIODIC if boundary == "periodic" else bc.OPEN
     nid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         nid.copy_(torch.frombuffer(bytearray(bc.slab_unique_id()), dtype=torch.uint8))
     dist.broadcast(nid, 0)
     e = bc.Engine(L, b, 1, local, seed, slab=(world, rank, bytes(nid.cpu().numpy().tobytes())))
+    if p2p:
+        connect_p2p(bc, e, rank, world, boundary == "periodic")
     e.set_params(*TC)
     e.init_random()
     obs = e.sweep(n, 2)
+    if p2p:  # a second lattice through upload: exercises the out-of-cadence exchange
+        e.upload(e.download(0), 0)
+        obs2 = e.sweep(3, 0)
     mine = e.download(0)
     m = e.measure()
     e.close()
@@ -87,6 +104,8 @@ def gpu_slab(boundary):
         s.set_params(*TC)
         s.init_random()
         so = s.sweep(n, 2)
+        if p2p:
+            s.sweep(3, 0)
         whole = s.download(0)
         sm = s.measure()
         s.close()
@@ -109,4 +128,4 @@ def gpu_slab(boundary):
 
 if __name__ == "__main__":
     mode, boundary = sys.argv[1], sys.argv[2]
-    sys.exit(cpu_slab(boundary) if mode == "cpu" else gpu_slab(boundary))
+    sys.exit(cpu_slab(boundary) if mode == "cpu" else gpu_slab(boundary, p2p=(mode == "gpu_p2p")))

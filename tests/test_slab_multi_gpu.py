@@ -42,3 +42,16 @@ def test_slab_nccl_two_gpus(boundary):
     r = _torchrun(2, ["gpu", boundary])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SLAB_OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("boundary", ["periodic", "open"])
+def test_slab_peer_store_halo_two_gpus(boundary):
+    """Halo rows stored directly into the neighbour's ghost rows over NVLink (CUDA IPC peer pointers +
+    epoch flags) instead of NCCL send/recv; L = 2048 so the boundary-strips-first split is active."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, ["gpu_p2p", boundary])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "SLAB_OK" in r.stdout

@@ -27,6 +27,14 @@ if world > 1:
     dist.broadcast(t, 0)
     nid = bytes(t.cpu().numpy().tobytes())
 e = bc.Engine(L, bc.PERIODIC, 1, local, 0x5EED0004, slab=(world, rank, nid))
+P2P = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if P2P and world > 1:  # halo rows by direct peer stores instead of NCCL send/recv
+    mine = torch.frombuffer(bytearray(e.ipc_export()), dtype=torch.uint8).cuda()
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    blobs = [bytes(t.cpu().numpy().tobytes()) for t in allb]
+    e.ipc_connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
+    dist.barrier()
 e.set_params(0.608, 1.966, 1.0)
 e.init_random()
 e.sweep(5)
@@ -41,7 +49,7 @@ tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
 if dist: dist.all_reduce(tms, op=dist.ReduceOp.MAX)
 if rank == 0:
     ups = float(L) * L * SWEEPS / (tms.item() * 1e6)
-    print(json.dumps({"config": f"L={L} periodic int8, {world} row slab(s), NCCL halo exchange per half-sweep",
+    print(json.dumps({"config": f"L={L} periodic int8, {world} row slab(s), halo exchange per half-sweep by " + ("peer stores over NVLink (CUDA IPC) + epoch flags" if P2P and world > 1 else "NCCL send/recv"),
                       "n_gpus": world, "sweeps": SWEEPS, "ms": tms.item(), "updates_per_ns": ups,
                       "updates_per_ns_per_gpu": ups / world, "hbm_frac_per_gpu": ups / world * 3 / 6546.2,
                       "M": int(obs[0, 0]["M"]), "Q": int(obs[0, 0]["Q"]), "B": int(obs[0, 0]["B"])}), flush=True)
