@@ -612,7 +612,8 @@ static LaunchPlan make_plan(const bc_engine* e) {
 
 // part: 0 = all strips, 1 = the two boundary strips of the slab, 2 = the interior strips
 static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
-                       const int64_t* t_ptr = nullptr, int part = 0) {
+                       const int64_t* t_ptr = nullptr, int part = 0, cudaStream_t stream = nullptr) {
+    if (!stream) stream = e->stream;
     SweepParams P;
     P.own = e->d_c[col];
     P.other = e->d_c[1 - col];
@@ -646,14 +647,14 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
         fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN);
         if (e->opt_pdl) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             cudaLaunchKernelEx(&cfg, fn, P);
         } else {
-            fn<<<grid, FAST_THREADS, 0, e->stream>>>(P);
+            fn<<<grid, FAST_THREADS, 0, stream>>>(P);
         }
     } else {
         if (measure) sweep_generic_kernel<true><<<plan.grid, 256, 0, e->stream>>>(P, col, e->boundary == BC_OPEN);
@@ -696,32 +697,25 @@ static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure
     const long long ipr_part = (long long)2 * plan.cpr, ipr_int = (long long)(plan.strips - 2) * plan.cpr;
     const bool can_split = plan.fast && !plan.small && plan.strips >= 4 && (ipr_part % FAST_THREADS) == 0 &&
                            (ipr_int % FAST_THREADS) == 0 && e->opt_overlap;
-    if (e->p2p) {
-        // wait for the ghost rows of the other colour (pushed by the neighbours one half-sweep ago), update the
-        // boundary strips, push + signal, then the interior: everything on the main stream, no NCCL kernels
+    if (!can_split) {
         int rc = halo_wait(e, e->stream);
         if (rc != BC_OK) return rc;
-        if (!can_split) {
-            launch_half(e, plan, col, measure, t, slot);
-            return exchange_halo(e, col);
-        }
-        launch_half(e, plan, col, measure, t, slot, nullptr, 1);
-        rc = exchange_halo(e, col);
-        if (rc != BC_OK) return rc;
-        launch_half(e, plan, col, measure, t, slot, nullptr, 2);
-        return BC_OK;
-    }
-    if (!can_split) {
         launch_half(e, plan, col, measure, t, slot);
         return exchange_halo(e, col);
     }
-    launch_half(e, plan, col, measure, t, slot, nullptr, 1);
+    // Split half-sweep.  Side stream (high priority): wait for the neighbours' ghost rows (P2P mode), update
+    // the two boundary strips, send their fresh rows (peer stores + flag, or NCCL).  Main stream: the
+    // interior strips, which read no ghost row, run concurrently.  Both start after the previous half-sweep
+    // is complete on both streams; the next half-sweep starts after both parts.
     BC_CUDA(e, cudaEventRecord(e->ev_boundary, e->stream));
     BC_CUDA(e, cudaStreamWaitEvent(e->halo_stream, e->ev_boundary, 0));
-    int rc = exchange_halo(e, col, e->halo_stream);
+    int rc = halo_wait(e, e->halo_stream);
+    if (rc != BC_OK) return rc;
+    launch_half(e, plan, col, measure, t, slot, nullptr, 1, e->halo_stream);
+    rc = exchange_halo(e, col, e->halo_stream);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaEventRecord(e->ev_halo, e->halo_stream));
-    launch_half(e, plan, col, measure, t, slot, nullptr, 2);
+    launch_half(e, plan, col, measure, t, slot, nullptr, 2, e->stream);
     BC_CUDA(e, cudaStreamWaitEvent(e->stream, e->ev_halo, 0));
     return BC_OK;
 }
