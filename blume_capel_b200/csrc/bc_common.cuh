@@ -73,6 +73,9 @@ struct SweepParams {
     int n_replicas;
     int open;                // 1 = open boundary (off-lattice neighbours are spin 0)
     uint32_t key0, key1;     // Philox key of replica 0; replica r uses (key0, key1 ^ r)
+    int Ly;                  // owned rows (== rows_arr unless ghost rows are present)
+    uint8_t* peer_prev;      // HALO kernels: the rank above's array of the colour being updated (peer memory);
+    uint8_t* peer_next;      //   the rank below's.  nullptr at an open edge.
 };
 
 }  // namespace bc

@@ -89,6 +89,7 @@ struct bc_engine {
     cudaStream_t halo_stream = nullptr;  // high-priority side stream for the slab halo exchange
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
     int opt_overlap = 1;
+    int opt_fused_halo = 1;  // peer-memory slabs: halo stores issued by the boundary-strip kernel itself
     size_t colour_bytes = 0;  // bytes of one colour array (all replicas)
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
@@ -386,7 +387,8 @@ extern "C" int bc_get_table(const bc_engine* e, int replica, uint32_t thr31[54])
 // of the rank above and its last owned row to the top ghost row of the rank below (periodic wrap; an
 // open lattice keeps code-1 ghost rows at the global edges).  32 KiB per message at L = 65536.
 // ---------------------------------------------------------------------------------------------
-static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr) {
+// fused = true: the boundary-strip kernel already stored the halo rows into the neighbours (peer-memory mode)
+static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr, bool fused = false) {
     if (!e->ghost) return BC_OK;
     if (!stream) stream = e->stream;
     const bool periodic = e->boundary == BC_PERIODIC;
@@ -404,14 +406,17 @@ static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr) {
     const int next = dn < e->nranks ? dn : (periodic ? 0 : -1);
     if (e->p2p) {
         // direct stores into the neighbours' ghost rows over NVLink, then publish the epoch in their flags
-        const long long total = 2LL * (e->Wc / 16) * e->n_rep;
-        halo_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-            e->d_c[col], prev >= 0 ? e->peer_prev_c[col] : nullptr, next >= 0 ? e->peer_next_c[col] : nullptr,
-            geom_of(e), e->n_rep);
+        if (!fused) {
+            const long long total = 2LL * (e->Wc / 16) * e->n_rep;
+            halo_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+                e->d_c[col], prev >= 0 ? e->peer_prev_c[col] : nullptr, next >= 0 ? e->peer_next_c[col] : nullptr,
+                geom_of(e), e->n_rep);
+            ++e->launches;
+        }
         ++e->halo_epoch;
         halo_signal_kernel<<<1, 1, 0, stream>>>(prev >= 0 ? e->peer_prev_flags : nullptr,
                                                 next >= 0 ? e->peer_next_flags : nullptr, e->halo_epoch);
-        e->launches += 2;
+        ++e->launches;
         BC_CUDA(e, cudaGetLastError());
         return BC_OK;
     }
@@ -561,7 +566,16 @@ static fast_fn fast_open(bool open) {
     return open ? (fast_fn)sweep_fast_kernel<COL, SMALL, MEAS, true> : (fast_fn)sweep_fast_kernel<COL, SMALL, MEAS, false>;
 }
 
-static fast_fn pick_fast(int col, bool small, bool meas, bool open) {
+template <int COL, bool MEAS>
+static fast_fn fast_halo(bool open) {
+    return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true>;
+}
+
+static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false) {
+    if (halo && !small) {
+        if (col == 0) return meas ? fast_halo<0, true>(open) : fast_halo<0, false>(open);
+        return meas ? fast_halo<1, true>(open) : fast_halo<1, false>(open);
+    }
     if (col == 0) {
         if (!small) return meas ? fast_open<0, false, true>(open) : fast_open<0, false, false>(open);
         return meas ? fast_open<0, true, true>(open) : fast_open<0, true, false>(open);
@@ -630,6 +644,16 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.row_first = e->row_first;
     P.rows_per_strip = plan.rows;
     P.y_rng_off = e->y_glob0 - e->row_first;
+    P.Ly = e->Ly;
+    P.peer_prev = nullptr;
+    P.peer_next = nullptr;
+    // boundary-strip launch of a peer-memory slab: the kernel itself stores the halo rows into the neighbours
+    const bool fused_halo = part == 1 && e->p2p && e->opt_fused_halo && plan.fast && !plan.small;
+    if (fused_halo) {
+        const bool periodic = e->boundary == BC_PERIODIC;
+        if (e->rank > 0 || periodic) P.peer_prev = e->peer_prev_c[col];
+        if (e->rank + 1 < e->nranks || periodic) P.peer_next = e->peer_next_c[col];
+    }
     P.Wc = e->Wc;
     P.cpr = plan.cpr;
     P.strips = plan.strips;
@@ -644,7 +668,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
-        fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN);
+        fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN, fused_halo);
         if (e->opt_pdl) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
@@ -712,7 +736,7 @@ static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure
     int rc = halo_wait(e, e->halo_stream);
     if (rc != BC_OK) return rc;
     launch_half(e, plan, col, measure, t, slot, nullptr, 1, e->halo_stream);
-    rc = exchange_halo(e, col, e->halo_stream);
+    rc = exchange_halo(e, col, e->halo_stream, e->p2p && e->opt_fused_halo);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaEventRecord(e->ev_halo, e->halo_stream));
     launch_half(e, plan, col, measure, t, slot, nullptr, 2, e->stream);
@@ -1017,6 +1041,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
+    if (n == "fused_halo") { e->opt_fused_halo = value != 0; return BC_OK; }
     if (n == "overlap") { e->opt_overlap = value != 0; return BC_OK; }
     if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }

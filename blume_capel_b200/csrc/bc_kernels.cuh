@@ -204,7 +204,10 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #define BC_FAST_MIN_BLOCKS 6
 #endif
 
-template <int COL, bool SMALL, bool MEASURE, bool OPEN>
+//   HALO  = true : slab boundary-strip launch in peer-memory mode: the thread that produces a chunk of the
+//                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank
+//                  above / below (peer pointers over NVLink): compute and halo transfer are one kernel.
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false>
 __global__ void __launch_bounds__(FAST_THREADS, (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
@@ -276,8 +279,19 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
-        *reinterpret_cast<uint4*>(own_col + off) =
-            update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+        if (!HALO) {
+            *reinterpret_cast<uint4*>(own_col + off) =
+                update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+        } else {
+            const uint4 nv = update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            *reinterpret_cast<uint4*>(own_col + off) = nv;
+            // fused halo transfer: first owned row -> bottom ghost row of the rank above, last owned row -> top
+            // ghost row of the rank below (same array geometry on every rank)
+            if (P.peer_prev && off == (uint32_t)P.row_first * Wc)
+                *reinterpret_cast<uint4*>(P.peer_prev + rep_base + (size_t)(P.Ly + 1) * Wc + (size_t)j * 16) = nv;
+            if (P.peer_next && off == (uint32_t)(P.row_first + P.Ly - 1) * Wc)
+                *reinterpret_cast<uint4*>(P.peer_next + rep_base + (size_t)j * 16) = nv;
+        }
     };
 
     // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour

@@ -35,6 +35,8 @@ if P2P and world > 1:  # halo rows by direct peer stores instead of NCCL send/re
     blobs = [bytes(t.cpu().numpy().tobytes()) for t in allb]
     e.ipc_connect(blobs[(rank - 1) % world], blobs[(rank + 1) % world])
     dist.barrier()
+FUSED = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+e.set_option("fused_halo", FUSED)
 e.set_params(0.608, 1.966, 1.0)
 e.init_random()
 e.sweep(5)
@@ -49,7 +51,7 @@ tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
 if dist: dist.all_reduce(tms, op=dist.ReduceOp.MAX)
 if rank == 0:
     ups = float(L) * L * SWEEPS / (tms.item() * 1e6)
-    print(json.dumps({"config": f"L={L} periodic int8, {world} row slab(s), halo exchange per half-sweep by " + ("peer stores over NVLink (CUDA IPC) + epoch flags" if P2P and world > 1 else "NCCL send/recv"),
+    print(json.dumps({"config": f"L={L} periodic int8, {world} row slab(s), halo exchange per half-sweep by " + (("peer stores fused into the boundary-strip kernel" if FUSED else "peer stores (separate push kernel)") + " over NVLink (CUDA IPC) + epoch flags" if P2P and world > 1 else "NCCL send/recv"),
                       "n_gpus": world, "sweeps": SWEEPS, "ms": tms.item(), "updates_per_ns": ups,
                       "updates_per_ns_per_gpu": ups / world, "hbm_frac_per_gpu": ups / world * 3 / 6546.2,
                       "M": int(obs[0, 0]["M"]), "Q": int(obs[0, 0]["Q"]), "B": int(obs[0, 0]["B"])}), flush=True)
