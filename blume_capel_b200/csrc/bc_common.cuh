@@ -16,6 +16,8 @@ constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t STREAM_COARSE = 0u;
 constexpr uint32_t STREAM_FINE = 1u;
 constexpr uint32_t STREAM_INIT = 2u;
+constexpr uint32_t STREAM_BOND = 3u;
+constexpr uint32_t STREAM_FLIP = 4u;
 
 constexpr int TABLE_ENTRIES = 54;        // 18*c + 9*flip + S
 constexpr int TAB16_WORDS = 27;          // 54 x u16 -> 27 words: every entry in its own bank

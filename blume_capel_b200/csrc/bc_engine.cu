@@ -114,6 +114,13 @@ struct bc_engine {
     cudaGraphExec_t graph_exec = nullptr;
     int graph_rows = -1, graph_block = 0;  // plan signature the graph was captured for
     unsigned graph_grid = 0;
+    // cluster move scratch
+    int32_t* d_parent = nullptr;
+    uint8_t* d_bonds = nullptr;
+    int* d_changed = nullptr;
+    size_t cluster_cap = 0;
+    int64_t cluster_step = 0;  // counter of the cluster-move RNG streams
+    std::vector<double> h_TJ;  // (T, J) per replica, for the bond probability
     // options
     int opt_use_graph = 1;
     int opt_graph_block = 16;  // sweeps per graph launch
@@ -206,6 +213,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->halo_stream) cudaStreamDestroy(e->halo_stream);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->d_clock);
+    cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_changed);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31);
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
@@ -261,6 +269,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     e->colour_bytes = (size_t)n_replicas * (size_t)e->rows_arr * (size_t)e->Wc;
     e->h_tab31.assign((size_t)n_replicas * TABLE_ENTRIES, 0u);
     e->params_set.assign((size_t)n_replicas, 0);
+    e->h_TJ.assign((size_t)n_replicas * 2, 0.0);
     auto bail = [&](const char* what, cudaError_t s) {
         g_create_error = std::string("bc_create: ") + what + ": " + cudaGetErrorString(s);
         bc_destroy(e);
@@ -364,6 +373,7 @@ extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, doub
         std::memcpy(&e->h_tab31[(size_t)r * TABLE_ENTRIES], thr, sizeof(thr));
         std::memcpy(&h16[(size_t)(r - r0) * TABLE_ENTRIES], t16, sizeof(t16));
         e->params_set[r] = 1;
+        e->h_TJ[(size_t)r * 2] = T; e->h_TJ[(size_t)r * 2 + 1] = J;
     }
     // synchronous copies: the tables are tiny and the host vectors are temporaries
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -946,6 +956,74 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
     cudaFree(d_raw);
     if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_measure: ") + cudaGetErrorString(st));
     for (int r = 0; r < e->n_rep; ++r) raw_to_obs(e, &raw[(size_t)r * OBS_RAW], e->t - 1, &out[r]);
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cluster move: Swendsen-Wang on the +-1 spins, all replicas
+// ---------------------------------------------------------------------------------------------
+extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
+    if (!e || n_updates < 0) return BC_ERR_ARG;
+    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: not available on a slab handle");
+    for (int r = 0; r < e->n_rep; ++r) {
+        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, "bc_cluster_update: bc_set_params not called for every replica");
+        if (e->h_TJ[(size_t)r * 2] != e->h_TJ[0] || e->h_TJ[(size_t)r * 2 + 1] != e->h_TJ[1])
+            return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: all replicas of the handle must share (T, J)");
+    }
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const long long N = (long long)e->L * e->L, total = N * e->n_rep;
+    int rc = ensure_stage(e, (size_t)total);
+    if (rc != BC_OK) return rc;
+    if (e->cluster_cap < (size_t)total) {
+        BC_CUDA(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_parent); cudaFree(e->d_bonds);
+        e->d_parent = nullptr; e->d_bonds = nullptr; e->cluster_cap = 0;
+        BC_CUDA(e, cudaMalloc(&e->d_parent, (size_t)total * sizeof(int32_t)));
+        BC_CUDA(e, cudaMalloc(&e->d_bonds, (size_t)total));
+        if (!e->d_changed) BC_CUDA(e, cudaMalloc(&e->d_changed, sizeof(int)));
+        e->cluster_cap = (size_t)total;
+    }
+    // bond probability p = 1 - exp(-2 J / T) (main.cpp:115) as a 32-bit threshold
+    const double p = 1 - std::exp(-2 * (1 / e->h_TJ[0]) * e->h_TJ[1]);
+    uint32_t thr = 0;
+    if (p > 0) { double q = std::floor(p * 4294967296.0 + 0.5); thr = q > 4294967295.0 ? 4294967295u : (uint32_t)q; }
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const Geom g = geom_of(e);
+    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    for (int64_t u = 0; u < n_updates; ++u) {
+        const uint32_t c_lo = (uint32_t)((uint64_t)e->cluster_step & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)e->cluster_step >> 32);
+        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], g, 0, e->n_rep);
+        sw_init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, e->n_rep,
+                                                      e->boundary == BC_OPEN, thr, k0, k1, c_lo, c_hi);
+        e->launches += 2;
+        for (int iter = 0; iter < 64; ++iter) {  // hooking + pointer jumping until no root changes
+            int changed = 0;
+            BC_CUDA(e, cudaMemsetAsync(e->d_changed, 0, sizeof(int), e->stream));
+            sw_hook_kernel<<<blocks, 256, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, e->n_rep, e->d_changed);
+            sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
+            e->launches += 2;
+            BC_CUDA(e, cudaMemcpyAsync(&changed, e->d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+            BC_CUDA(e, cudaStreamSynchronize(e->stream));
+            if (!changed) break;
+        }
+        sw_flip_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->L, e->n_rep, k0, k1, c_lo, c_hi);
+        const long long ptotal = (long long)e->n_rep * e->Ly * e->Wc;
+        pack_kernel<<<(unsigned)((ptotal + 255) / 256), 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], g, 0, e->n_rep);
+        e->launches += 2;
+        BC_CUDA(e, cudaGetLastError());
+        ++e->cluster_step;
+    }
+    return BC_OK;
+}
+
+extern "C" int bc_get_cluster_counter(const bc_engine* e, int64_t* c) {
+    if (!e || !c) return BC_ERR_ARG;
+    *c = e->cluster_step;
+    return BC_OK;
+}
+extern "C" int bc_set_cluster_counter(bc_engine* e, int64_t c) {
+    if (!e || c < 0) return BC_ERR_ARG;
+    e->cluster_step = c;
     return BC_OK;
 }
 

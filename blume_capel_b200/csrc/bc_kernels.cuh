@@ -785,4 +785,100 @@ __global__ void measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Cluster move (Swendsen-Wang on the +-1 spins; zeros never join, like wolff() of main.cpp:113-154; bond
+// probability 1 - exp(-2J/T), main.cpp:115).  Works on the row-major int8 staging copy of the lattices:
+// bonds from Philox stream 3, connected components by min-root hooking + pointer jumping (the root of a
+// cluster is its smallest site index, so the result does not depend on the order of the unions), one
+// flip bit per cluster from Philox stream 4.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t sw_find(const int32_t* __restrict__ parent, int32_t a) {
+    int32_t p = parent[a];
+    while (p != a) { a = p; p = parent[a]; }
+    return a;
+}
+
+// bonds[i]: bit 0 = bond to +x neighbour open, bit 1 = bond to +y neighbour open; parent[i] = i
+__global__ void sw_init_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, int32_t* __restrict__ parent,
+                               int L, int n_rep, int open, uint32_t bond_thr, uint32_t key0, uint32_t key1,
+                               uint32_t c_lo, uint32_t c_hi) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * n_rep) return;
+    const int rep = (int)(gid / N);
+    const int32_t i = (int32_t)(gid - (long long)rep * N);
+    const int y = i / L, x = i - y * L;
+    const int8_t* sp = spins + (size_t)rep * N;
+    const int8_t s = sp[i];
+    parent[gid] = i;
+    uint32_t b = 0;
+    if (s != 0) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)(i >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, key1 ^ (uint32_t)rep, w);
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            int nx = x + (dir == 0), ny = y + (dir == 1);
+            if (nx == L || ny == L) {
+                if (open) continue;
+                nx = nx == L ? 0 : nx;
+                ny = ny == L ? 0 : ny;
+            }
+            const int32_t j = nx + ny * L;
+            if (j != i && sp[j] == s && w[2 * (i & 1) + dir] < bond_thr) b |= 1u << dir;
+        }
+    }
+    bonds[gid] = (uint8_t)b;
+}
+
+// one hooking pass: for every open bond link the larger root under the smaller one
+__global__ void sw_hook_kernel(const uint8_t* __restrict__ bonds, int32_t* __restrict__ parent, int L, int n_rep,
+                               int* __restrict__ changed) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * n_rep) return;
+    const uint32_t b = bonds[gid];
+    if (!b) return;
+    const int rep = (int)(gid / N);
+    const int32_t i = (int32_t)(gid - (long long)rep * N);
+    const int y = i / L, x = i - y * L;
+    int32_t* par = parent + (size_t)rep * N;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        if (!(b & (1u << dir))) continue;
+        const int nx = (x + (dir == 0)) % L, ny = (y + (dir == 1)) % L;
+        int32_t ra = sw_find(par, i), rb = sw_find(par, nx + ny * L);
+        while (ra != rb) {  // link the larger root under the smaller one; retry if it stopped being a root meanwhile
+            if (ra < rb) { const int32_t t = ra; ra = rb; rb = t; }
+            const int32_t old = atomicCAS(&par[ra], ra, rb);
+            *changed = 1;
+            if (old == ra) break;      // ra was still a root: linked (trees only ever merge)
+            ra = sw_find(par, old);    // ra had been linked elsewhere: continue from the current roots
+            rb = sw_find(par, rb);
+        }
+    }
+}
+
+__global__ void sw_compress_kernel(int32_t* __restrict__ parent, long long total, int L) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    int32_t* par = parent + (gid / N) * N;
+    const int32_t i = (int32_t)(gid % N);
+    par[i] = sw_find(par, i);
+}
+
+__global__ void sw_flip_kernel(int8_t* __restrict__ spins, const int32_t* __restrict__ parent, int L, int n_rep,
+                               uint32_t key0, uint32_t key1, uint32_t c_lo, uint32_t c_hi) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * n_rep) return;
+    const int8_t s = spins[gid];
+    if (s == 0) return;
+    const int rep = (int)(gid / N);
+    const int32_t root = sw_find(parent + (size_t)rep * N, (int32_t)(gid - (long long)rep * N));
+    uint32_t w[4];
+    philox4x32_10((uint32_t)root, c_lo, c_hi, STREAM_FLIP << 1, key0, key1 ^ (uint32_t)rep, w);
+    if (w[0] & 1u) spins[gid] = (int8_t)-s;
+}
+
 }  // namespace bc

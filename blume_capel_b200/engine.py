@@ -56,6 +56,9 @@ SYMBOLS = {
     "bc_get_sweep_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_sweep_counter": (C.c_int, [_P, C.c_int64]),
     "bc_sweep": (C.c_int64, [_P, C.c_int64, C.c_int64, _P]),
+    "bc_cluster_update": (C.c_int, [_P, C.c_int64]),
+    "bc_get_cluster_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "bc_set_cluster_counter": (C.c_int, [_P, C.c_int64]),
     "bc_read_obs": (C.c_int64, [_P, _P, C.c_int64]),
     "bc_measure": (C.c_int, [_P, _P]),
     "bc_sync": (C.c_int, [_P]),
@@ -217,6 +220,20 @@ class Engine:
             return buf
         self._check(self._lib.bc_sweep(self._h, n_sweeps, measure_every, None))
         return None
+
+    def cluster_update(self, n_updates: int = 1):
+        """Swendsen-Wang move on the +-1 spins of every replica (zeros never join a cluster)."""
+        self._check(self._lib.bc_cluster_update(self._h, n_updates))
+
+    @property
+    def cluster_counter(self) -> int:
+        c = C.c_int64()
+        self._check(self._lib.bc_get_cluster_counter(self._h, C.byref(c)))
+        return c.value
+
+    @cluster_counter.setter
+    def cluster_counter(self, c: int):
+        self._check(self._lib.bc_set_cluster_counter(self._h, c))
 
     def read_obs(self, n_meas: int) -> np.ndarray:
         buf = np.zeros((n_meas, self.n_replicas), OBS_DTYPE)

@@ -9,7 +9,9 @@
 // What differs: L is a flag instead of -DL_MACRO; the lattice update is the GPU checkerboard
 // Metropolis sweep (no Wolff move); sweeps per burn-in / per sample default to the reference's
 // attempt counts (1500*N resp. 9*N step() calls of 3 sweeps each, main.cpp:342,362,159) and can be
-// set with flags; --seed makes the run reproducible (the reference seeds from random_device).
+// set with flags; --cluster-every k adds one GPU Swendsen-Wang cluster move per k sweeps (the reference
+// interleaves Wolff clusters, main.cpp:162); --seed makes the run reproducible (the reference seeds from
+// random_device).
 #include <cerrno>
 #include <cmath>
 #include <cstdint>
@@ -66,7 +68,7 @@ int main(int argc, const char* argv[]) {
         if (argc < 8) {
             std::cerr << "usage: bc_run run root burn nsteps T D J [--L n] [--boundary periodic|open] [--seed s]\n"
                          "              [--device d] [--burn-sweeps n] [--sweeps-per-sample n] [--obs file.csv]\n"
-                         "              [--no-fk] [--mkdir]\n";
+                         "              [--cluster-every k] [--no-fk] [--mkdir]\n";
             return 2;
         }
         run = std::atoi(argv[1]); root = argv[2]; burn = std::atoi(argv[3]); nsteps = std::atoi(argv[4]);
@@ -76,7 +78,7 @@ int main(int argc, const char* argv[]) {
     int L = 64, device = 0, boundary = BC_PERIODIC;
     bool have_seed = false, write_fk = true, do_mkdir = false;
     uint64_t seed = 0;
-    int64_t burn_sweeps = -1, sweeps_per_sample = -1;
+    int64_t burn_sweeps = -1, sweeps_per_sample = -1, cluster_every = 0;
     std::string obs_path;
     for (; argi < argc; ++argi) {
         const std::string a = argv[argi];
@@ -87,6 +89,7 @@ int main(int argc, const char* argv[]) {
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--burn-sweeps") burn_sweeps = std::atoll(next());
         else if (a == "--sweeps-per-sample") sweeps_per_sample = std::atoll(next());
+        else if (a == "--cluster-every") cluster_every = std::atoll(next());
         else if (a == "--obs") obs_path = next();
         else if (a == "--no-fk") write_fk = false;
         else if (a == "--mkdir") do_mkdir = true;
@@ -109,6 +112,18 @@ int main(int argc, const char* argv[]) {
 
     bc_engine* eng = nullptr;
     if (bc_create(&eng, L, boundary, 1, BC_STORAGE_INT8, device, seed) != BC_OK) return die(nullptr, "bc_create");
+    // n sweeps, with one Swendsen-Wang cluster move after every `cluster_every` sweeps if requested: the
+    // counterpart of the Wolff move the reference interleaves in step() (main.cpp:158-163)
+    auto evolve = [&](int64_t n) -> bool {
+        if (cluster_every <= 0) return bc_sweep(eng, n, 0, nullptr) >= 0;
+        while (n > 0) {
+            const int64_t k = n < cluster_every ? n : cluster_every;
+            if (bc_sweep(eng, k, 0, nullptr) < 0) return false;
+            if (k == cluster_every && bc_cluster_update(eng, 1) != BC_OK) return false;
+            n -= k;
+        }
+        return true;
+    };
     if (bc_set_params(eng, -1, T, D, J) != BC_OK) return die(eng, "bc_set_params");
     std::vector<int8_t> spins((size_t)N);
     const bool periodic = boundary == BC_PERIODIC;
@@ -116,7 +131,7 @@ int main(int argc, const char* argv[]) {
     if (burn >= 1) {
         std::cout << "burning " + sL << std::endl;  // main.cpp:338
         if (bc_init_random(eng, 0) != BC_OK) return die(eng, "bc_init_random");
-        if (bc_sweep(eng, burn_sweeps, 0, nullptr) < 0) return die(eng, "bc_sweep");
+        if (!evolve(burn_sweeps)) return die(eng, "bc_sweep");
         if (bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_download");
         if (!bcgap::write_file(burn_path, bcgap::spin_clusters_to_gap(spins.data(), L, periodic)))
             std::cerr << "bc_run: cannot write " << burn_path << " (the reference fails silently here)" << std::endl;
@@ -146,7 +161,7 @@ int main(int argc, const char* argv[]) {
     for (int i = 0; i < nsteps; ++i) {
         bc_obs o;
         // measure_every = sweeps_per_sample: one fused measurement at the end of the block when aligned
-        if (bc_sweep(eng, sweeps_per_sample, 0, nullptr) < 0) return die(eng, "bc_sweep");
+        if (!evolve(sweeps_per_sample)) return die(eng, "bc_sweep");
         if (bc_measure(eng, &o) != BC_OK) return die(eng, "bc_measure");
         if (bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_download");
         const double E = (-J * (double)o.B + D * (double)o.Q) / (double)N, m = (double)o.M / (double)N,

@@ -133,6 +133,15 @@ int bc_set_sweep_counter(bc_engine* e, int64_t t);
  * Returns the number of records written (>= 0) or a negative status. */
 int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out);
 
+/* Cluster move (the reference interleaves one Wolff cluster per 3L Metropolis attempts,
+ * main.cpp:113-154,158-163): n_updates Swendsen-Wang updates of every replica -- bonds between equal non-zero
+ * neighbours with probability 1 - exp(-2J/T) (main.cpp:115; zeros never join, main.cpp:123-130,144), every
+ * cluster flipped with probability 1/2.  Same stationary distribution as the reference's Wolff move, all
+ * clusters at once instead of one.  All replicas of the handle must share (T, J).  Has its own RNG counter. */
+int bc_cluster_update(bc_engine* e, int64_t n_updates);
+int bc_get_cluster_counter(const bc_engine* e, int64_t* c);
+int bc_set_cluster_counter(bc_engine* e, int64_t c);
+
 /* Fetch the records of the last bc_sweep that was called with out == NULL (waits for it).
  * Returns the number of records written or a negative status. */
 int64_t bc_read_obs(bc_engine* e, bc_obs* out, int64_t max_records);

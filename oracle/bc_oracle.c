@@ -205,6 +205,59 @@ int64_t bc_oracle_sweep(int L, int boundary, int8_t* spins, const uint32_t thr31
     return n_obs;
 }
 
+/* ---------------------------------------------------------------- cluster move */
+uint32_t bc_oracle_bond_threshold(double T, double J) {
+    const double p = 1 - exp(-2 * (1 / T) * J); /* main.cpp:115 */
+    if (!(p > 0)) return 0u;
+    double q = floor(p * 4294967296.0 + 0.5);
+    if (q > 4294967295.0) q = 4294967295.0;
+    return (uint32_t)q;
+}
+
+static int32_t uf_find(int32_t* parent, int32_t a) {
+    while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; }
+    return a;
+}
+
+void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
+                              int64_t cstep) {
+    const int64_t N = (int64_t)L * L;
+    int32_t* parent = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+    uint32_t key[2];
+    site_key(seed, replica, key);
+    for (int64_t i = 0; i < N; ++i) parent[i] = (int32_t)i;
+    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
+    for (int y = 0; y < L; ++y)
+        for (int x = 0; x < L; ++x) {
+            const int64_t i = x + (int64_t)y * L;
+            const int8_t s = spins[i];
+            if (s == 0) continue;
+            uint32_t ctr[4] = {(uint32_t)(i >> 1), c_lo, c_hi, BC_STREAM_BOND << 1}, w[4];
+            bc_oracle_philox4x32_10(ctr, key, w);
+            for (int dir = 0; dir < 2; ++dir) {
+                int nx = x + (dir == 0), ny = y + (dir == 1);
+                if (nx == L || ny == L) {
+                    if (boundary != BC_ORACLE_PERIODIC) continue;
+                    nx %= L; ny %= L;
+                }
+                const int64_t j = nx + (int64_t)ny * L;
+                if (j == i || spins[j] != s) continue;
+                if (w[2 * (i & 1) + dir] < bond_thr) {
+                    int32_t a = uf_find(parent, (int32_t)i), b = uf_find(parent, (int32_t)j);
+                    if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } /* root = smallest site */
+                }
+            }
+        }
+    for (int64_t i = 0; i < N; ++i) {
+        if (spins[i] == 0) continue;
+        const int32_t r = uf_find(parent, (int32_t)i);
+        uint32_t ctr[4] = {(uint32_t)r, c_lo, c_hi, BC_STREAM_FLIP << 1}, w[4];
+        bc_oracle_philox4x32_10(ctr, key, w);
+        if (w[0] & 1u) spins[i] = (int8_t)-spins[i];
+    }
+    free(parent);
+}
+
 /* ---------------------------------------------------------------- exact enumeration */
 int bc_oracle_enumerate(int L, double T, double D, double J, double out[5]) {
     if (L < 1 || L > 4) return -1;

@@ -77,6 +77,17 @@ int64_t bc_oracle_sweep(int L, int boundary, int8_t* spins, const uint32_t thr31
 void bc_oracle_half_sweep_rows(int L, int boundary, int8_t* spins, const uint32_t thr31[54], uint64_t seed,
                                uint32_t replica, int64_t t, int colour, int y0, int y1);
 
+/* Cluster move (Swendsen-Wang on the +-1 spins; zeros never join, like wolff() main.cpp:113-154):
+ * bond between equal non-zero neighbours open with probability p = 1 - exp(-2J/T) (main.cpp:115), every
+ * cluster (identified by its smallest site index) flipped with probability 1/2.  Philox streams 3 (bonds:
+ * counter (i>>1, cstep_lo, cstep_hi, 3<<1), word 2*(i&1)+dir, dir 0 = +x, 1 = +y) and 4 (flips: counter
+ * (cluster id, cstep_lo, cstep_hi, 4<<1), bit 0 of word 0).  NEW relative to the reference (which grows one
+ * Wolff cluster at a time from a non-reproducible RNG); same stationary distribution. */
+#define BC_STREAM_FLIP 4u
+uint32_t bc_oracle_bond_threshold(double T, double J);
+void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
+                              int64_t cstep);
+
 /* Counts ties (coarse 15-bit draw equal to coarse threshold) seen since last reset; diagnostics. */
 int64_t bc_oracle_tie_count(int reset);
 

@@ -48,6 +48,9 @@ def lib():
         l.bc_oracle_reference_metropolis.restype = C.c_int64
         l.bc_oracle_reference_metropolis.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                                      C.c_int64, C.c_uint64]
+        l.bc_oracle_bond_threshold.restype = C.c_uint32
+        l.bc_oracle_bond_threshold.argtypes = [C.c_double, C.c_double]
+        l.bc_oracle_cluster_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64]
         _lib = l
     return _lib
 
@@ -123,3 +126,13 @@ def reference_metropolis(lattice_i32, T, D, J, n_attempts, seed):
     assert lattice_i32.dtype == np.int32 and lattice_i32.flags.c_contiguous
     L = lattice_i32.shape[0]
     return lib().bc_oracle_reference_metropolis(L, lattice_i32.ctypes.data, T, D, J, n_attempts, seed)
+
+
+def bond_threshold(T, J=1.0):
+    return lib().bc_oracle_bond_threshold(T, J)
+
+
+def cluster_update(spins, T, J, seed, replica=0, cstep=0, boundary=PERIODIC):
+    """One Swendsen-Wang move on the +-1 spins (in place)."""
+    assert spins.dtype == np.int8 and spins.flags.c_contiguous
+    lib().bc_oracle_cluster_update(spins.shape[0], boundary, spins.ctypes.data, bond_threshold(T, J), seed, replica, cstep)

@@ -1,0 +1,79 @@
+"""f-3: Swendsen-Wang cluster move on the GPU against the CPU oracle (bit-exact) and exact enumeration."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TC = (0.608, 1.966, 1.0)
+
+
+@pytest.mark.parametrize("L,boundary,T,D", [(8, 0, 0.608, 1.966), (24, 0, 2.0, 0.0), (64, 0, 0.608, 1.966), (64, 1, 1.2, 0.5),
+                                            (33, 1, 0.608, 1.966), (256, 0, 2.2691853, -1000.0), (512, 0, 0.5, 1.0)])
+def test_cluster_update_matches_oracle(bc, oracle, L, boundary, T, D):
+    n_rep, seed = 2, 0xC1 + L
+    e = bc.Engine(L, boundary, n_rep, 0, seed)
+    e.set_params(T, D, 1.0)
+    e.init_random()
+    ref = np.stack([oracle.init_random(L, seed, r) for r in range(n_rep)])
+    tab = oracle.build_table(T, D, 1.0)
+    for step in range(3):  # sweeps and cluster moves interleaved, like step() of main.cpp:158-163
+        e.sweep(2)
+        e.cluster_update(1)
+        for r in range(n_rep):
+            oracle.sweep(ref[r], tab, seed, r, 2 * step, 2, 0, boundary)
+            oracle.cluster_update(ref[r], T, 1.0, seed, r, step, boundary)
+        assert np.array_equal(e.download(), ref), (step,)
+    assert e.cluster_counter == 3
+    e.close()
+
+
+def test_cluster_update_low_temperature_giant_cluster(bc, oracle):
+    """All-plus start at low T: one cluster spans the lattice (long union-find chains)."""
+    L, seed = 128, 9
+    s = np.ones((1, L, L), np.int8)
+    s[0, 5, 7] = 0
+    s[0, 40:60, 10:30] = -1
+    e = bc.Engine(L, 0, 1, 0, seed)
+    e.set_params(0.3, 1.0, 1.0)
+    e.upload(s)
+    e.cluster_update(2)
+    ref = s[0].copy()
+    for c in range(2):
+        oracle.cluster_update(ref, 0.3, 1.0, seed, 0, c)
+    assert np.array_equal(e.download(0), ref)
+    e.close()
+
+
+def test_metropolis_plus_cluster_statistics_L4(bc):
+    """Sweeps interleaved with cluster moves still sample the Boltzmann distribution (exact enumeration)."""
+    exact = np.array([0.13644431, 0.65236652, 0.66068962])
+    L, n_rep = 4, 4096
+    e = bc.Engine(L, 0, n_rep, 0, 77)
+    e.set_params(*TC)
+    e.init_random()
+    acc = []
+    for it in range(400):
+        e.sweep(5)
+        e.cluster_update(1)
+        if it >= 100:
+            m = e.measure()
+            N = L * L
+            acc.append([((-TC[2] * m["B"] + TC[1] * m["Q"]) / N).mean(), (np.abs(m["M"]) / N).mean(), (m["Q"] / N).mean()])
+    e.close()
+    acc = np.array(acc)
+    mean = acc.mean(0)
+    err = acc.std(0, ddof=1) / np.sqrt(len(acc) / 4)  # crude allowance for autocorrelation
+    assert np.all(np.abs(mean - exact) < 5 * err + 5e-4), (mean, err)
+
+
+def test_cluster_update_errors(bc):
+    e = bc.Engine(32, 0, 2, 0, 1)
+    e.set_params(1.0, 0.0, 1.0, replica=0)
+    e.set_params(2.0, 0.0, 1.0, replica=1)
+    with pytest.raises(bc.BCError):
+        e.cluster_update(1)  # replicas at different T
+    e.close()
+    s = bc.Engine(64, 0, 1, 0, 1, slab=(1, 0, None))
+    s.set_params(1.0, 0.0, 1.0)
+    with pytest.raises(bc.BCError):
+        s.cluster_update(1)
+    s.close()

@@ -156,3 +156,34 @@ def test_row_range_half_sweeps_compose(oracle):
                 parts.append(w[y0:y1])
             b = np.concatenate(parts, 0)
     assert np.array_equal(a, b)
+
+
+def test_cluster_move_preserves_the_boltzmann_distribution(oracle):
+    """Metropolis sweeps interleaved with Swendsen-Wang moves on the +-1 spins against exact enumeration
+    (fast-mixing points; the tricritical point is covered on the GPU with thousands of replicas)."""
+    for (T, D) in ((2.0, 0.0), (2.27, -1000.0)):
+        ex = oracle.enumerate_exact(4, T, D, 1.0)
+        tab = oracle.build_table(T, D, 1.0)
+        s = oracle.init_random(4, 5, 0)
+        E, M = [], []
+        for it in range(30000):
+            oracle.sweep(s, tab, 5, 0, it, 1, 0)
+            oracle.cluster_update(s, T, 1.0, 5, 0, it)
+            m, q, b = oracle.observables(s)
+            E.append((-b + D * q) / 16)
+            M.append(abs(m) / 16)
+        assert abs(np.mean(E[1000:]) - ex["E"]) < 6e-3, (T, D)
+        assert abs(np.mean(M[1000:]) - ex["absm"]) < 6e-3, (T, D)
+
+
+def test_cluster_move_never_touches_zeros_and_only_flips_signs(oracle):
+    rng = np.random.default_rng(4)
+    s = rng.integers(-1, 2, size=(16, 16), dtype=np.int8)
+    before = s.copy()
+    oracle.cluster_update(s, 0.608, 1.0, 11, 0, 0)
+    assert np.array_equal(s == 0, before == 0)
+    assert np.array_equal(np.abs(s), np.abs(before))
+    # J = 0: no bonds, every non-zero site is its own cluster and flips with probability 1/2
+    t = np.ones((64, 64), np.int8)
+    oracle.cluster_update(t, 1.0, 0.0, 11, 0, 0)
+    assert 0.4 < (t == -1).mean() < 0.6
