@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle, ref_runner  # noqa: E402
 
 T, D, J = 0.608, 1.966, 1.0
-PLAN = {4: 2500, 8: 500, 16: 250, 32: 40}  # samples per run
+PLAN = {4: 2500, 8: 500, 16: 250, 32: 40, 64: 6}  # samples per run
 RUNS = 8
 
 

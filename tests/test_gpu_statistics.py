@@ -61,3 +61,47 @@ def test_against_unmodified_reference(bc, L, n_rep, therm, n_meas, gap):
     # E, |m|, q, U4 (chi is reported but its error bar from 8 reference runs is too crude to gate on)
     assert np.all(np.abs(z[:4]) < 4.0), dict(L=L, gpu=got.tolist(), gpu_err=err.tolist(), ref=mean.tolist(),
                                               ref_err=rerr.tolist(), z=z.tolist())
+
+
+@pytest.mark.parametrize("L,n_rep", [(32, 1024), (64, 512)])
+def test_with_cluster_moves_against_unmodified_reference(bc, L, n_rep):
+    """Same comparison with the dynamics the reference actually uses: local updates interleaved with cluster
+    moves (step() of main.cpp:158-163; here 3 sweeps + 1 Swendsen-Wang update), which decorrelates large
+    lattices at the tricritical point where checkerboard-only dynamics needs ~L^2.2 sweeps."""
+    gold = json.load(open(GOLD))
+    if str(L) not in gold:
+        pytest.skip(f"no reference statistics for L={L}")
+    ref = gold[str(L)]
+    mean, rerr = np.array(ref["mean"]), np.array(ref["err"])
+    e = bc.Engine(L, 0, n_rep, 0, 4000 + L)
+    e.set_params(*TC)
+    # all-plus start, as in the reference procedure behind the golden numbers (cluster moves flip signs
+    # but do not create or remove zeros, so the vacancy density still equilibrates through local updates)
+    e.upload(np.ones((n_rep, L, L), np.int8))
+    for _ in range(3000):  # thermalise: 9000 sweeps + 3000 cluster moves
+        e.sweep(3)
+        e.cluster_update(1)
+    N = L * L
+    samples = []
+    for k in range(40):
+        for _ in range(25):
+            e.sweep(3)
+            e.cluster_update(1)
+        o = e.measure()
+        samples.append(np.stack([(-TC[2] * o["B"] + TC[1] * o["Q"]) / N, o["M"] / N, o["Q"] / N]))
+    e.close()
+    s = np.array(samples)  # (k, 3, n_rep)
+    nb = 32
+    blocks = np.array_split(np.arange(n_rep), nb)
+
+    def est(idx):
+        m = s[:, 1][:, idx]
+        m2, m4, am = (m**2).mean(), (m**4).mean(), np.abs(m).mean()
+        return np.array([s[:, 0][:, idx].mean(), am, s[:, 2][:, idx].mean(), 1 - m4 / (3 * m2 * m2)])
+
+    full = est(np.arange(n_rep))
+    jk = np.array([est(np.concatenate([b for j, b in enumerate(blocks) if j != i])) for i in range(nb)])
+    err = np.sqrt((nb - 1) / nb * ((jk - jk.mean(0)) ** 2).sum(0))
+    z = (full - mean[:4]) / np.sqrt(err**2 + rerr[:4] ** 2)
+    assert np.all(np.abs(z) < 4.0), dict(L=L, gpu=full.tolist(), gpu_err=err.tolist(), ref=mean[:4].tolist(),
+                                         ref_err=rerr[:4].tolist(), z=z.tolist())
