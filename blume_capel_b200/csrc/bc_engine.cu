@@ -962,15 +962,9 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
 // ---------------------------------------------------------------------------------------------
 // cluster move: Swendsen-Wang on the +-1 spins, all replicas
 // ---------------------------------------------------------------------------------------------
-extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
-    if (!e || n_updates < 0) return BC_ERR_ARG;
-    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: not available on a slab handle");
-    for (int r = 0; r < e->n_rep; ++r) {
-        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, "bc_cluster_update: bc_set_params not called for every replica");
-        if (e->h_TJ[(size_t)r * 2] != e->h_TJ[0] || e->h_TJ[(size_t)r * 2 + 1] != e->h_TJ[1])
-            return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: all replicas of the handle must share (T, J)");
-    }
-    BC_CUDA(e, cudaSetDevice(e->device));
+// shared by the cluster move and the cluster-size measurement: stage the lattices row-major, draw the bonds
+// (threshold thr on Philox stream 3 at counter `cstep`), label connected components (root = smallest site)
+static int label_clusters(bc_engine* e, uint32_t thr, int64_t cstep, bool always = false) {
     const long long N = (long long)e->L * e->L, total = N * e->n_rep;
     int rc = ensure_stage(e, (size_t)total);
     if (rc != BC_OK) return rc;
@@ -983,35 +977,104 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
         if (!e->d_changed) BC_CUDA(e, cudaMalloc(&e->d_changed, sizeof(int)));
         e->cluster_cap = (size_t)total;
     }
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
+    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), 0, e->n_rep);
+    sw_init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, e->n_rep,
+                                                  e->boundary == BC_OPEN, always ? 1 : 0, thr, k0, k1, c_lo, c_hi);
+    e->launches += 2;
+    for (int iter = 0; iter < 64; ++iter) {  // hooking + pointer jumping until no root changes
+        int changed = 0;
+        BC_CUDA(e, cudaMemsetAsync(e->d_changed, 0, sizeof(int), e->stream));
+        sw_hook_kernel<<<blocks, 256, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, e->n_rep, e->d_changed);
+        sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
+        e->launches += 2;
+        BC_CUDA(e, cudaMemcpyAsync(&changed, e->d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        BC_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (!changed) break;
+    }
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int bond_threshold_of(bc_engine* e, const char* who, uint32_t* thr) {
+    for (int r = 0; r < e->n_rep; ++r) {
+        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, std::string(who) + ": bc_set_params not called for every replica");
+        if (e->h_TJ[(size_t)r * 2] != e->h_TJ[0] || e->h_TJ[(size_t)r * 2 + 1] != e->h_TJ[1])
+            return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": all replicas of the handle must share (T, J)");
+    }
     // bond probability p = 1 - exp(-2 J / T) (main.cpp:115) as a 32-bit threshold
     const double p = 1 - std::exp(-2 * (1 / e->h_TJ[0]) * e->h_TJ[1]);
+    *thr = 0;
+    if (p > 0) { double q = std::floor(p * 4294967296.0 + 0.5); *thr = q > 4294967295.0 ? 4294967295u : (uint32_t)q; }
+    return BC_OK;
+}
+
+extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
+    if (!e || n_updates < 0) return BC_ERR_ARG;
+    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: not available on a slab handle");
     uint32_t thr = 0;
-    if (p > 0) { double q = std::floor(p * 4294967296.0 + 0.5); thr = q > 4294967295.0 ? 4294967295u : (uint32_t)q; }
+    int rc = bond_threshold_of(e, "bc_cluster_update", &thr);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const long long N = (long long)e->L * e->L, total = N * e->n_rep;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    const Geom g = geom_of(e);
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     for (int64_t u = 0; u < n_updates; ++u) {
+        rc = label_clusters(e, thr, e->cluster_step);
+        if (rc != BC_OK) return rc;
         const uint32_t c_lo = (uint32_t)((uint64_t)e->cluster_step & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)e->cluster_step >> 32);
-        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], g, 0, e->n_rep);
-        sw_init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, e->n_rep,
-                                                      e->boundary == BC_OPEN, thr, k0, k1, c_lo, c_hi);
-        e->launches += 2;
-        for (int iter = 0; iter < 64; ++iter) {  // hooking + pointer jumping until no root changes
-            int changed = 0;
-            BC_CUDA(e, cudaMemsetAsync(e->d_changed, 0, sizeof(int), e->stream));
-            sw_hook_kernel<<<blocks, 256, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, e->n_rep, e->d_changed);
-            sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
-            e->launches += 2;
-            BC_CUDA(e, cudaMemcpyAsync(&changed, e->d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-            BC_CUDA(e, cudaStreamSynchronize(e->stream));
-            if (!changed) break;
-        }
         sw_flip_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->L, e->n_rep, k0, k1, c_lo, c_hi);
         const long long ptotal = (long long)e->n_rep * e->Ly * e->Wc;
-        pack_kernel<<<(unsigned)((ptotal + 255) / 256), 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], g, 0, e->n_rep);
+        pack_kernel<<<(unsigned)((ptotal + 255) / 256), 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), 0, e->n_rep);
         e->launches += 2;
         BC_CUDA(e, cudaGetLastError());
         ++e->cluster_step;
+    }
+    return BC_OK;
+}
+
+// Cluster-size moments of the current configurations (consumer gamma_nu.cpp:35-60):
+// kind 0 = geometric "spin" clusters (every bond between equal non-zero neighbours, what export_clusters
+// writes to spin/ with bond probability 1, main.cpp:369-370), kind 1 = FK clusters (bond probability
+// 1 - exp(-2J/T), main.cpp:371-372; random bonds from the measurement counter `mstep`).
+extern "C" int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_cluster_stats* out) {
+    if (!e || !out || (kind != 0 && kind != 1) || mstep < 0) return BC_ERR_ARG;
+    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_moments: not available on a slab handle");
+    uint32_t thr = 0xFFFFFFFFu;
+    bool always = true;
+    if (kind == 1) {
+        int rc0 = bond_threshold_of(e, "bc_cluster_moments", &thr);
+        if (rc0 != BC_OK) return rc0;
+        always = false;
+    }
+    BC_CUDA(e, cudaSetDevice(e->device));
+    // measurement bonds use counters above 2^62 so that they never collide with the cluster move's stream
+    int rc = label_clusters(e, thr, ((int64_t)1 << 62) + mstep, always);
+    if (rc != BC_OK) return rc;
+    const long long N = (long long)e->L * e->L, total = N * e->n_rep;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    int32_t* d_size = nullptr;
+    unsigned long long* d_out = nullptr;
+    BC_CUDA(e, cudaMalloc(&d_size, (size_t)total * sizeof(int32_t)));
+    cudaError_t st = cudaMalloc(&d_out, (size_t)e->n_rep * 3 * sizeof(unsigned long long));
+    if (st == cudaSuccess) st = cudaMemsetAsync(d_size, 0, (size_t)total * sizeof(int32_t), e->stream);
+    if (st == cudaSuccess) st = cudaMemsetAsync(d_out, 0, (size_t)e->n_rep * 3 * sizeof(unsigned long long), e->stream);
+    std::vector<unsigned long long> h((size_t)e->n_rep * 3);
+    if (st == cudaSuccess) {
+        sw_count_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, d_size, e->L, e->n_rep);
+        sw_moments_kernel<<<blocks, 256, 0, e->stream>>>(d_size, e->L, e->n_rep, d_out);
+        e->launches += 2;
+        st = cudaGetLastError();
+    }
+    if (st == cudaSuccess) st = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
+    if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+    cudaFree(d_size); cudaFree(d_out);
+    if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_cluster_moments: ") + cudaGetErrorString(st));
+    for (int r = 0; r < e->n_rep; ++r) {
+        out[r].sum_size_sq = (int64_t)h[(size_t)r * 3]; out[r].max_size = (int64_t)h[(size_t)r * 3 + 1];
+        out[r].n_clusters = (int64_t)h[(size_t)r * 3 + 2];
     }
     return BC_OK;
 }

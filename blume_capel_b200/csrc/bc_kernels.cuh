@@ -800,7 +800,7 @@ __device__ __forceinline__ int32_t sw_find(const int32_t* __restrict__ parent, i
 
 // bonds[i]: bit 0 = bond to +x neighbour open, bit 1 = bond to +y neighbour open; parent[i] = i
 __global__ void sw_init_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, int32_t* __restrict__ parent,
-                               int L, int n_rep, int open, uint32_t bond_thr, uint32_t key0, uint32_t key1,
+                               int L, int n_rep, int open, int always, uint32_t bond_thr, uint32_t key0, uint32_t key1,
                                uint32_t c_lo, uint32_t c_hi) {
     const long long N = (long long)L * L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,8 +813,8 @@ __global__ void sw_init_kernel(const int8_t* __restrict__ spins, uint8_t* __rest
     parent[gid] = i;
     uint32_t b = 0;
     if (s != 0) {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)(i >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, key1 ^ (uint32_t)rep, w);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (!always) philox4x32_10((uint32_t)(i >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, key1 ^ (uint32_t)rep, w);
 #pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
             int nx = x + (dir == 0), ny = y + (dir == 1);
@@ -824,7 +824,7 @@ __global__ void sw_init_kernel(const int8_t* __restrict__ spins, uint8_t* __rest
                 ny = ny == L ? 0 : ny;
             }
             const int32_t j = nx + ny * L;
-            if (j != i && sp[j] == s && w[2 * (i & 1) + dir] < bond_thr) b |= 1u << dir;
+            if (j != i && sp[j] == s && (always || w[2 * (i & 1) + dir] < bond_thr)) b |= 1u << dir;
         }
     }
     bonds[gid] = (uint8_t)b;
@@ -865,6 +865,31 @@ __global__ void sw_compress_kernel(int32_t* __restrict__ parent, long long total
     int32_t* par = parent + (gid / N) * N;
     const int32_t i = (int32_t)(gid % N);
     par[i] = sw_find(par, i);
+}
+
+// cluster sizes: size[root] += 1 for every non-zero site (parent compressed), then per replica
+// sum of size^2, largest size and number of clusters (gamma_nu.cpp:35-60 needs sum size^2 - max^2)
+__global__ void sw_count_kernel(const int8_t* __restrict__ spins, const int32_t* __restrict__ parent,
+                                int32_t* __restrict__ size, int L, int n_rep) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * n_rep) return;
+    if (spins[gid] == 0) return;
+    const long long rep = gid / N;
+    atomicAdd(&size[rep * N + parent[gid]], 1);
+}
+
+__global__ void sw_moments_kernel(const int32_t* __restrict__ size, int L, int n_rep,
+                                  unsigned long long* __restrict__ out /* [rep][3]: sum sq, max, count */) {
+    const long long N = (long long)L * L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= N * n_rep) return;
+    const int32_t sz = size[gid];
+    if (sz == 0) return;
+    unsigned long long* o = out + (gid / N) * 3;
+    atomicAdd(o + 0, (unsigned long long)sz * (unsigned long long)sz);
+    atomicMax(o + 1, (unsigned long long)sz);
+    atomicAdd(o + 2, 1ull);
 }
 
 __global__ void sw_flip_kernel(int8_t* __restrict__ spins, const int32_t* __restrict__ parent, int L, int n_rep,

@@ -59,6 +59,7 @@ SYMBOLS = {
     "bc_cluster_update": (C.c_int, [_P, C.c_int64]),
     "bc_get_cluster_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_cluster_counter": (C.c_int, [_P, C.c_int64]),
+    "bc_cluster_moments": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
     "bc_read_obs": (C.c_int64, [_P, _P, C.c_int64]),
     "bc_measure": (C.c_int, [_P, _P]),
     "bc_sync": (C.c_int, [_P]),
@@ -234,6 +235,12 @@ class Engine:
     @cluster_counter.setter
     def cluster_counter(self, c: int):
         self._check(self._lib.bc_set_cluster_counter(self._h, c))
+
+    def cluster_moments(self, kind: int = 0, mstep: int = 0) -> np.ndarray:
+        """Per replica (sum size^2, max size, number of clusters) of the spin (kind 0) or FK (kind 1) clusters."""
+        buf = np.zeros(self.n_replicas, np.dtype([("sum_size_sq", "<i8"), ("max_size", "<i8"), ("n_clusters", "<i8")]))
+        self._check(self._lib.bc_cluster_moments(self._h, kind, mstep, buf.ctypes.data))
+        return buf
 
     def read_obs(self, n_meas: int) -> np.ndarray:
         buf = np.zeros((n_meas, self.n_replicas), OBS_DTYPE)

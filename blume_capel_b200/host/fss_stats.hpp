@@ -50,4 +50,28 @@ inline std::string magnet_csv(const std::vector<int>& Ls, const std::vector<std:
     return out;
 }
 
+// Cluster-size susceptibility table of corner_contribution/gamma_nu.cpp:
+//   per sample S = (sum size^2 - max^2) / L^2 (gamma_nu.cpp:35-60), per run the mean over samples (:62-73),
+//   per L the mean over runs and population stdev / sqrt(nruns) (:99-117); "L Chi SE" header, to_string
+//   formatting, one extra newline at the end (:99,117,121).
+struct ClusterSample { double sum_sq, max_size; };
+inline std::string gamma_nu_table(const std::vector<int>& Ls, const std::vector<std::vector<std::vector<ClusterSample>>>& S) {
+    std::string out = "L Chi SE\n";
+    for (size_t li = 0; li < Ls.size(); ++li) {
+        const int L = Ls[li];
+        const size_t nruns = S[li].size();
+        std::vector<double> stat(nruns);
+        for (size_t r = 0; r < nruns; ++r) {
+            double tot = 0;
+            // +1: the reference counts the blank last line of every cluster file as a "cluster" of size -1
+            // (count_size("") = -1 passes the `size == 0` filter, gamma_nu.cpp:24-33,44-49); kept for parity
+            for (const ClusterSample& c : S[li][r]) tot += (c.sum_sq + 1.0 - c.max_size * c.max_size) / (L * L);
+            stat[r] = tot / (double)S[li][r].size();
+        }
+        out += std::to_string(L) + " " + std::to_string(mean(stat)) + " " + std::to_string(stdev(stat) / std::sqrt((double)nruns)) + "\n";
+    }
+    out += "\n";
+    return out;
+}
+
 }  // namespace bcfss

@@ -142,6 +142,17 @@ int bc_cluster_update(bc_engine* e, int64_t n_updates);
 int bc_get_cluster_counter(const bc_engine* e, int64_t* c);
 int bc_set_cluster_counter(bc_engine* e, int64_t c);
 
+/* Cluster-size moments of the current configurations (what gamma_nu.cpp:35-60 derives from
+ * the line lengths of a cluster file): kind 0 = geometric "spin" clusters (the content of spin/ files, bond
+ * probability 1, main.cpp:369-370), kind 1 = FK clusters (bond probability 1 - exp(-2J/T), main.cpp:371-372,
+ * bonds drawn from Philox stream 3 at the measurement counter mstep).  out: n_replicas records. */
+typedef struct {
+    int64_t sum_size_sq; /* sum over clusters of size^2 */
+    int64_t max_size;    /* size of the largest cluster */
+    int64_t n_clusters;
+} bc_cluster_stats;
+int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_cluster_stats* out);
+
 /* Fetch the records of the last bc_sweep that was called with out == NULL (waits for it).
  * Returns the number of records written or a negative status. */
 int64_t bc_read_obs(bc_engine* e, bc_obs* out, int64_t max_records);

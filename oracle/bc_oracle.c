@@ -219,8 +219,9 @@ static int32_t uf_find(int32_t* parent, int32_t a) {
     return a;
 }
 
-void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
-                              int64_t cstep) {
+/* union-find over the open bonds; parent[] ends up holding the smallest site index of each cluster */
+static int32_t* label_clusters(int L, int boundary, const int8_t* spins, int always, uint32_t bond_thr, uint64_t seed,
+                               uint32_t replica, int64_t cstep) {
     const int64_t N = (int64_t)L * L;
     int32_t* parent = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
     uint32_t key[2];
@@ -232,8 +233,8 @@ void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_
             const int64_t i = x + (int64_t)y * L;
             const int8_t s = spins[i];
             if (s == 0) continue;
-            uint32_t ctr[4] = {(uint32_t)(i >> 1), c_lo, c_hi, BC_STREAM_BOND << 1}, w[4];
-            bc_oracle_philox4x32_10(ctr, key, w);
+            uint32_t ctr[4] = {(uint32_t)(i >> 1), c_lo, c_hi, BC_STREAM_BOND << 1}, w[4] = {0, 0, 0, 0};
+            if (!always) bc_oracle_philox4x32_10(ctr, key, w);
             for (int dir = 0; dir < 2; ++dir) {
                 int nx = x + (dir == 0), ny = y + (dir == 1);
                 if (nx == L || ny == L) {
@@ -242,19 +243,47 @@ void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_
                 }
                 const int64_t j = nx + (int64_t)ny * L;
                 if (j == i || spins[j] != s) continue;
-                if (w[2 * (i & 1) + dir] < bond_thr) {
+                if (always || w[2 * (i & 1) + dir] < bond_thr) {
                     int32_t a = uf_find(parent, (int32_t)i), b = uf_find(parent, (int32_t)j);
                     if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } /* root = smallest site */
                 }
             }
         }
+    for (int64_t i = 0; i < N; ++i) parent[i] = uf_find(parent, (int32_t)i);
+    return parent;
+}
+
+void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
+                              int64_t cstep) {
+    const int64_t N = (int64_t)L * L;
+    int32_t* parent = label_clusters(L, boundary, spins, 0, bond_thr, seed, replica, cstep);
+    uint32_t key[2];
+    site_key(seed, replica, key);
+    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
     for (int64_t i = 0; i < N; ++i) {
         if (spins[i] == 0) continue;
-        const int32_t r = uf_find(parent, (int32_t)i);
-        uint32_t ctr[4] = {(uint32_t)r, c_lo, c_hi, BC_STREAM_FLIP << 1}, w[4];
+        uint32_t ctr[4] = {(uint32_t)parent[i], c_lo, c_hi, BC_STREAM_FLIP << 1}, w[4];
         bc_oracle_philox4x32_10(ctr, key, w);
         if (w[0] & 1u) spins[i] = (int8_t)-spins[i];
     }
+    free(parent);
+}
+
+/* sum size^2, max size, number of clusters (what gamma_nu.cpp:35-60 derives from a cluster file);
+ * kind 0 = spin clusters (every equal-sign bond), kind 1 = FK clusters (bonds at counter 2^62 + mstep) */
+void bc_oracle_cluster_moments(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                               uint32_t replica, int64_t mstep, int64_t out[3]) {
+    const int64_t N = (int64_t)L * L;
+    int32_t* parent = label_clusters(L, boundary, spins, kind == 0, bond_thr, seed, replica, ((int64_t)1 << 62) + mstep);
+    int32_t* size = (int32_t*)calloc((size_t)N, sizeof(int32_t));
+    for (int64_t i = 0; i < N; ++i) if (spins[i] != 0) ++size[parent[i]];
+    out[0] = out[1] = out[2] = 0;
+    for (int64_t i = 0; i < N; ++i) if (size[i]) {
+        out[0] += (int64_t)size[i] * size[i];
+        if (size[i] > out[1]) out[1] = size[i];
+        ++out[2];
+    }
+    free(size);
     free(parent);
 }
 

@@ -88,6 +88,9 @@ uint32_t bc_oracle_bond_threshold(double T, double J);
 void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
                               int64_t cstep);
 
+void bc_oracle_cluster_moments(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                               uint32_t replica, int64_t mstep, int64_t out[3]);
+
 /* Counts ties (coarse 15-bit draw equal to coarse threshold) seen since last reset; diagnostics. */
 int64_t bc_oracle_tie_count(int reset);
 

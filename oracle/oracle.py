@@ -51,6 +51,8 @@ def lib():
         l.bc_oracle_bond_threshold.restype = C.c_uint32
         l.bc_oracle_bond_threshold.argtypes = [C.c_double, C.c_double]
         l.bc_oracle_cluster_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64]
+        l.bc_oracle_cluster_moments.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32,
+                                                C.c_int64, C.c_void_p]
         _lib = l
     return _lib
 
@@ -136,3 +138,12 @@ def cluster_update(spins, T, J, seed, replica=0, cstep=0, boundary=PERIODIC):
     """One Swendsen-Wang move on the +-1 spins (in place)."""
     assert spins.dtype == np.int8 and spins.flags.c_contiguous
     lib().bc_oracle_cluster_update(spins.shape[0], boundary, spins.ctypes.data, bond_threshold(T, J), seed, replica, cstep)
+
+
+def cluster_moments(spins, kind, T, J, seed, replica=0, mstep=0, boundary=PERIODIC):
+    """(sum size^2, max size, number of clusters) of the spin (kind 0) or FK (kind 1) clusters."""
+    s = np.ascontiguousarray(spins, np.int8)
+    out = np.zeros(3, np.int64)
+    lib().bc_oracle_cluster_moments(s.shape[0], boundary, s.ctypes.data, kind, bond_threshold(T, J), seed, replica, mstep,
+                                    out.ctypes.data)
+    return tuple(int(x) for x in out)

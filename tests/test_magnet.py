@@ -30,3 +30,48 @@ def test_bc_magnet_on_gpu(tmp_path):
     for r in rows[1:]:
         b, L, chi, err = r.split(",")
         assert int(L) in (32, 64) and float(chi) > 0 and float(err) >= 0
+
+
+GAMMA_TOOL = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gamma_nu")
+
+
+def test_gamma_nu_table_is_byte_identical_to_the_reference_tool(tmp_path):
+    """gamma_nu_expected.txt was written by the unmodified gamma_nu.cpp from cluster files; bc_gamma_nu prints the
+    same bytes from (sum size^2, max size) per sample -- including the reference's +1 from the blank last line."""
+    if not os.access(GAMMA_TOOL, os.X_OK):
+        pytest.skip("bc_gamma_nu not built")
+    out = tmp_path / "g.txt"
+    subprocess.run([GAMMA_TOOL, str(out), "--from-s", os.path.join(GOLD, "gamma_nu_samples.txt")], check=True)
+    assert out.read_bytes() == open(os.path.join(GOLD, "gamma_nu_expected.txt"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_cluster_moments_on_gpu_match_oracle(tmp_path):
+    import numpy as np
+    import blume_capel_b200 as bc
+    from oracle import oracle
+    rng = np.random.default_rng(6)
+    for L, b in ((12, 0), (32, 0), (64, 1), (100, 0)):
+        s = rng.integers(-1, 2, size=(3, L, L), dtype=np.int8)
+        e = bc.Engine(L, b, 3, 0, 321)
+        e.set_params(0.608, 1.966, 1.0)
+        e.upload(s)
+        for kind in (0, 1):
+            got = e.cluster_moments(kind, mstep=7)
+            for r in range(3):
+                want = oracle.cluster_moments(s[r], kind, 0.608, 1.0, 321, r, 7, b)
+                assert (got[r]["sum_size_sq"], got[r]["max_size"], got[r]["n_clusters"]) == want, (L, b, kind, r)
+        assert np.array_equal(e.download(), s)  # measuring does not change the lattice
+        e.close()
+
+
+@pytest.mark.gpu
+def test_bc_gamma_nu_on_gpu(tmp_path):
+    out = tmp_path / "g.txt"
+    subprocess.run([GAMMA_TOOL, str(out), "0.608", "1.966", "1.0", "--L", "12,32", "--runs", "8", "--samples", "10",
+                    "--burn-sweeps", "300", "--kind", "fk", "--seed", "3"], check=True)
+    rows = out.read_text().strip().splitlines()
+    assert rows[0] == "L Chi SE" and len(rows) == 3
+    for r in rows[1:]:
+        L, chi, se = r.split(" ")
+        assert int(L) in (12, 32) and float(chi) >= 0 and float(se) >= 0
