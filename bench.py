@@ -315,6 +315,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(os.path.join(ROOT, "blume_capel_b200", "libbc_engine.so")) and rank == 0:
+        import __graft_entry__  # built artefacts are git-ignored: build once if the checkout has none
+        __graft_entry__.build()
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
