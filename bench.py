@@ -212,11 +212,15 @@ def run_ours(args, rank, world, local_rank):
     # ---- way a caller with many batches would: while one batch is swept, the other batch's lattices are
     # ---- uploaded / downloaded.  Every step still uploads its 1 GiB of input lattices and reads back its
     # ---- observables and its 1 GiB of final lattices inside the timed region.
-    eng2 = bc.Engine(L, bc.PERIODIC, N_REPLICAS, local_rank, SEED + (rank << 40) + 1)
-    eng2.set_params(T, D, J)
-    engs = [eng, eng2]
+    n_handles = max(2, args.e2e_handles)
+    extra = []
+    for k in range(1, n_handles):
+        e_k = bc.Engine(L, bc.PERIODIC, N_REPLICAS, local_rank, SEED + (rank << 40) + k)
+        e_k.set_params(T, D, J)
+        extra.append(e_k)
+    engs = [eng] + extra
     hosts = []
-    for k in range(2):
+    for k in range(n_handles):
         h = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True).numpy()
         eng.download(out=h)
         hosts.append(h)
@@ -224,9 +228,9 @@ def run_ours(args, rank, world, local_rank):
 
     def e2e_steps(n):
         nonlocal obs_buf
-        pending = [False, False]
+        pending = [False] * n_handles
         for i in range(n):
-            k = i & 1
+            k = i % n_handles
             e = engs[k]
             if pending[k]:
                 obs_buf = e.read_obs(n_meas)                 # waits for step i-2 on this handle (d2h observables)
@@ -234,12 +238,12 @@ def run_ours(args, rank, world, local_rank):
             e.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
             e.download_async(hosts[k])                        # d2h: the step's final lattices (the sample dump)
             pending[k] = True
-        for k in range(2):
+        for k in range(n_handles):
             if pending[k]:
                 obs_buf = engs[k].read_obs(n_meas)
                 engs[k].sync()
 
-    e2e_steps(min(args.warmup, 2))
+    e2e_steps(max(min(args.warmup, 2), n_handles))
     barrier()
     t0 = time.perf_counter()
     e2e_steps(args.steps)
@@ -299,7 +303,8 @@ def run_ours(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     eng.close()
-    eng2.close()
+    for e_k in extra:
+        e_k.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -311,6 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-handles", type=int, default=3, help="handles (streams) the end-to-end loop pipelines over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
