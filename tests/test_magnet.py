@@ -75,3 +75,38 @@ def test_bc_gamma_nu_on_gpu(tmp_path):
     for r in rows[1:]:
         L, chi, se = r.split(" ")
         assert int(L) in (12, 32) and float(chi) >= 0 and float(se) >= 0
+
+
+def test_gap_histogram_is_byte_identical_to_the_reference_tool(tmp_path):
+    """gap_stats_expected.json holds per-run outputs of the unmodified gap_size_statistics.cpp; bc_gap_stats
+    must reproduce them from cluster files that bc_gaptool writes for the same lattices."""
+    import json
+    import numpy as np
+    tool = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gap_stats")
+    gaptool = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gaptool")
+    if not (os.access(tool, os.X_OK) and os.access(gaptool, os.X_OK)):
+        pytest.skip("host tools not built")
+    lat = np.load(os.path.join(GOLD, "gap_stats_lattices.npz"))
+    want = json.load(open(os.path.join(GOLD, "gap_stats_expected.json")))
+    for key, expected in want.items():
+        L = int(key[1:3])
+        files = []
+        for i in range(3):
+            raw = tmp_path / f"{key}_{i}.bin"
+            raw.write_bytes(lat[f"{key}_s{i}"].astype(np.int8).tobytes())
+            txt = tmp_path / f"{key}_{i}.txt"
+            subprocess.run([gaptool, "write", str(L), "periodic", str(raw), str(txt)], check=True)
+            files.append(str(txt))
+        out = tmp_path / f"{key}.out"
+        subprocess.run([tool, "hist", str(out), str(L)] + files, check=True)
+        assert out.read_text() == expected, key
+
+
+@pytest.mark.gpu
+def test_bc_gap_stats_on_gpu(tmp_path):
+    tool = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gap_stats")
+    subprocess.run([tool, "run", str(tmp_path / "gap"), "0.608", "1.966", "1.0", "--L", "48", "--runs", "6", "--samples", "4",
+                    "--burn-sweeps", "200", "--kind", "spin", "--seed", "2"], check=True)
+    for r in range(6):
+        rows = (tmp_path / "gap" / "48" / f"{r}.txt").read_text().split("\n")
+        assert rows[0] == "4" and len(rows[1].split()) == 24 and sum(map(int, rows[1].split())) > 0
