@@ -317,3 +317,46 @@ def test_resident_per_replica_parameters_and_counter_offset(bc, oracle):
         assert np.array_equal(got[r], ref), r
         assert np.array_equal(obs[:, r]["B"], ro["B"]) and np.array_equal(obs[:, r]["sweep"], ro["sweep"])
     e.close()
+
+
+def test_randomised_configurations(bc, oracle):
+    """40 seeded random configurations across every dispatch path (generic / streaming / resident / slab
+    handle), both boundaries, ragged sizes, random parameters, replica counts, call splits and counter
+    offsets: lattice and observables must equal the oracle bit for bit."""
+    rng = np.random.default_rng(20261020)
+    for case in range(40):
+        boundary = int(rng.integers(0, 2))
+        kind = rng.choice(["generic", "stream", "resident", "slab"])
+        if kind == "generic":
+            L = int(rng.choice([2, 4, 6, 10, 14, 18, 22, 30, 34, 50]) if boundary == 0 else rng.integers(2, 60))
+        else:
+            L = int(rng.choice([32, 64, 96, 128, 160, 256]))
+        n_rep = int(rng.integers(1, 5))
+        T = float(rng.uniform(0.3, 3.0)); D = float(rng.uniform(-2.0, 2.5)); J = float(rng.choice([1.0, 1.0, 0.5, -1.0]))
+        seed = int(rng.integers(0, 2**63))
+        t0 = int(rng.choice([0, 7, (1 << 32) - 3, (1 << 40) + 1]))
+        chunks = [int(c) for c in rng.integers(1, 6, size=int(rng.integers(1, 4)))]
+        me = int(rng.choice([0, 1, 2, 3]))
+        slab = (1, 0, None) if kind == "slab" else None
+        e = bc.Engine(L, boundary, n_rep, 0, seed, slab=slab)
+        if kind == "stream":
+            e.set_option("resident", 0)
+            e.set_option("rows_per_thread", int(rng.choice([0, 1, 2, 4, 8])))
+        if kind == "resident":
+            e.set_option("resident", 1)
+        e.set_params(T, D, J)
+        e.init_random()
+        e.sweep_counter = t0
+        tab = oracle.build_table(T, D, J)
+        ref = np.stack([oracle.init_random(L, seed, r) for r in range(n_rep)])
+        t = t0
+        for c in chunks:
+            obs = e.sweep(c, me)
+            for r in range(n_rep):
+                ro = oracle.sweep(ref[r], tab, seed, r, t, c, me, boundary)
+                if me:
+                    for f in ("sweep", "M", "Q", "B"):
+                        assert np.array_equal(obs[:, r][f], ro[f]), (case, kind, L, boundary, f)
+            t += c
+        assert np.array_equal(e.download(), ref), (case, kind, L, boundary, n_rep, T, D, J, t0, chunks)
+        e.close()
