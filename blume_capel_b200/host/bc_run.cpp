@@ -68,7 +68,7 @@ int main(int argc, const char* argv[]) {
         if (argc < 8) {
             std::cerr << "usage: bc_run run root burn nsteps T D J [--L n] [--boundary periodic|open] [--seed s]\n"
                          "              [--device d] [--burn-sweeps n] [--sweeps-per-sample n] [--obs file.csv]\n"
-                         "              [--cluster-every k] [--no-fk] [--mkdir]\n";
+                         "              [--cluster-every k] [--no-fk] [--mkdir] [--save-state f] [--load-state f]\n";
             return 2;
         }
         run = std::atoi(argv[1]); root = argv[2]; burn = std::atoi(argv[3]); nsteps = std::atoi(argv[4]);
@@ -79,7 +79,7 @@ int main(int argc, const char* argv[]) {
     bool have_seed = false, write_fk = true, do_mkdir = false;
     uint64_t seed = 0;
     int64_t burn_sweeps = -1, sweeps_per_sample = -1, cluster_every = 0;
-    std::string obs_path;
+    std::string obs_path, save_state, load_state;
     for (; argi < argc; ++argi) {
         const std::string a = argv[argi];
         auto next = [&]() -> const char* { return argi + 1 < argc ? argv[++argi] : ""; };
@@ -91,6 +91,8 @@ int main(int argc, const char* argv[]) {
         else if (a == "--sweeps-per-sample") sweeps_per_sample = std::atoll(next());
         else if (a == "--cluster-every") cluster_every = std::atoll(next());
         else if (a == "--obs") obs_path = next();
+        else if (a == "--save-state") save_state = next();
+        else if (a == "--load-state") load_state = next();
         else if (a == "--no-fk") write_fk = false;
         else if (a == "--mkdir") do_mkdir = true;
         else { std::cerr << "bc_run: unknown flag " << a << std::endl; return 2; }
@@ -139,17 +141,46 @@ int main(int argc, const char* argv[]) {
         if (burn == 1) { bc_destroy(eng); return 0; }
     }
 
-    // If not burning in, grab the burned-in lattice (main.cpp:358)
-    std::string text;
-    if (!bcgap::read_file(burn_path, text) || !bcgap::gap_to_lattice(text, L, spins.data())) {
-        std::cerr << "bc_run: cannot read burn file " << burn_path << std::endl;
-        bc_destroy(eng);
-        return 1;
+    // If not burning in, grab the burned-in lattice (main.cpp:358) -- or an exact checkpoint: the reference saves no
+    // RNG state; here (lattice, seed, sweep counter, cluster counter) is the whole state of the run
+    struct StateHeader { char magic[8]; int32_t L, boundary; uint64_t seed; int64_t sweep, cluster; };
+    int first_sample = 0;
+    if (!load_state.empty()) {
+        std::string raw;
+        StateHeader h;
+        if (!bcgap::read_file(load_state, raw) || raw.size() != sizeof(h) + sizeof(int32_t) + (size_t)N) {
+            std::cerr << "bc_run: cannot read state file " << load_state << std::endl;
+            bc_destroy(eng);
+            return 1;
+        }
+        std::memcpy(&h, raw.data(), sizeof(h));
+        int32_t done = 0;
+        std::memcpy(&done, raw.data() + sizeof(h), sizeof(done));
+        if (std::memcmp(h.magic, "BCSTATE1", 8) != 0 || h.L != L || h.boundary != boundary) {
+            std::cerr << "bc_run: state file does not match this run" << std::endl;
+            bc_destroy(eng);
+            return 1;
+        }
+        bc_destroy(eng);  // the seed is part of the state: recreate the handle with it
+        seed = h.seed;
+        if (bc_create(&eng, L, boundary, 1, BC_STORAGE_INT8, device, seed) != BC_OK) return die(nullptr, "bc_create");
+        if (bc_set_params(eng, -1, T, D, J) != BC_OK) return die(eng, "bc_set_params");
+        std::memcpy(spins.data(), raw.data() + sizeof(h) + sizeof(done), (size_t)N);
+        if (bc_upload(eng, 0, spins.data()) != BC_OK || bc_set_sweep_counter(eng, h.sweep) != BC_OK ||
+            bc_set_cluster_counter(eng, h.cluster) != BC_OK) return die(eng, "restore state");
+        first_sample = done;
+    } else {
+        std::string text;
+        if (!bcgap::read_file(burn_path, text) || !bcgap::gap_to_lattice(text, L, spins.data())) {
+            std::cerr << "bc_run: cannot read burn file " << burn_path << std::endl;
+            bc_destroy(eng);
+            return 1;
+        }
+        if (bc_upload(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_upload");
+        // burn = 0: continue the sweep counter after the nominal burn-in so that a collection run started
+        // with the same --seed does not replay the random numbers the burn-in consumed
+        if (burn < 1 && bc_set_sweep_counter(eng, burn_sweeps) != BC_OK) return die(eng, "bc_set_sweep_counter");
     }
-    if (bc_upload(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_upload");
-    // burn = 0: continue the sweep counter after the nominal burn-in so that a collection run started
-    // with the same --seed does not replay the random numbers the burn-in consumed
-    if (burn < 1 && bc_set_sweep_counter(eng, burn_sweeps) != BC_OK) return die(eng, "bc_set_sweep_counter");
 
     FILE* obs_file = nullptr;
     if (!obs_path.empty()) {
@@ -158,7 +189,7 @@ int main(int argc, const char* argv[]) {
     }
     double sE = 0, sAm = 0, sQ = 0, sM2 = 0, sM4 = 0;
     const double p_fk = 1 - std::exp(-2 * (1 / T) * J);  // main.cpp:371
-    for (int i = 0; i < nsteps; ++i) {
+    for (int i = first_sample; i < nsteps; ++i) {
         bc_obs o;
         // measure_every = sweeps_per_sample: one fused measurement at the end of the block when aligned
         if (!evolve(sweeps_per_sample)) return die(eng, "bc_sweep");
@@ -184,8 +215,20 @@ int main(int argc, const char* argv[]) {
         }
     }
     if (obs_file) std::fclose(obs_file);
-    if (nsteps > 0) {
-        const double n = nsteps, m2 = sM2 / n, am = sAm / n;
+    if (!save_state.empty()) {
+        StateHeader h;
+        std::memcpy(h.magic, "BCSTATE1", 8);
+        h.L = L; h.boundary = boundary; h.seed = seed;
+        if (bc_get_sweep_counter(eng, &h.sweep) != BC_OK || bc_get_cluster_counter(eng, &h.cluster) != BC_OK ||
+            bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "save state");
+        const int32_t done = nsteps;
+        std::string raw((const char*)&h, sizeof(h));
+        raw.append((const char*)&done, sizeof(done));
+        raw.append((const char*)spins.data(), (size_t)N);
+        if (!bcgap::write_file(save_state, raw)) std::cerr << "bc_run: cannot write " << save_state << std::endl;
+    }
+    if (nsteps > first_sample) {
+        const double n = nsteps - first_sample, m2 = sM2 / n, am = sAm / n;
         std::printf("{\"L\": %d, \"T\": %.10g, \"D\": %.10g, \"J\": %.10g, \"samples\": %d, \"sweeps_per_sample\": %lld, "
                     "\"E_per_site\": %.10g, \"abs_m\": %.10g, \"q\": %.10g, \"U4\": %.10g, \"chi\": %.10g, \"seed\": %llu}\n",
                     L, T, D, J, nsteps, (long long)sweeps_per_sample, sE / n, am, sQ / n, 1 - (sM4 / n) / (3 * m2 * m2),

@@ -61,3 +61,21 @@ def test_bc_run_missing_burn_file_is_an_error(tmp_path):
     r = subprocess.run([BC_RUN, "0", "nowhere", "0", "1", "0.608", "1.966", "1.0", "--L", "32"], cwd=tmp_path,
                        capture_output=True, text=True)
     assert r.returncode != 0 and "burn file" in r.stderr
+
+
+def test_bc_run_exact_checkpoint(tmp_path):
+    """(lattice, seed, sweep counter, cluster counter) restores a run exactly: 6 samples in one go equal
+    3 samples + --save-state, then --load-state + the remaining 3 (cluster moves interleaved)."""
+    common = ["--L", "64", "--seed", "99", "--burn-sweeps", "30", "--sweeps-per-sample", "12", "--cluster-every", "4",
+              "--mkdir", "--no-fk"]
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    subprocess.run([BC_RUN, "0", "d", "2", "6", "0.608", "1.966", "1.0"] + common, cwd=a, check=True, capture_output=True)
+    subprocess.run([BC_RUN, "0", "d", "2", "3", "0.608", "1.966", "1.0"] + common + ["--save-state", "state.bin"], cwd=b,
+                   check=True, capture_output=True)
+    subprocess.run([BC_RUN, "0", "d", "0", "6", "0.608", "1.966", "1.0"] + common + ["--load-state", "state.bin"], cwd=b,
+                   check=True, capture_output=True)
+    for i in range(6):
+        fa = (a / "d" / "spin" / "64" / "0" / f"{i}.txt").read_bytes()
+        fb = (b / "d" / "spin" / "64" / "0" / f"{i}.txt").read_bytes()
+        assert fa == fb, i
