@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is bound lazily with dlopen, so libbc_engine.so has no NCCL dependency
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -124,6 +125,10 @@ struct bc_engine {
     // options
     int opt_use_graph = 1;
     int opt_graph_block = 16;  // sweeps per graph launch
+    int opt_wave = 0;  // wavefront kernel for L2-resident lattices: 0 off (default: measured slower), 1 on
+    int* d_wave = nullptr;        // [0] task counter, [1] abort flag, [2..] per-block progress
+    size_t wave_cap = 0;
+    int wave_grid[2] = {0, 0};
     int opt_pdl = 1;  // programmatic dependent launch between consecutive half-sweeps
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
     bool resident_attr_set[2] = {false, false};
@@ -214,6 +219,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     cudaFree(e->d_clock);
     cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_changed);
+    cudaFree(e->d_wave);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31);
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
@@ -777,8 +783,58 @@ static int ensure_graph(bc_engine* e, const LaunchPlan& plan, int block) {
     return BC_OK;
 }
 
+// ---- wavefront kernel: all half-sweeps of a run of unmeasured sweeps in one launch (L2-resident lattices) ----
+static bool wave_eligible(const bc_engine* e, const LaunchPlan& plan, int64_t n) {
+    if (e->opt_wave == 0 || e->ghost || !plan.fast || plan.small || (plan.rows & 3) || n < 2) return false;
+    if (plan.cpr > FAST_THREADS && (plan.cpr % FAST_THREADS)) return false;  // blocks must not straddle strips
+    return e->opt_wave > 0;
+}
+
+static int run_wave(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n) {
+    const bool open = e->boundary == BC_OPEN;
+    auto fn = open ? sweep_wave_kernel<true> : sweep_wave_kernel<false>;
+    const int nblk = (int)(((long long)plan.strips * plan.cpr) / FAST_THREADS);
+    const size_t need = 2 + (size_t)e->n_rep * nblk;
+    if (e->wave_cap < need) {
+        BC_CUDA(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_wave);
+        e->d_wave = nullptr; e->wave_cap = 0;
+        BC_CUDA(e, cudaMalloc(&e->d_wave, need * sizeof(int)));
+        e->wave_cap = need;
+    }
+    if (!e->wave_grid[open]) {
+        int per_sm = 0, sms = 0;
+        BC_CUDA(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FAST_THREADS, 0));
+        BC_CUDA(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+        e->wave_grid[open] = per_sm * sms;
+    }
+    // at most 2^30 tasks per launch
+    const int64_t per_half = (int64_t)e->n_rep * nblk;
+    int64_t done = 0;
+    while (done < n) {
+        int64_t chunk = n - done;
+        if (2 * chunk * per_half > (1LL << 30)) chunk = std::max<int64_t>(1, (1LL << 29) / per_half);
+        BC_CUDA(e, cudaMemsetAsync(e->d_wave, 0, need * sizeof(int), e->stream));
+        WaveParams P;
+        P.c0 = e->d_c[0]; P.c1 = e->d_c[1]; P.tab16 = e->d_tab16; P.tab31 = e->d_tab31; P.ties = e->d_ties;
+        P.next_task = e->d_wave; P.abort = e->d_wave + 1; P.progress = e->d_wave + 2;
+        P.t0 = t0 + done; P.n_half = (int)(2 * chunk);
+        P.L = e->L; P.Wc = e->Wc; P.cpr = plan.cpr; P.rows_per_strip = plan.rows; P.strips = plan.strips;
+        P.n_replicas = e->n_rep; P.rows_arr = e->rows_arr; P.nblk = nblk;
+        P.key0 = (uint32_t)e->seed; P.key1 = (uint32_t)(e->seed >> 32);
+        const long long tasks = 2 * chunk * per_half;
+        const unsigned grid = (unsigned)std::min<long long>(tasks, e->wave_grid[open]);
+        fn<<<grid, FAST_THREADS, 0, e->stream>>>(P);
+        ++e->launches;
+        BC_CUDA(e, cudaGetLastError());
+        done += chunk;
+    }
+    return BC_OK;
+}
+
 // n unmeasured sweeps starting at sweep index t0
 static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n) {
+    if (wave_eligible(e, plan, n)) return run_wave(e, plan, t0, n);
     int64_t done = 0;
     const int block = e->opt_graph_block;
     if (e->opt_use_graph && !e->ghost && block > 0 && n >= block) {
@@ -1094,6 +1150,11 @@ extern "C" int bc_sync(bc_engine* e) {
     if (!e) return BC_ERR_ARG;
     BC_CUDA(e, cudaSetDevice(e->device));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->d_wave) {
+        int flags[2] = {0, 0};
+        BC_CUDA(e, cudaMemcpy(flags, e->d_wave, sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags[1]) return fail(e, BC_ERR_STATE, "bc_sync: the wavefront kernel timed out waiting for a dependency");
+    }
     if (e->d_halo_err) {
         int err = 0;
         BC_CUDA(e, cudaMemcpy(&err, e->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1181,6 +1242,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "wave") { e->opt_wave = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "fused_halo") { e->opt_fused_halo = value != 0; return BC_OK; }
     if (n == "overlap") { e->opt_overlap = value != 0; return BC_OK; }

@@ -360,3 +360,34 @@ def test_randomised_configurations(bc, oracle):
             t += c
         assert np.array_equal(e.download(), ref), (case, kind, L, boundary, n_rep, T, D, J, t0, chunks)
         e.close()
+
+
+@pytest.mark.parametrize("L,n_rep,rows", [(128, 1, 4), (128, 3, 8), (256, 2, 4), (512, 1, 4), (1024, 1, 8)])
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_wavefront_kernel_matches_oracle(bc, oracle, L, n_rep, rows, boundary):
+    """All half-sweeps of a call in one launch, ordered by per-block progress counters instead of kernel
+    boundaries; must equal the oracle (and hence the launch-per-half-sweep path) bit for bit."""
+    n = 7
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, n, 0x3A7E + L, measure_every=0,
+                                            opts=(("resident", 0), ("wave", 1), ("rows_per_thread", rows)))
+    assert np.array_equal(got, ref)
+
+
+def test_wavefront_kernel_large_and_launch_count(bc):
+    """L = 4096 and 8192 (one and two 128-chunk blocks per strip): wavefront == streaming, one launch per call."""
+    for L, n in ((4096, 6), (8192, 4)):
+        res = []
+        for wave in (1, 0):
+            e = bc.Engine(L, 0, 1, 0, 0xABC)
+            e.set_option("wave", wave)
+            e.set_params(*TC)
+            e.init_random()
+            e.sync()
+            l0 = e.launch_count
+            e.sweep(n)
+            launches = e.launch_count - l0
+            e.sync()
+            res.append((e.download(0), launches))
+            e.close()
+        assert np.array_equal(res[0][0], res[1][0]), L
+        assert res[0][1] == 1 and res[1][1] >= 2 * n

@@ -31,9 +31,10 @@ if __name__ == "__main__":
     tag = os.environ.get("BC_ENGINE_LIB", "default")
     cases = []
     if mode == "quick":
-        for L, nr, sw in ((4096, 1, 200), (2048, 8, 200), (1024, 8, 400), (8192, 1, 100), (16384, 1, 50)):
-            for rows in (0, 2, 4, 8, 16):
-                cases.append((L, nr, rows, sw, 0, 0))
+        for L, nr, sw in ((4096, 1, 400), (2048, 8, 200), (1024, 8, 400), (512, 8, 800), (8192, 1, 100), (2048, 1, 800)):
+            cases.append((L, nr, 0, sw, 0, 0, (("wave", 0),)))
+            for rows in (4, 8, 16):
+                cases.append((L, nr, rows, sw, 0, 0, (("wave", 1),)))
         cases.append((4096, 64, 8, 10, 0, 0))
         cases.append((4096, 64, 32, 10, 0, 0))
         cases.append((4096, 64, 0, 10, 1, 0))
