@@ -172,8 +172,15 @@ int bc_last_sweep_ms(bc_engine* e, float* ms);
  * bc_timer_start records an event, bc_timer_stop records another, waits, returns the ms between. */
 int bc_timer_start(bc_engine* e);
 int bc_timer_stop(bc_engine* e, float* ms);
-/* Select kernel variant for experiments: name/value pairs, e.g. ("rows_per_thread", 4),
- * ("use_graph", 1), ("force_generic", 1).  Unknown names give BC_ERR_ARG. */
+/* Tuning / test knobs (name, value); unknown names give BC_ERR_ARG.  Results never depend on them:
+ *   "rows_per_thread" n   rows each thread of the streaming kernel marches over (0 = auto)
+ *   "resident" -1|0|1     shared-memory-resident kernel for L <= 448 (auto / off / force)
+ *   "use_graph" 0|1, "graph_block" n   CUDA-graph replay of blocks of n unmeasured sweeps
+ *   "pdl" 0|1             programmatic dependent launch between half-sweeps
+ *   "wave" 0|1            experimental single-launch wavefront kernel (off by default)
+ *   "overlap" 0|1         slab handles: boundary strips + halo exchange concurrent with the interior
+ *   "fused_halo" 0|1      peer-memory slabs: halo stores issued by the boundary-strip kernel itself
+ *   "force_generic" 0|1   one-thread-per-site kernel for every size (second implementation, for tests) */
 int bc_set_option(bc_engine* e, const char* name, int64_t value);
 /* The launch geometry bc_sweep would use now (any pointer may be NULL). */
 int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, int* grid, int* block);
