@@ -21,6 +21,11 @@ constexpr uint32_t STREAM_FLIP = 4u;
 
 constexpr int TABLE_ENTRIES = 54;        // 18*c + 9*flip + S
 constexpr int TAB16_WORDS = 27;          // 54 x u16 -> 27 words: every entry in its own bank
+// Pair table of the streaming kernel (one lookup per two sites): word a + 54*b for the entry numbers a (low
+// halfword of the random word) and b (high halfword); 11664 bytes per replica.  The kernel's entry numbers
+// carry a bias of +9 (f+1 instead of f), folded into the base address.
+constexpr int TAB2_WORDS = TABLE_ENTRIES * TABLE_ENTRIES;
+constexpr uint32_t TAB2_BIAS = 9u * 4u + 9u * 4u * TABLE_ENTRIES;
 constexpr uint32_t ONES = 0x01010101u;   // code 1 == spin 0 in every byte
 
 // Philox4x32-10 with a runtime key.  The multiply pairs compile to IMAD.WIDE.U32.
@@ -56,6 +61,7 @@ struct SweepParams {
     const uint8_t* other;    // the other colour's array      [replica][y][Wc]
     const uint16_t* tab16;   // [replica][54] coarse thresholds incl. flip in bit 15 (see engine)
     const uint32_t* tab31;   // [replica][54] full thresholds (tie resolution)
+    const uint32_t* tab2;    // [replica][54*54] pair table (PAIR kernels) or nullptr
     unsigned long long* obs; // raw accumulators [slot][replica][OBS_RAW] or nullptr
     unsigned long long* ties;// tie counter (diagnostics)
     const int64_t* t_ptr;    // optional device-resident sweep counter (graph replay); t = *t_ptr + t

@@ -95,6 +95,7 @@ struct bc_engine {
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
     uint32_t* d_tab31 = nullptr;
+    uint32_t* d_tab2 = nullptr;   // [replica][54*54] pair tables of the streaming kernel (L % 32 == 0, L >= 256)
     std::vector<uint32_t> h_tab31;
     std::vector<uint8_t> params_set;
     unsigned long long* d_obs = nullptr;
@@ -133,6 +134,7 @@ struct bc_engine {
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
     bool resident_attr_set[2] = {false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
+    int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
     int opt_force_generic = 0;
     std::string err;
 };
@@ -145,6 +147,9 @@ struct bc_engine {
             return BC_ERR_NCCL;                                                                  \
         }                                                                                        \
     } while (0)
+
+typedef void (*fast_fn)(const SweepParams);
+static void pair_kernels(fast_fn (&out)[8]);
 
 static Geom geom_of(const bc_engine* e) {
     Geom g;
@@ -221,7 +226,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_changed);
     cudaFree(e->d_wave);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
-    cudaFree(e->d_tab16); cudaFree(e->d_tab31);
+    cudaFree(e->d_tab16); cudaFree(e->d_tab31); cudaFree(e->d_tab2);
     cudaFree(e->d_obs); cudaFree(e->d_ties); cudaFree(e->d_stage);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -291,6 +296,13 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_c[1], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
+    if (L % 32 == 0 && L >= 256 &&
+        (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
+    if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
+        fast_fn pf[8];
+        pair_kernels(pf);
+        for (fast_fn f : pf) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if ((st = cudaMalloc(&e->d_ties, sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc ties", st);
     if ((st = cudaMalloc(&e->d_clock, sizeof(int64_t))) != cudaSuccess) return bail("cudaMalloc clock", st);
     if ((st = cudaMemsetAsync(e->d_ties, 0, sizeof(unsigned long long), e->stream)) != cudaSuccess) return bail("memset", st);
@@ -387,6 +399,11 @@ extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, doub
                           (size_t)(r1 - r0) * TABLE_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice));
     BC_CUDA(e, cudaMemcpy(e->d_tab16 + (size_t)r0 * TABLE_ENTRIES, h16.data(),
                           h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (e->d_tab2) {
+        const long long words = (long long)(r1 - r0) * TAB2_WORDS;
+        pair_table_kernel<<<(unsigned)((words + 255) / 256), 256, 0, e->stream>>>(e->d_tab16, e->d_tab2, r0, r1 - r0);
+        BC_CUDA(e, cudaGetLastError());
+    }
     return BC_OK;
 }
 
@@ -575,7 +592,6 @@ extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
 // ---------------------------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------------------------
-typedef void (*fast_fn)(const SweepParams);
 
 template <int COL, bool SMALL, bool MEAS>
 static fast_fn fast_open(bool open) {
@@ -587,7 +603,25 @@ static fast_fn fast_halo(bool open) {
     return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true>;
 }
 
-static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false) {
+template <int COL, bool MEAS>
+static fast_fn fast_pair(bool open) {
+    return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, false, true>
+                : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, false, true>;
+}
+
+static void pair_kernels(fast_fn (&out)[8]) {
+    int n = 0;
+    for (int open = 0; open < 2; ++open) {
+        out[n++] = fast_pair<0, false>(open); out[n++] = fast_pair<0, true>(open);
+        out[n++] = fast_pair<1, false>(open); out[n++] = fast_pair<1, true>(open);
+    }
+}
+
+static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false, bool pair = false) {
+    if (pair && !small && !halo) {
+        if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open);
+        return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open);
+    }
     if (halo && !small) {
         if (col == 0) return meas ? fast_halo<0, true>(open) : fast_halo<0, false>(open);
         return meas ? fast_halo<1, true>(open) : fast_halo<1, false>(open);
@@ -603,6 +637,7 @@ static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = 
 struct LaunchPlan {
     bool fast = false;
     bool small = false;
+    bool pair = false;  // pair-table kernels: one replica per CTA and enough rows per thread to amortise the 11.4 KB table
     int cpr = 0, strips = 0, rows = 0;
     unsigned grid = 0;
 };
@@ -631,6 +666,7 @@ static LaunchPlan make_plan(const bc_engine* e) {
         p.rows = R;
         p.strips = Ly / R;
         p.small = (R & 1) != 0 || (((long long)p.strips * p.cpr) % FAST_THREADS) != 0;
+        p.pair = !p.small && e->d_tab2 && e->opt_pair_min_rows > 0 && R >= e->opt_pair_min_rows;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
     } else {
@@ -649,6 +685,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.other = e->d_c[1 - col];
     P.tab16 = e->d_tab16;
     P.tab31 = e->d_tab31;
+    P.tab2 = e->d_tab2;
     P.obs = e->d_obs;
     P.ties = e->d_ties;
     P.t_ptr = t_ptr;  // graph replay: t = *t_ptr + t
@@ -684,7 +721,7 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.key0 = (uint32_t)e->seed;
     P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
-        fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN, fused_halo);
+        fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN, fused_halo, plan.pair);
         if (e->opt_pdl) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
@@ -1242,6 +1279,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "pair_min_rows") { e->opt_pair_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "wave") { e->opt_wave = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "fused_halo") { e->opt_fused_halo = value != 0; return BC_OK; }
@@ -1274,7 +1312,7 @@ extern "C" int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, i
         if (block) *block = r.T * r.reps_per_cta;
         return BC_OK;
     }
-    if (fast) *fast = p.fast;
+    if (fast) *fast = p.fast ? (p.pair ? 3 : 1) : 0;  // 3 = streaming kernel with the pair table
     if (rows_per_thread) *rows_per_thread = p.rows;
     if (grid) *grid = (int)p.grid;
     if (block) *block = p.fast ? FAST_THREADS : 256;

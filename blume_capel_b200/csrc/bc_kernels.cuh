@@ -78,50 +78,59 @@ struct RowCtx {
     int64_t t;
     const char* tabm;
     const uint32_t* t31_rep;
+    uint32_t tab2s;  // PAIR: shared-space address of the pair table, biased by -TAB2_BIAS bytes
 };
 
-template <int COL, bool MEASURE>
-__device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t y, const int par, const uint4& upv,
-                                                const uint4& midv, const uint4& dnv, const uint32_t side,
-                                                const uint4& ownv, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
-                                                uint32_t& a_S, uint32_t& n_ties) {
+// Half of a chunk: the 8 sites served by one Philox call (HALF = 0: words 0,1; HALF = 1: words 2,3).
+template <int COL, bool MEASURE, int HALF, bool PAIR>
+__device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, const int par, const uint32_t (&o)[4],
+                                             const uint32_t (&u)[4], const uint32_t (&m)[4], const uint32_t (&d)[4],
+                                             const uint32_t side, const uint32_t ones_r, uint32_t (&nw)[4], uint32_t& a_c,
+                                             uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S, uint32_t& n_ties) {
     const uint32_t j = C.j, ctr2 = C.ctr2, ctr3 = C.ctr3, k0 = C.k0, k1 = C.k1;
     const int64_t t = C.t;
     const char* tabm = C.tabm;
     const uint32_t* t31_rep = C.t31_rep;
-    uint32_t ones_r;  // ONES held in a register the compiler cannot fold back into an immediate
-    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
-    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
-    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
-    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
-    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-    uint32_t nw[4];
+    constexpr int half = HALF;
+    // coarse randoms: one Philox call per 8 sites, 16 bits per site
+    uint32_t q[4];
+    philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
+    uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
+    uint32_t tiemin = 0x7FFF7FFFu;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        // coarse randoms: one Philox call per 8 sites, 16 bits per site
-        uint32_t q[4];
-        philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
-        uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
-        uint32_t tiemin = 0x7FFF7FFFu;
-#pragma unroll
-        for (int w2 = 0; w2 < 2; ++w2) {
-            const int wi = 2 * half + w2;
-            // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
-            const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
-            const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
-            const uint32_t sh = par ? sr : sl;
-            const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
-            const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
-            const uint32_t c4 = o[wi];
-            // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
-            const uint32_t fO = and_xor(prmt(ra, rb, 0xFDB9u), 0x03030303u, ones_r);  // one LOP3
-            // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
-            // u16 byte offset is applied by the IDP.4A that extracts each byte
-            const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
-            // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
-            const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
-            const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
-            xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
+    for (int w2 = 0; w2 < 2; ++w2) {
+        const int wi = 2 * half + w2;
+        // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
+        const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
+        const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
+        const uint32_t sh = par ? sr : sl;
+        const uint32_t S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
+        const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
+        const uint32_t c4 = o[wi];
+        // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
+        const uint32_t fO = and_xor(prmt(ra, rb, 0xFDB9u), 0x03030303u, ones_r);  // one LOP3
+        // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
+        // u16 byte offset is applied by the IDP.4A that extracts each byte
+        const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
+        // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
+        const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
+        const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
+        xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
+        uint32_t Z01, Z23;
+        if (PAIR) {
+            // Pair table: ONE lookup per two sites.  Byte offset 4*(b0-9) + 216*(b1-9) by one IDP.4A (the
+            // bias and the shared-space base are its accumulator), LDS.32 returns the packed word T with
+            // ra - T = lanes 0x8000 + u15 - E15 exactly: the flip bits of ra (bits 15, 31) are known to the
+            // table through the entry numbers and cancel, so no guard-bit OR and no PRMT to pack two
+            // thresholds (see pair_table_kernel).
+            const uint32_t a01 = __dp4a(idx4, 0x0000D804u, C.tab2s);
+            const uint32_t a23 = __dp4a(idx4, 0xD8040000u, C.tab2s);
+            uint32_t T01, T23;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(T01) : "r"(a01));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(T23) : "r"(a23));
+            Z01 = ra - T01;
+            Z23 = rb - T23;
+        } else {
             // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
             const uint32_t a0 = __dp4a(idx4, 0x00000002u, 0u);
             const uint32_t a3 = __dp4a(idx4, 0x02000000u, 0u);
@@ -134,49 +143,65 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
             // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
             // in [1, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
             // tie.  E15 = min(thr31 >> 16, 32767).
-            const uint32_t Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
-            const uint32_t Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
-            msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
-            // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
-            tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
-            idx[w2] = idx4;
-            Ssave[w2] = S4;
+            Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
+            Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
         }
-        if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
-            // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
-            uint32_t f[4];
-            philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
-            const uint32_t* t31 = t31_rep;
+        msk[w2] = prmt(Z01, Z23, 0xFDB9u);                  // 0xFF where u15 >= E15 (REJECT mask)
+        // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
+        tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
+        idx[w2] = idx4;
+        Ssave[w2] = S4;
+    }
+    if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
+        // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
+        uint32_t f[4];
+        philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
+        const uint32_t* t31 = t31_rep;
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const int w2 = s >> 2, b = s & 3;
-                const uint32_t a = ((idx[w2] >> (8 * b)) & 0xFFu) * 2u;
-                const uint32_t rw = q[s >> 1];
-                const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
-                const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
-                if ((h & 0x7FFFu) == E) {
-                    const uint32_t fw = f[s >> 1];
-                    const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
-                    if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] &= ~(0xFFu << (8 * b));
-                    ++n_ties;
-                }
+        for (int s = 0; s < 8; ++s) {
+            const int w2 = s >> 2, b = s & 3;
+            const uint32_t a = ((idx[w2] >> (8 * b)) & 0xFFu) * 2u;
+            const uint32_t rw = q[s >> 1];
+            const uint32_t h = (s & 1) ? (rw >> 16) : (rw & 0xFFFFu);
+            const uint32_t E = *reinterpret_cast<const uint16_t*>(tabm + a);
+            if ((h & 0x7FFFu) == E) {
+                const uint32_t fw = f[s >> 1];
+                const uint32_t f16 = (s & 1) ? (fw >> 16) : (fw & 0xFFFFu);
+                if (exact_accept(h, f16, __ldg(t31 + ((a - 18u) >> 1)))) msk[w2] &= ~(0xFFu << (8 * b));
+                ++n_ties;
             }
-        }
-#pragma unroll
-        for (int w2 = 0; w2 < 2; ++w2) {
-            const int wi = 2 * half + w2;
-            const uint32_t v = o[wi] ^ (xr[w2] & ~msk[w2]);
-            if (MEASURE) {
-                a_c = __dp4a(v, ONES, a_c);
-                a_c2 = __dp4a(v, v, a_c2);
-                if (COL == 1) {
-                    a_cS = __dp4a(v, Ssave[w2], a_cS);
-                    a_S = __dp4a(Ssave[w2], ONES, a_S);
-                }
-            }
-            nw[wi] = v;
         }
     }
+#pragma unroll
+    for (int w2 = 0; w2 < 2; ++w2) {
+        const int wi = 2 * half + w2;
+        const uint32_t v = o[wi] ^ (xr[w2] & ~msk[w2]);
+        if (MEASURE) {
+            a_c = __dp4a(v, ONES, a_c);
+            a_c2 = __dp4a(v, v, a_c2);
+            if (COL == 1) {
+                a_cS = __dp4a(v, Ssave[w2], a_cS);
+                a_S = __dp4a(Ssave[w2], ONES, a_S);
+            }
+        }
+        nw[wi] = v;
+    }
+}
+
+template <int COL, bool MEASURE, bool PAIR = false>
+__device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t y, const int par, const uint4& upv,
+                                                const uint4& midv, const uint4& dnv, const uint32_t side,
+                                                const uint4& ownv, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
+                                                uint32_t& a_S, uint32_t& n_ties) {
+    uint32_t ones_r;  // ONES held in a register the compiler cannot fold back into an immediate
+    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
+    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
+    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
+    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
+    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
+    uint32_t nw[4];
+    update_half8<COL, MEASURE, 0, PAIR>(C, y, par, o, u, m, d, side, ones_r, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    update_half8<COL, MEASURE, 1, PAIR>(C, y, par, o, u, m, d, side, ones_r, nw, a_c, a_c2, a_cS, a_S, n_ties);
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
 }
 
@@ -207,10 +232,15 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 //   HALO  = true : slab boundary-strip launch in peer-memory mode: the thread that produces a chunk of the
 //                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank
 //                  above / below (peer pointers over NVLink): compute and halo transfer are one kernel.
-template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false>
+//   PAIR  = true : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
+//                  thresholds of two sites up with one IDP.4A + one LDS.32; pays when a CTA marches over enough
+//                  rows to amortise the staging (host: LaunchPlan::pair).
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, bool PAIR = false>
 __global__ void __launch_bounds__(FAST_THREADS, (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
+    static_assert(!(PAIR && SMALL), "the pair table is one replica per CTA");
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
+    __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
     __shared__ uint4 s_own[2][FAST_THREADS];     // thread-private own chunks (current / next row)
     __shared__ uint32_t s_side[2][FAST_THREADS];  // thread-private side words
@@ -228,6 +258,12 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         s_tab[i] = (r < (uint32_t)P.n_replicas)
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
+    }
+    if (PAIR) {  // the tables are written by bc_set_params, never by a sweep: safe before griddepcontrol.wait
+        const uint4* src = reinterpret_cast<const uint4*>(P.tab2 + (size_t)rep0 * TAB2_WORDS);
+        for (int i = threadIdx.x; i < TAB2_WORDS / 4; i += FAST_THREADS) cp_async16(&s_tab2[4 * i], src + i);
+        cp_async_commit();
+        cp_async_wait<0>();
     }
     __syncthreads();
 
@@ -277,13 +313,14 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     RowCtx ctx;
     ctx.j = j; ctx.ctr2 = ctr2; ctx.ctr3 = ctr3; ctx.k0 = k0; ctx.k1 = k1; ctx.t = t; ctx.tabm = tabm;
     ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
+    ctx.tab2s = PAIR ? (uint32_t)__cvta_generic_to_shared(s_tab2) - TAB2_BIAS : 0u;
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
         if (!HALO) {
             *reinterpret_cast<uint4*>(own_col + off) =
-                update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+                update_chunk16<COL, MEASURE, PAIR>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
         } else {
-            const uint4 nv = update_chunk16<COL, MEASURE>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            const uint4 nv = update_chunk16<COL, MEASURE, PAIR>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
             *reinterpret_cast<uint4*>(own_col + off) = nv;
             // fused halo transfer: first owned row -> bottom ghost row of the rank above, last owned row -> top
             // ghost row of the rank below (same array geometry on every rank)
@@ -835,6 +872,21 @@ __global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, 
 }
 
 // device-resident sweep counter used by CUDA-graph replay: kernels read t = *clock + offset
+// Pair table of replicas [rep_first, rep_first + n): word a + 54*b = the 32-bit T with
+//   (h_a | h_b << 16) - T  ==  (0x8000 + u15_a - E15_a) | (0x8000 + u15_b - E15_b) << 16   (mod 2^32)
+// for coarse draws h = flip << 15 | u15 whose flip bits agree with the entry numbers a, b (flip = (i % 18) >= 9):
+// lane = flip*0x8000 - 0x8000 + E15.  Both result lanes lie in [1, 0xFFFF], so they never borrow from each other.
+__global__ void pair_table_kernel(const uint16_t* __restrict__ tab16, uint32_t* __restrict__ tab2, int rep_first, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n * TAB2_WORDS) return;
+    const int r = rep_first + (int)(i / TAB2_WORDS), w = (int)(i % TAB2_WORDS);
+    const int a = w % TABLE_ENTRIES, b = w / TABLE_ENTRIES;
+    const uint16_t* t = tab16 + (size_t)r * TABLE_ENTRIES;
+    const uint32_t la = ((a % 18) >= 9 ? 0u : 0xFFFF8000u) + t[a];
+    const uint32_t lb = ((b % 18) >= 9 ? 0u : 0xFFFF8000u) + t[b];
+    tab2[(size_t)r * TAB2_WORDS + w] = la + (lb << 16);
+}
+
 __global__ void clock_set_kernel(int64_t* clock, int64_t value) { *clock = value; }
 __global__ void clock_add_kernel(int64_t* clock, int64_t delta) { *clock += delta; }
 

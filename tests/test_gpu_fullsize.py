@@ -56,6 +56,27 @@ def test_rows_per_thread_invariance_L4096(bc):
         assert np.array_equal(o, out[0])
 
 
+def test_pair_table_on_off_L4096(bc):
+    """The pair-table kernels (default for >= 8 rows per thread) and the per-site-lookup kernels produce the
+    same lattices, observables and tie counts on a 4-replica L=4096 batch."""
+    L, n = 4096, 5
+    out = []
+    for pair in (8, 0):
+        e = bc.Engine(L, 0, 4, 0, 0xAB)
+        e.set_option("rows_per_thread", 32)
+        e.set_option("pair_min_rows", pair)
+        e.set_params(*TC)
+        e.init_random()
+        assert e.plan()["pair"] == (pair > 0)
+        obs = e.sweep(n, 2)
+        out.append((e.download(), obs, e.tie_count))
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for f in ("M", "Q", "B"):
+        assert np.array_equal(out[0][1][f], out[1][1][f])
+    assert out[0][2] == out[1][2] and out[0][2] > 0
+
+
 def test_replica_batch_equals_single_runs(bc):
     """Replica r of a batch uses key (seed_lo, seed_hi ^ r): equal to a 1-replica engine with that seed."""
     L, n, seed = 1024, 5, 0x1234_0000_0042

@@ -73,6 +73,23 @@ def test_fast_kernel(bc, oracle, L, rows, boundary):
             assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
 
 
+@pytest.mark.parametrize("L,n_rep,rows", [(256, 2, 8), (256, 1, 16), (512, 2, 16), (1024, 1, 32)])
+@pytest.mark.parametrize("boundary", [0, 1])
+@pytest.mark.parametrize("params", [TC, (0.3, 1.0, 1.0), (5.0, -2.0, -1.0)])
+def test_pair_table_kernel(bc, oracle, L, n_rep, rows, boundary, params):
+    """Streaming kernel with the 54 x 54 pair table (one threshold lookup per two sites) against the oracle,
+    with and without fused observables, at parameter points whose tables hold the extreme entries
+    (always accept: E15 = 32767; never accept: E15 = 0)."""
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, 6, 0x9A1 + L + rows, params=params,
+                                            opts=(("rows_per_thread", rows), ("resident", 0), ("pair_min_rows", 8)),
+                                            measure_every=2)
+    assert plan["pair"] and plan["rows_per_thread"] == rows
+    assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
+
+
 @pytest.mark.parametrize("params", [(0.608, 1.966, 1.0), (2.2691853, -1000.0, 1.0), (1.0, 0.5, 0.0), (0.3, 1.0, 1.0),
                                     (5.0, -2.0, -1.0)])
 def test_parameter_points(bc, oracle, params):
@@ -342,6 +359,7 @@ def test_randomised_configurations(bc, oracle):
         if kind == "stream":
             e.set_option("resident", 0)
             e.set_option("rows_per_thread", int(rng.choice([0, 1, 2, 4, 8])))
+            e.set_option("pair_min_rows", int(rng.choice([0, 2, 8])))
         if kind == "resident":
             e.set_option("resident", 1)
         e.set_params(T, D, J)
