@@ -135,6 +135,7 @@ struct bc_engine {
     bool resident_attr_set[2] = {false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
+    int opt_swp_min_rows = 32;  // ... with software-pipelined Philox draws from this many rows on (0 = never)
     int opt_force_generic = 0;
     std::string err;
 };
@@ -149,7 +150,7 @@ struct bc_engine {
     } while (0)
 
 typedef void (*fast_fn)(const SweepParams);
-static void pair_kernels(fast_fn (&out)[8]);
+static void pair_kernels(fast_fn (&out)[10]);
 
 static Geom geom_of(const bc_engine* e) {
     Geom g;
@@ -194,11 +195,10 @@ static void build_table(double T, double D, double J, uint32_t thr31[TABLE_ENTRI
                 }
                 const int i = 18 * c + 9 * f + S;
                 thr31[i] = thr;
-                // coarse 15-bit threshold compared against u15 (bits 0..14 of the draw): accept iff u15 < E,
-                // tie iff u15 == E.  Clamped to 32767: the clamp only turns the single value u15 = 32767 of an
-                // always-accept entry into a tie, which the exact path then accepts.
-                uint32_t E = thr >> 16;
-                if (E > 32767u) E = 32767u;
+                // coarse threshold compared against u15 (bits 0..14 of the draw): accept iff u15 < E, tie iff
+                // u15 == E.  E = thr31 >> 16 in [0, 32768]; 32768 (always accept, thr31 = 2^31) never ties, exactly
+                // like the oracle's lazy rule, and still fits the 16-bit lanes: 0x8000 + u15 - 32768 = u15 >= 0.
+                const uint32_t E = thr >> 16;
                 tab16[i] = (uint16_t)E;
             }
 }
@@ -299,7 +299,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if (L % 32 == 0 && L >= 256 &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
     if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
-        fast_fn pf[8];
+        fast_fn pf[10];
         pair_kernels(pf);
         for (fast_fn f : pf) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -604,23 +604,25 @@ static fast_fn fast_halo(bool open) {
 }
 
 template <int COL, bool MEAS>
-static fast_fn fast_pair(bool open) {
-    return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, false, true>
-                : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, false, true>;
+static fast_fn fast_pair(bool open, bool swp = false) {
+    if (swp && !open && !MEAS) return (fast_fn)sweep_fast_kernel<COL, false, false, false, false, 2>;
+    return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, false, 1>
+                : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, false, 1>;
 }
 
-static void pair_kernels(fast_fn (&out)[8]) {
+static void pair_kernels(fast_fn (&out)[10]) {
     int n = 0;
     for (int open = 0; open < 2; ++open) {
         out[n++] = fast_pair<0, false>(open); out[n++] = fast_pair<0, true>(open);
         out[n++] = fast_pair<1, false>(open); out[n++] = fast_pair<1, true>(open);
     }
+    out[n++] = fast_pair<0, false>(false, true); out[n++] = fast_pair<1, false>(false, true);
 }
 
-static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false, bool pair = false) {
+static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false, int pair = 0) {
     if (pair && !small && !halo) {
-        if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open);
-        return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open);
+        if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open, pair == 2);
+        return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open, pair == 2);
     }
     if (halo && !small) {
         if (col == 0) return meas ? fast_halo<0, true>(open) : fast_halo<0, false>(open);
@@ -637,7 +639,8 @@ static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = 
 struct LaunchPlan {
     bool fast = false;
     bool small = false;
-    bool pair = false;  // pair-table kernels: one replica per CTA and enough rows per thread to amortise the 11.4 KB table
+    int pair = 0;  // 1: pair-table kernels (one replica per CTA, enough rows per thread to amortise the 11.4 KB
+                   // table); 2: with software-pipelined draws as well (long strips)
     int cpr = 0, strips = 0, rows = 0;
     unsigned grid = 0;
 };
@@ -658,6 +661,9 @@ static LaunchPlan make_plan(const bc_engine* e) {
             R = e->opt_rows;
         } else {
             const long long want = 148LL * 768;  // enough threads to fill the chip (6-7 CTAs of 128 per SM)
+            // 64 rows amortise the per-strip prologue (pair table, first draws) best, but only when the grid still
+            // has four full waves of CTAs (1821 -> 1841 updates/ns on 64 x L=4096)
+            if (rows_valid(Ly, p.cpr, 64) && (long long)e->n_rep * (Ly / 64) * p.cpr >= 4 * want) R = 64;
             const int cand[5] = {32, 16, 8, 4, 2};
             for (int i = 0; i < 5 && !R; ++i)
                 if (rows_valid(Ly, p.cpr, cand[i]) && (long long)e->n_rep * (Ly / cand[i]) * p.cpr >= want) R = cand[i];
@@ -666,7 +672,8 @@ static LaunchPlan make_plan(const bc_engine* e) {
         p.rows = R;
         p.strips = Ly / R;
         p.small = (R & 1) != 0 || (((long long)p.strips * p.cpr) % FAST_THREADS) != 0;
-        p.pair = !p.small && e->d_tab2 && e->opt_pair_min_rows > 0 && R >= e->opt_pair_min_rows;
+        if (!p.small && e->d_tab2 && e->opt_pair_min_rows > 0 && R >= e->opt_pair_min_rows)
+            p.pair = (e->opt_swp_min_rows > 0 && R >= e->opt_swp_min_rows) ? 2 : 1;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
     } else {
@@ -1279,6 +1286,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
+    if (n == "swp_min_rows") { e->opt_swp_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "pair_min_rows") { e->opt_pair_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "wave") { e->opt_wave = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
@@ -1312,7 +1320,7 @@ extern "C" int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, i
         if (block) *block = r.T * r.reps_per_cta;
         return BC_OK;
     }
-    if (fast) *fast = p.fast ? (p.pair ? 3 : 1) : 0;  // 3 = streaming kernel with the pair table
+    if (fast) *fast = p.fast ? (p.pair ? 2 + p.pair : 1) : 0;  // 3 = pair table, 4 = + pipelined draws
     if (rows_per_thread) *rows_per_thread = p.rows;
     if (grid) *grid = (int)p.grid;
     if (block) *block = p.fast ? FAST_THREADS : 256;

@@ -85,16 +85,15 @@ struct RowCtx {
 template <int COL, bool MEASURE, int HALF, bool PAIR>
 __device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, const int par, const uint32_t (&o)[4],
                                              const uint32_t (&u)[4], const uint32_t (&m)[4], const uint32_t (&d)[4],
-                                             const uint32_t side, const uint32_t ones_r, uint32_t (&nw)[4], uint32_t& a_c,
-                                             uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S, uint32_t& n_ties) {
-    const uint32_t j = C.j, ctr2 = C.ctr2, ctr3 = C.ctr3, k0 = C.k0, k1 = C.k1;
+                                             const uint32_t side, const uint32_t ones_r, const uint32_t (&q)[4],
+                                             uint32_t (&nw)[4], uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
+                                             uint32_t& a_S, uint32_t& n_ties) {
+    const uint32_t j = C.j, ctr2 = C.ctr2, k0 = C.k0, k1 = C.k1;
     const int64_t t = C.t;
     const char* tabm = C.tabm;
     const uint32_t* t31_rep = C.t31_rep;
     constexpr int half = HALF;
-    // coarse randoms: one Philox call per 8 sites, 16 bits per site
-    uint32_t q[4];
-    philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3, k0, k1, q);
+    // q = the coarse randoms of this half: one Philox call per 8 sites, 16 bits per site (coarse_draw)
     uint32_t idx[2], xr[2], msk[2] /* reject byte masks */, Ssave[2];
     uint32_t tiemin = 0x7FFF7FFFu;
 #pragma unroll
@@ -114,8 +113,10 @@ __device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, 
         const uint32_t idx4 = imad(c4, 18u, imad(fO, 9u, S4));
         // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
         const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
-        const uint32_t ge = (q1 >> 2) & ONES;            // 2c + f >= 3
-        xr[w2] = imad(ge, 0xFFFFFFFDu, q1);             // q1 - 3*ge
+        // (q1 + [q1 >= 4]) & 3: the shift drags the low bits of the next byte into bits 6..7, the byte sums stay
+        // below 256 (no carry) and the mask drops them.  Shift + add fuse into one LEA.HI: two ALU-pipe
+        // instructions, none on the FMA-heavy pipe that Philox saturates.
+        xr[w2] = (q1 + (q1 >> 2)) & 0x03030303u;
         uint32_t Z01, Z23;
         if (PAIR) {
             // Pair table: ONE lookup per two sites.  Byte offset 4*(b0-9) + 216*(b1-9) by one IDP.4A (the
@@ -141,8 +142,8 @@ __device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, 
             const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
             const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
             // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
-            // in [1, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
-            // tie.  E15 = min(thr31 >> 16, 32767).
+            // in [0, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
+            // tie.  E15 = thr31 >> 16 (32768 = always accept: lane = u15, never a tie).
             Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
             Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
         }
@@ -152,8 +153,9 @@ __device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, 
         idx[w2] = idx4;
         Ssave[w2] = S4;
     }
-    if ((tiemin & 0xFFFFu) == 0x8000u || (tiemin >> 16) == 0x8000u) {
-        // rare (about 2^-15 per site): redo the tied sites exactly with the fine stream
+    // high lane == 0x8000 <=> the word, as a signed number, is below 0x80010000; low lane: shifted to the top
+    if ((int32_t)tiemin < (int32_t)0x80010000u || (tiemin << 16) == 0x80000000u) {
+        // rare (about 2^-15 per uphill site): redo the tied sites exactly with the fine stream
         uint32_t f[4];
         philox4x32_10(2u * j + (uint32_t)half, y, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, f);
         const uint32_t* t31 = t31_rep;
@@ -188,6 +190,11 @@ __device__ __forceinline__ void update_half8(const RowCtx& C, const uint32_t y, 
     }
 }
 
+// coarse draws of half `half` (0/1) of chunk C.j in row y
+__device__ __forceinline__ void coarse_draw(const RowCtx& C, const uint32_t y, const uint32_t half, uint32_t (&q)[4]) {
+    philox4x32_10(2u * C.j + half, y, C.ctr2, C.ctr3, C.k0, C.k1, q);
+}
+
 template <int COL, bool MEASURE, bool PAIR = false>
 __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t y, const int par, const uint4& upv,
                                                 const uint4& midv, const uint4& dnv, const uint32_t side,
@@ -199,9 +206,37 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
     const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
     const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
     const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-    uint32_t nw[4];
-    update_half8<COL, MEASURE, 0, PAIR>(C, y, par, o, u, m, d, side, ones_r, nw, a_c, a_c2, a_cS, a_S, n_ties);
-    update_half8<COL, MEASURE, 1, PAIR>(C, y, par, o, u, m, d, side, ones_r, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    uint32_t nw[4], q[4];
+    coarse_draw(C, y, 0u, q);
+    update_half8<COL, MEASURE, 0, PAIR>(C, y, par, o, u, m, d, side, ones_r, q, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    coarse_draw(C, y, 1u, q);
+    update_half8<COL, MEASURE, 1, PAIR>(C, y, par, o, u, m, d, side, ones_r, q, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    return make_uint4(nw[0], nw[1], nw[2], nw[3]);
+}
+
+// Software-pipelined form for the streaming kernel: on entry qn holds the coarse draws of (row y, half 0); on exit
+// those of (row y_next, half 0).  The draws of the NEXT half are issued in the same basic block as the site
+// arithmetic of the current half (the rare-tie branch ends a block), so the scheduler can interleave the
+// IMAD.WIDE chain of Philox (FMA-heavy pipe) with the LOP3/PRMT work (ALU pipe) of independent data instead of
+// running them back to back.
+template <int COL, bool MEASURE, bool PAIR>
+__device__ __forceinline__ uint4 update_chunk16_sp(const RowCtx& C, const uint32_t y, const uint32_t y_next, const int par,
+                                                   const uint4& upv, const uint4& midv, const uint4& dnv,
+                                                   const uint32_t side, const uint4& ownv, uint32_t (&qn)[4],
+                                                   uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S,
+                                                   uint32_t& n_ties) {
+    uint32_t ones_r;
+    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
+    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
+    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
+    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
+    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
+    uint32_t nw[4], q1[4];
+    const uint32_t q0[4] = {qn[0], qn[1], qn[2], qn[3]};
+    coarse_draw(C, y, 1u, q1);
+    update_half8<COL, MEASURE, 0, PAIR>(C, y, par, o, u, m, d, side, ones_r, q0, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    coarse_draw(C, y_next, 0u, qn);
+    update_half8<COL, MEASURE, 1, PAIR>(C, y, par, o, u, m, d, side, ones_r, q1, nw, a_c, a_c2, a_cS, a_S, n_ties);
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
 }
 
@@ -232,13 +267,25 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 //   HALO  = true : slab boundary-strip launch in peer-memory mode: the thread that produces a chunk of the
 //                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank
 //                  above / below (peer pointers over NVLink): compute and halo transfer are one kernel.
-//   PAIR  = true : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
+//   PAIR >= 1    : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
 //                  thresholds of two sites up with one IDP.4A + one LDS.32; pays when a CTA marches over enough
 //                  rows to amortise the staging (host: LaunchPlan::pair).
-template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, bool PAIR = false>
-__global__ void __launch_bounds__(FAST_THREADS, (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1)
+//   PAIR == 2    : additionally the software-pipelined Philox draws (plain periodic kernel only; long strips).
+// Software pipelining of the Philox draws (update_chunk16_sp) needs ~8 more registers: it pays for the plain
+// periodic pair-table kernel at 6 CTAs/SM (80 registers: 1778 -> 1813 updates/ns) and loses wherever it spills
+// (72 registers) or drops the measuring / open variants to 5 CTAs/SM.
+template <bool MEASURE, bool OPEN, int PAIR>
+struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; };
+template <bool SMALL, bool MEASURE, bool OPEN, int PAIR>
+struct FastMinBlocks {
+    static constexpr int value =
+        (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+};
+
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, int PAIR = 0>
+__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR>::value)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
-    static_assert(!(PAIR && SMALL), "the pair table is one replica per CTA");
+    static_assert(!(PAIR && SMALL) && !(PAIR && HALO), "the pair table is one replica per CTA; HALO kernels use the per-site table");
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
@@ -314,13 +361,19 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     ctx.j = j; ctx.ctr2 = ctr2; ctx.ctr3 = ctr3; ctx.k0 = k0; ctx.k1 = k1; ctx.t = t; ctx.tabm = tabm;
     ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
     ctx.tab2s = PAIR ? (uint32_t)__cvta_generic_to_shared(s_tab2) - TAB2_BIAS : 0u;
+    constexpr bool SWP = FastSwp<MEASURE, OPEN, PAIR>::value;
+    uint32_t qn[4];
+    if (SWP) coarse_draw(ctx, yg0, 0u, qn);
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
-        if (!HALO) {
+        if (SWP) {
+            *reinterpret_cast<uint4*>(own_col + off) = update_chunk16_sp<COL, MEASURE, (PAIR > 0)>(
+                ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, n_ties);
+        } else if (!HALO) {
             *reinterpret_cast<uint4*>(own_col + off) =
-                update_chunk16<COL, MEASURE, PAIR>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+                update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
         } else {
-            const uint4 nv = update_chunk16<COL, MEASURE, PAIR>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            const uint4 nv = update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
             *reinterpret_cast<uint4*>(own_col + off) = nv;
             // fused halo transfer: first owned row -> bottom ghost row of the rank above, last owned row -> top
             // ghost row of the rank below (same array geometry on every rank)
@@ -875,7 +928,7 @@ __global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, 
 // Pair table of replicas [rep_first, rep_first + n): word a + 54*b = the 32-bit T with
 //   (h_a | h_b << 16) - T  ==  (0x8000 + u15_a - E15_a) | (0x8000 + u15_b - E15_b) << 16   (mod 2^32)
 // for coarse draws h = flip << 15 | u15 whose flip bits agree with the entry numbers a, b (flip = (i % 18) >= 9):
-// lane = flip*0x8000 - 0x8000 + E15.  Both result lanes lie in [1, 0xFFFF], so they never borrow from each other.
+// lane = flip*0x8000 - 0x8000 + E15.  Both result lanes lie in [0, 0xFFFF], so they never borrow from each other.
 __global__ void pair_table_kernel(const uint16_t* __restrict__ tab16, uint32_t* __restrict__ tab2, int rep_first, int n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n * TAB2_WORDS) return;

@@ -175,9 +175,17 @@ def test_ties_are_resolved_like_the_oracle(bc, oracle):
     """Enough attempts that coarse ties (2^-15 per uphill attempt) occur; lattice must still match."""
     L, n = 128, 40
     oracle.tie_count(reset=True)
-    got, ref, obs, ref_obs, _ = run_pair(bc, oracle, L, 0, 1, n, 31337, measure_every=0)
+    eng = bc.Engine(L, 0, 1, 0, 31337)
+    eng.set_params(*TC)
+    eng.init_random()
+    eng.sweep(n, 0)
+    got, gpu_ties = eng.download(0), eng.tie_count
+    eng.close()
+    ref = oracle.init_random(L, 31337, 0)
+    oracle.sweep(ref, oracle.build_table(*TC), 31337, 0, 0, n, 0, 0)
     assert np.array_equal(got, ref)
     assert oracle.tie_count() > 0  # the case was exercised
+    assert gpu_ties == oracle.tie_count()  # the kernels take the fine-stream path exactly when the oracle does
 
 
 def test_errors(bc):

@@ -1,6 +1,7 @@
 """Instruction histogram of the main loop of a kernel in libbc_engine.so (development aid)."""
 import re, collections, subprocess, sys
-lib = "blume_capel_b200/libbc_engine.so"
+import os
+lib = os.environ.get("BC_ENGINE_LIB", "blume_capel_b200/libbc_engine.so")
 pat = sys.argv[1] if len(sys.argv) > 1 else "fast_kernelILi0ELb0ELb0ELi1"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 ALU = {"LOP3","PRMT","SHF","ISETP","SEL","IADD3","VIADD","LEA","IABS","VIMNMX","MOV","PLOP3","P2R","R2P","BMSK","SGXT","FLO","POPC","IADD","UIADD3"}
