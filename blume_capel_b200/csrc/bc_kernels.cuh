@@ -260,6 +260,9 @@ __device__ __forceinline__ uint4 update_chunk16_sp(const RowCtx& C, const uint32
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
+#ifndef BC_DEEP_PREFETCH
+#define BC_DEEP_PREFETCH 1  // 0: one row ahead everywhere, 1: two rows ahead where it pays (see DEEP), 2: everywhere
+#endif
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
@@ -289,8 +292,12 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
-    __shared__ uint4 s_own[2][FAST_THREADS];     // thread-private own chunks (current / next row)
-    __shared__ uint32_t s_side[2][FAST_THREADS];  // thread-private side words
+    // DEEP: inputs are requested two rows ahead instead of one (the row above is then carried in registers and
+    // the ring holds rows y, y+1 and the two rows in flight).  Measured (tools/tune_libs2.sh): +1..3 % for the
+    // periodic pair-table kernels at 8..16 rows per thread, -1 % for the pipelined kernel, -2 % with open edges.
+    constexpr bool DEEP = BC_DEEP_PREFETCH == 2 || (BC_DEEP_PREFETCH == 1 && PAIR == 1 && !OPEN);
+    __shared__ uint4 s_own[DEEP ? 4 : 2][FAST_THREADS];     // thread-private own chunks (current / next rows)
+    __shared__ uint32_t s_side[DEEP ? 4 : 2][FAST_THREADS];  // thread-private side words
 
     // Programmatic dependent launch: let the next half-sweep's grid be scheduled as soon as SMs free up; its
     // CTAs run their prologue (table staging, index arithmetic) and then block in griddepcontrol.wait until
@@ -406,37 +413,83 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous half-sweep (other colour) is complete
     uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
-    if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
-    else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
-    cp_async16(&s_rows[1][tid], oth_col + off);
-    stage_other(2, off + Wc);
-    stage_row_inputs(0, off, (int)((yg0 + COL) & 1u));
-    cp_async_commit();
-
-    // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
-    auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
-        if (!last) {
-            stage_other((sl + 3) & 3, off + 2 * Wc);
-            stage_row_inputs((sl + 1) & 1, off + Wc, 1 - par);
-        }
+    if (!DEEP) {
+        if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
+        else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
+        cp_async16(&s_rows[1][tid], oth_col + off);
+        stage_other(2, off + Wc);
+        stage_row_inputs(0, off, (int)((yg0 + COL) & 1u));
         cp_async_commit();
-        cp_async_wait<1>();  // everything but the group just committed has landed: row r is ready
-        const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
-        const uint4 ownv = s_own[sl & 1][tid];
-        const uint32_t side = s_side[sl & 1][tid];
-        update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
-        off += Wc;
-    };
 
-    if (SMALL || (rows & 3u)) {
-        for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
+        // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
+        auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
+            if (!last) {
+                stage_other((sl + 3) & 3, off + 2 * Wc);
+                stage_row_inputs((sl + 1) & 1, off + Wc, 1 - par);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();  // everything but the group just committed has landed: row r is ready
+            const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
+            const uint4 ownv = s_own[sl & 1][tid];
+            const uint32_t side = s_side[sl & 1][tid];
+            update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
+            off += Wc;
+        };
+
+        if (SMALL || (rows & 3u)) {
+            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
+        } else {
+            // yg0 is even and rows is a multiple of 4: parities alternate COL, 1-COL statically; static ring slots
+            for (uint32_t r = 0; r < rows; r += 4) {
+                march(r, COL, false, 0);
+                march(r + 1, 1 - COL, false, 1);
+                march(r + 2, COL, false, 2);
+                march(r + 3, 1 - COL, r + 4 == rows, 3);
+            }
+        }
     } else {
-        // yg0 is even and rows is a multiple of 4: parities alternate COL, 1-COL statically; static ring slots
-        for (uint32_t r = 0; r < rows; r += 4) {
-            march(r, COL, false, 0);
-            march(r + 1, 1 - COL, false, 1);
-            march(r + 2, COL, false, 2);
-            march(r + 3, 1 - COL, r + 4 == rows, 3);
+        // Strip row r lives in ring slot r&3 (other colour) and r&3 (own chunk, side word).  Group G_r, committed at
+        // the top of row r, holds other row r+3 and the own chunk / side word of row r+2; row r needs G_{r-2}, so
+        // two groups stay in flight (wait_group 2).  Row r-1 of the other colour is carried in registers.
+        const int par0 = (int)((yg0 + COL) & 1u);
+        uint4 upv;
+        if (y0 == 0) upv = open ? ones4 : __ldcg(reinterpret_cast<const uint4*>(oth_col + (total - Wc)));
+        else upv = __ldcg(reinterpret_cast<const uint4*>(oth_col + (off - Wc)));
+        cp_async16(&s_rows[0][tid], oth_col + off);
+        stage_other(1, off + Wc);
+        stage_row_inputs(0, off, par0);
+        cp_async_commit();  // G_{-2}
+        if (rows > 1) {
+            stage_other(2, off + 2 * Wc);
+            stage_row_inputs(1, off + Wc, 1 - par0);
+        }
+        cp_async_commit();  // G_{-1}
+
+        auto march = [&](const uint32_t r, const int par, const bool more, const int sl) {
+            if (more) {  // row r+2 exists (same parity as row r)
+                stage_other((sl + 3) & 3, off + 3 * Wc);
+                stage_row_inputs((sl + 2) & 3, off + 2 * Wc, par);
+            }
+            cp_async_commit();
+            cp_async_wait<2>();
+            const uint4 midv = s_rows[sl & 3][tid], dnv = s_rows[(sl + 1) & 3][tid];
+            const uint4 ownv = s_own[sl & 3][tid];
+            const uint32_t side = s_side[sl & 3][tid];
+            update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
+            upv = midv;
+            off += Wc;
+        };
+
+        if (SMALL || (rows & 3u)) {
+            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 3 <= rows, (int)(r & 3u));
+        } else {
+            for (uint32_t r = 0; r < rows; r += 4) {
+                const bool more = r + 4 != rows;
+                march(r, COL, true, 0);
+                march(r + 1, 1 - COL, true, 1);
+                march(r + 2, COL, more, 2);
+                march(r + 3, 1 - COL, more, 3);
+            }
         }
     }
 
