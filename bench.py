@@ -194,6 +194,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     last_obs = eng.read_obs(n_meas)
+    ties_resident = eng.tie_count
 
     # ---- for the record: ONE L=4096 lattice (16 MiB, L2 resident, launch-bound), not the headline
     single = None
@@ -208,22 +209,33 @@ def run_ours(args, rank, world, local_rank):
         single = float(L) * L * 1024 / (e1.timer_stop() * 1e6)
         e1.close()
 
-    # ---- end to end through the C ABI from pinned host buffers.  Two handles (two streams) are used the
-    # ---- way a caller with many batches would: while one batch is swept, the other batch's lattices are
-    # ---- uploaded / downloaded.  Every step still uploads its 1 GiB of input lattices and reads back its
-    # ---- observables and its 1 GiB of final lattices inside the timed region.
+    # ---- end to end through the C ABI from pinned host buffers.  Several handles (streams) are used the way a
+    # ---- caller with many batches would: while one batch is swept, other batches' lattices are uploaded /
+    # ---- downloaded.  A step's 64 replicas travel as --e2e-split sub-batches (own handle each), so the first
+    # ---- sweep starts after the first sub-batch has arrived instead of after the whole GiB.  Every step still
+    # ---- uploads its 1 GiB of input lattices and reads back its observables and its 1 GiB of final lattices
+    # ---- inside the timed region.
     n_handles = max(2, args.e2e_handles)
-    extra = []
-    for k in range(1, n_handles):
-        e_k = bc.Engine(L, bc.PERIODIC, N_REPLICAS, local_rank, SEED + (rank << 40) + k)
-        e_k.set_params(T, D, J)
-        extra.append(e_k)
-    engs = [eng] + extra
-    hosts = []
+    split = max(1, args.e2e_split)
+    while N_REPLICAS % split:
+        split -= 1
+    sub = N_REPLICAS // split
+    full_host = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True).numpy()
+    eng.download(out=full_host)
+    eng.close()  # the device-resident handle is done; the end-to-end loop owns its own
+    engs, hosts = [], []
     for k in range(n_handles):
-        h = torch.empty((N_REPLICAS, L, L), dtype=torch.int8, pin_memory=True).numpy()
-        eng.download(out=h)
-        hosts.append(h)
+        row_e, row_h = [], []
+        for p_ in range(split):
+            e_k = bc.Engine(L, bc.PERIODIC, sub, local_rank, SEED + (rank << 40) + 64 * k + p_)
+            e_k.set_params(T, D, J)
+            h = torch.empty((sub, L, L), dtype=torch.int8, pin_memory=True).numpy()
+            h[:] = full_host[p_ * sub:(p_ + 1) * sub]
+            row_e.append(e_k)
+            row_h.append(h)
+        engs.append(row_e)
+        hosts.append(row_h)
+    del full_host
     obs_buf = None
 
     def e2e_steps(n):
@@ -231,17 +243,19 @@ def run_ours(args, rank, world, local_rank):
         pending = [False] * n_handles
         for i in range(n):
             k = i % n_handles
-            e = engs[k]
-            if pending[k]:
-                obs_buf = e.read_obs(n_meas)                 # waits for step i-2 on this handle (d2h observables)
-            e.upload_async(hosts[k])                          # h2d: the step's input lattices
-            e.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
-            e.download_async(hosts[k])                        # d2h: the step's final lattices (the sample dump)
+            for p_ in range(split):
+                e = engs[k][p_]
+                if pending[k]:
+                    obs_buf = e.read_obs(n_meas)              # waits for step i-n_handles on this handle (d2h observables)
+                e.upload_async(hosts[k][p_])                  # h2d: the sub-batch's input lattices
+                e.sweep(SWEEPS_PER_STEP, MEASURE_EVERY, fetch=False)
+                e.download_async(hosts[k][p_])                # d2h: its final lattices (the sample dump)
             pending[k] = True
         for k in range(n_handles):
-            if pending[k]:
-                obs_buf = engs[k].read_obs(n_meas)
-                engs[k].sync()
+            for p_ in range(split):
+                if pending[k]:
+                    obs_buf = engs[k][p_].read_obs(n_meas)
+                    engs[k][p_].sync()
 
     e2e_steps(max(min(args.warmup, 2), n_handles))
     barrier()
@@ -250,7 +264,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
-    host_np = hosts[0]
+    h2d_bytes = sum(h.nbytes for h in hosts[0])
+    d2h_bytes = h2d_bytes + obs_buf.nbytes * split
 
     ms_t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
@@ -287,8 +302,9 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "spin-updates/ns",
-                    "h2d_bytes_per_step": int(host_np.nbytes),
-                    "d2h_bytes_per_step": int(host_np.nbytes + obs_buf.nbytes)},
+                    "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes),
+                    "handles": n_handles, "sub_batches_per_step": split},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "bc::sweep_fast_kernel",
@@ -299,12 +315,12 @@ def run_ours(args, rank, world, local_rank):
             "single_lattice": {"workload": f"one L={L} lattice (16 MiB, L2-resident; CUDA-graph replay + PDL)",
                                "updates_per_ns": single},
             "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
-                      "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": eng.tie_count},
+                      "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": ties_resident},
         }
         print(json.dumps(line), flush=True)
-    eng.close()
-    for e_k in extra:
-        e_k.close()
+    for row in engs:
+        for e_k in row:
+            e_k.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -316,7 +332,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-handles", type=int, default=3, help="handles (streams) the end-to-end loop pipelines over")
+    ap.add_argument("--e2e-handles", type=int, default=3, help="steps in flight in the end-to-end loop")
+    ap.add_argument("--e2e-split", type=int, default=4, help="sub-batches (handles) a step's replicas travel as")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

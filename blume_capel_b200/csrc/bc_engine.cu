@@ -518,15 +518,25 @@ extern "C" int bc_init_random(bc_engine* e, int replica) {
     return exchange_both(e);
 }
 
+// 16-byte conversion kernels: rows 16-byte aligned on both sides, one grid row per replica
+static bool vector_layout(const bc_engine* e, int n) {
+    return e->L % 32 == 0 && e->Wc == e->L / 2 && n <= 65535 && (long long)e->Ly * (e->L / 32) < (1LL << 31);
+}
+
 static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool wait = true) {
     BC_CUDA(e, cudaSetDevice(e->device));
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
-    const long long total = (long long)n * e->Ly * e->Wc;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    if (vector_layout(e, n)) {
+        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
+        pack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
+    } else {
+        const long long total = (long long)n * e->Ly * e->Wc;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    }
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     rc = exchange_both(e);
@@ -540,9 +550,14 @@ static int download_range(bc_engine* e, int r0, int n, int8_t* spins, bool wait 
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
-    const long long total = (long long)bytes;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
-    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    if (vector_layout(e, n)) {
+        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
+        unpack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
+    } else {
+        const long long total = (long long)bytes;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    }
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));

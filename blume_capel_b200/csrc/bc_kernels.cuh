@@ -958,6 +958,56 @@ __global__ void unpack_kernel(int8_t* __restrict__ spins, const uint8_t* __restr
     spins[gid] = (int8_t)((int)code - 1);
 }
 
+// Vector forms for L % 32 == 0 (rows are 16-byte aligned, no pad bytes): one thread converts 32 consecutive sites
+// of a row = one 16-byte chunk of each colour array.  grid = (ceil(Ly * L/32 / 256), replicas).
+__device__ __forceinline__ uint32_t spins_to_codes4(uint32_t w) {  // bytes -1,0,1 -> 0,1,2 without inter-byte carries
+    return ((w & 0x03030303u) + ONES) & 0x03030303u;
+}
+__device__ __forceinline__ uint32_t codes_to_spins4(uint32_t c) {  // bytes 0,1,2 -> 0xFF,0,1
+    const uint32_t t = (c + 0x03030303u) & 0x03030303u;  // 3, 0, 1
+    const uint32_t neg = (t >> 1) & ONES;                // 1 where the spin is -1
+    return t | ((neg << 8) - neg);                        // neg * 0xFF per byte (mod 2^32)
+}
+
+__global__ void __launch_bounds__(256)
+pack16_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g, int rep_first) {
+    const uint32_t cpr = (uint32_t)g.L >> 5;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= (uint32_t)g.Ly * cpr) return;
+    const uint32_t r = blockIdx.y, y = idx / cpr, j = idx - y * cpr;
+    const uint4* src = reinterpret_cast<const uint4*>(spins + ((size_t)r * g.Ly + y) * g.L + (size_t)j * 32);
+    const uint4 a = __ldcs(src), b = __ldcs(src + 1);
+    const uint4 ev = make_uint4(spins_to_codes4(__byte_perm(a.x, a.y, 0x6420)), spins_to_codes4(__byte_perm(a.z, a.w, 0x6420)),
+                                spins_to_codes4(__byte_perm(b.x, b.y, 0x6420)), spins_to_codes4(__byte_perm(b.z, b.w, 0x6420)));
+    const uint4 od = make_uint4(spins_to_codes4(__byte_perm(a.x, a.y, 0x7531)), spins_to_codes4(__byte_perm(a.z, a.w, 0x7531)),
+                                spins_to_codes4(__byte_perm(b.x, b.y, 0x7531)), spins_to_codes4(__byte_perm(b.z, b.w, 0x7531)));
+    const size_t dst = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (size_t)j * 16;
+    const bool odd_row = ((y + (uint32_t)g.y_glob0) & 1u) != 0;  // colour 0 holds x = 2k + (row & 1)
+    *reinterpret_cast<uint4*>(c0 + dst) = odd_row ? od : ev;
+    *reinterpret_cast<uint4*>(c1 + dst) = odd_row ? ev : od;
+}
+
+__global__ void __launch_bounds__(256)
+unpack16_kernel(int8_t* __restrict__ spins, const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, const Geom g,
+                int rep_first) {
+    const uint32_t cpr = (uint32_t)g.L >> 5;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= (uint32_t)g.Ly * cpr) return;
+    const uint32_t r = blockIdx.y, y = idx / cpr, j = idx - y * cpr;
+    const size_t src = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (size_t)j * 16;
+    const bool odd_row = ((y + (uint32_t)g.y_glob0) & 1u) != 0;
+    const uint4 p = *reinterpret_cast<const uint4*>(c0 + src), q = *reinterpret_cast<const uint4*>(c1 + src);
+    const uint4 ev = odd_row ? q : p, od = odd_row ? p : q;
+    uint4 a, b;
+    a.x = codes_to_spins4(__byte_perm(ev.x, od.x, 0x5140)); a.y = codes_to_spins4(__byte_perm(ev.x, od.x, 0x7362));
+    a.z = codes_to_spins4(__byte_perm(ev.y, od.y, 0x5140)); a.w = codes_to_spins4(__byte_perm(ev.y, od.y, 0x7362));
+    b.x = codes_to_spins4(__byte_perm(ev.z, od.z, 0x5140)); b.y = codes_to_spins4(__byte_perm(ev.z, od.z, 0x7362));
+    b.z = codes_to_spins4(__byte_perm(ev.w, od.w, 0x5140)); b.w = codes_to_spins4(__byte_perm(ev.w, od.w, 0x7362));
+    uint4* dst = reinterpret_cast<uint4*>(spins + ((size_t)r * g.Ly + y) * g.L + (size_t)j * 32);
+    __stcs(dst, a);
+    __stcs(dst + 1, b);
+}
+
 // iid uniform {-1,0,1} (main.cpp:166-171) from Philox stream INIT, indexed by the GLOBAL site index x + y*L
 __global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g, int rep_first,
                             int n_rep, uint32_t key0, uint32_t key1) {
