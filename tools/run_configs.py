@@ -35,13 +35,17 @@ def config1():
     return out
 
 
-def config3(sweeps=200):
-    """Finite-size-scaling ladder: L = 32..2048, one GPU's share = 8 (T,D) points x 7 sizes, concurrent engines."""
+def config3(sweeps=200, ladder_rows=int(os.environ.get("BC_LADDER_ROWS", "8"))):
+    """Finite-size-scaling ladder: L = 32..2048, one GPU's share = 8 (T,D) points x 7 sizes, concurrent engines.
+    The engines share the GPU, so each one may use longer strips (fewer, more efficient CTAs) than the plan it
+    would pick for itself alone: ladder_rows > 0 sets "rows_per_thread" for the streaming sizes."""
     sizes = [32, 64, 128, 256, 512, 1024, 2048]
     pts = [(0.58 + 0.06 * i / 7, 1.94 + 0.05 * (i % 8) / 7) for i in range(8)]
     engines = []
     for L in sizes:
         e = bc.Engine(L, bc.PERIODIC, len(pts), 0, 0x5EED0003 + L)
+        if ladder_rows and L >= 256:
+            e.set_option("rows_per_thread", min(ladder_rows, L // 8))
         for r, (t, d) in enumerate(pts):
             e.set_params(t, d, J, replica=r)
         e.init_random()
@@ -58,7 +62,7 @@ def config3(sweeps=200):
     sites = sum(L * L * len(pts) for L in sizes)
     per = {str(e.L): e.last_sweep_ms() for e in engines}
     out = {"config": 3, "workload": "FSS ladder L=32..2048 x 8 (T,D) points per GPU (1/8 of the 64-point grid), per-replica tables",
-           "sweeps": sweeps, "sites_per_sweep": sites, "wall_ms": wall * 1e3, "updates_per_ns": sites * sweeps / (wall * 1e9),
+           "sweeps": sweeps, "ladder_rows": ladder_rows, "sites_per_sweep": sites, "wall_ms": wall * 1e3, "updates_per_ns": sites * sweeps / (wall * 1e9),
            "device_ms_per_size": per, "plans": {str(e.L): e.plan() for e in engines}}
     for e in engines:
         e.close()
