@@ -139,7 +139,7 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": value, "unit": "spin-updates/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be built for L >= 512 (main.cpp:57-59); its per-attempt rate is size independent",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -163,7 +163,6 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -318,7 +317,7 @@ def run_ours(args, rank, world, local_rank):
             "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
                       "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": ties_resident},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     for row in engs:
         for e_k in row:
             e_k.close()
@@ -326,7 +325,26 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private copy of fd 1 for it and point fd 1 at stderr, so
+    whatever libraries print there (NCCL's version banner at NCCL_DEBUG=VERSION, build output) cannot mix in."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
