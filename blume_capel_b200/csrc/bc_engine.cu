@@ -95,7 +95,7 @@ struct bc_engine {
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
     uint32_t* d_tab31 = nullptr;
-    uint32_t* d_tab2 = nullptr;   // [replica][54*54] pair tables of the streaming kernel (L % 32 == 0, L >= 256)
+    uint32_t* d_tab2 = nullptr;   // [replica][54*54] pair tables of the streaming kernel (L % 32 == 0, L >= 128)
     std::vector<uint32_t> h_tab31;
     std::vector<uint8_t> params_set;
     unsigned long long* d_obs = nullptr;
@@ -115,11 +115,16 @@ struct bc_engine {
     int64_t* d_clock = nullptr;      // device-resident sweep counter read by graph-captured kernels
     cudaGraphExec_t graph_exec = nullptr;
     int graph_rows = -1, graph_block = 0;  // plan signature the graph was captured for
+    // bc_sweep_group with this handle as member 0: graph of a block of unmeasured group sweeps + what it was built for
+    cudaGraphExec_t group_graph = nullptr;
+    std::vector<uint64_t> group_sig;
+    cudaEvent_t ev_group = nullptr;  // joins / forks the members' streams around a group sweep
     unsigned graph_grid = 0;
     // cluster move scratch
     int32_t* d_parent = nullptr;
     uint8_t* d_bonds = nullptr;
-    int* d_changed = nullptr;
+    int32_t* d_csize = nullptr;             // cluster sizes per root (bc_cluster_moments), allocated on first use
+    unsigned long long* d_cmom = nullptr;   // [replica][3] moments
     size_t cluster_cap = 0;
     int64_t cluster_step = 0;  // counter of the cluster-move RNG streams
     std::vector<double> h_TJ;  // (T, J) per replica, for the bond probability
@@ -222,8 +227,10 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->ev_halo) cudaEventDestroy(e->ev_halo);
     if (e->halo_stream) cudaStreamDestroy(e->halo_stream);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->group_graph) cudaGraphExecDestroy(e->group_graph);
+    if (e->ev_group) cudaEventDestroy(e->ev_group);
     cudaFree(e->d_clock);
-    cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_changed);
+    cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_csize); cudaFree(e->d_cmom);
     cudaFree(e->d_wave);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31); cudaFree(e->d_tab2);
@@ -296,7 +303,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_c[1], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
-    if (L % 32 == 0 && L >= 256 &&
+    if (L % 32 == 0 && L >= 128 &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
     if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
         fast_fn pf[10];
@@ -523,12 +530,8 @@ static bool vector_layout(const bc_engine* e, int n) {
     return e->L % 32 == 0 && e->Wc == e->L / 2 && n <= 65535 && (long long)e->Ly * (e->L / 32) < (1LL << 31);
 }
 
-static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool wait = true) {
-    BC_CUDA(e, cudaSetDevice(e->device));
-    const size_t bytes = (size_t)n * e->Ly * e->L;
-    int rc = ensure_stage(e, bytes);
-    if (rc != BC_OK) return rc;
-    BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
+// reference layout (row-major int8 in d_stage, replicas r0 .. r0+n-1 at the start of the buffer) <-> compact colour arrays
+static int stage_to_device(bc_engine* e, int r0, int n) {
     if (vector_layout(e, n)) {
         const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
         pack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
@@ -539,6 +542,31 @@ static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool w
     }
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int stage_from_device(bc_engine* e, int r0, int n) {
+    if (vector_layout(e, n)) {
+        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
+        unpack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
+    } else {
+        const long long total = (long long)n * e->Ly * e->L;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    }
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool wait = true) {
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * e->Ly * e->L;
+    int rc = ensure_stage(e, bytes);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
+    rc = stage_to_device(e, r0, n);
+    if (rc != BC_OK) return rc;
     rc = exchange_both(e);
     if (rc != BC_OK) return rc;
     if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
@@ -550,16 +578,8 @@ static int download_range(bc_engine* e, int r0, int n, int8_t* spins, bool wait 
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
-    if (vector_layout(e, n)) {
-        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
-        unpack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
-    } else {
-        const long long total = (long long)bytes;
-        const unsigned blocks = (unsigned)((total + 255) / 256);
-        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
-    }
-    ++e->launches;
-    BC_CUDA(e, cudaGetLastError());
+    rc = stage_from_device(e, r0, n);
+    if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
     if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));
     return BC_OK;
@@ -698,10 +718,9 @@ static LaunchPlan make_plan(const bc_engine* e) {
     return p;
 }
 
-// part: 0 = all strips, 1 = the two boundary strips of the slab, 2 = the interior strips
-static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
-                       const int64_t* t_ptr = nullptr, int part = 0, cudaStream_t stream = nullptr) {
-    if (!stream) stream = e->stream;
+// kernel arguments of one half-sweep (colour `col`) of all strips of handle e
+static SweepParams sweep_params(const bc_engine* e, const LaunchPlan& plan, int col, int64_t t, int64_t slot,
+                                const int64_t* t_ptr) {
     SweepParams P;
     P.own = e->d_c[col];
     P.other = e->d_c[1 - col];
@@ -722,6 +741,23 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
     P.Ly = e->Ly;
     P.peer_prev = nullptr;
     P.peer_next = nullptr;
+    P.Wc = e->Wc;
+    P.cpr = plan.cpr;
+    P.strips = plan.strips;
+    P.strip_base = 0;
+    P.strip_stride = 1;
+    P.n_replicas = e->n_rep;
+    P.open = e->boundary == BC_OPEN;
+    P.key0 = (uint32_t)e->seed;
+    P.key1 = (uint32_t)(e->seed >> 32);
+    return P;
+}
+
+// part: 0 = all strips, 1 = the two boundary strips of the slab, 2 = the interior strips
+static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
+                       const int64_t* t_ptr = nullptr, int part = 0, cudaStream_t stream = nullptr) {
+    if (!stream) stream = e->stream;
+    SweepParams P = sweep_params(e, plan, col, t, slot, t_ptr);
     // boundary-strip launch of a peer-memory slab: the kernel itself stores the halo rows into the neighbours
     const bool fused_halo = part == 1 && e->p2p && e->opt_fused_halo && plan.fast && !plan.small;
     if (fused_halo) {
@@ -729,19 +765,10 @@ static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measu
         if (e->rank > 0 || periodic) P.peer_prev = e->peer_prev_c[col];
         if (e->rank + 1 < e->nranks || periodic) P.peer_next = e->peer_next_c[col];
     }
-    P.Wc = e->Wc;
-    P.cpr = plan.cpr;
-    P.strips = plan.strips;
-    P.strip_base = 0;
-    P.strip_stride = 1;
     unsigned grid = plan.grid;
     if (part == 1) { P.strips = 2; P.strip_stride = plan.strips - 1; }
     if (part == 2) { P.strips = plan.strips - 2; P.strip_base = 1; }
     if (part != 0) grid = (unsigned)(((long long)e->n_rep * P.strips * plan.cpr + FAST_THREADS - 1) / FAST_THREADS);
-    P.n_replicas = e->n_rep;
-    P.open = e->boundary == BC_OPEN;
-    P.key0 = (uint32_t)e->seed;
-    P.key1 = (uint32_t)(e->seed >> 32);
     if (plan.fast) {
         fast_fn fn = pick_fast(col, plan.small, measure, e->boundary == BC_OPEN, fused_halo, plan.pair);
         if (e->opt_pdl) {
@@ -966,15 +993,8 @@ static int launch_resident(bc_engine* e, const ResidentPlan& rp, int64_t t0, int
     return BC_OK;
 }
 
-extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out) {
-    if (!e) return BC_ERR_ARG;
-    if (n_sweeps < 0 || measure_every < 0) return fail(e, BC_ERR_ARG, "bc_sweep: negative count");
-    for (int r = 0; r < e->n_rep; ++r)
-        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, "bc_sweep: bc_set_params not called for every replica");
-    BC_CUDA(e, cudaSetDevice(e->device));
-    const LaunchPlan plan = make_plan(e);
-
-    // measured sweeps: t with (t+1) % measure_every == 0
+// The measured sweeps of a call (t with (t+1) % measure_every == 0) and zeroed device slots for their sums.
+static int prepare_obs(bc_engine* e, int64_t n_sweeps, int64_t measure_every) {
     e->pending_meas = 0;
     e->pending_sweeps.clear();
     if (measure_every > 0)
@@ -991,6 +1011,20 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
         }
         BC_CUDA(e, cudaMemsetAsync(e->d_obs, 0, (size_t)n_meas * e->n_rep * OBS_RAW * sizeof(unsigned long long), e->stream));
     }
+    return BC_OK;
+}
+
+extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out) {
+    if (!e) return BC_ERR_ARG;
+    if (n_sweeps < 0 || measure_every < 0) return fail(e, BC_ERR_ARG, "bc_sweep: negative count");
+    for (int r = 0; r < e->n_rep; ++r)
+        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, "bc_sweep: bc_set_params not called for every replica");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const LaunchPlan plan = make_plan(e);
+
+    int rc0 = prepare_obs(e, n_sweeps, measure_every);
+    if (rc0 != BC_OK) return rc0;
+    const int64_t n_meas = (int64_t)e->pending_sweeps.size();
 
     BC_CUDA(e, cudaEventRecord(e->ev0, e->stream));
     const ResidentPlan rp = resident_plan(e);
@@ -1031,6 +1065,227 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
         if (rc != BC_OK) return rc;
         e->pending_meas = 0;  // fetched (and, for slabs, already all-reduced in place)
         return n_meas * e->n_rep;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// group sweep: several handles (different L), one launch per half-sweep (sweep_group_kernel)
+// ---------------------------------------------------------------------------------------------
+typedef void (*group_fn)(const GroupParams);
+
+template <int COL>
+static group_fn pick_group(bool meas, bool open, bool pair) {
+    if (pair) {
+        if (meas) return open ? (group_fn)sweep_group_kernel<COL, true, true, 1> : (group_fn)sweep_group_kernel<COL, true, false, 1>;
+        return open ? (group_fn)sweep_group_kernel<COL, false, true, 1> : (group_fn)sweep_group_kernel<COL, false, false, 1>;
+    }
+    if (meas) return open ? (group_fn)sweep_group_kernel<COL, true, true, 0> : (group_fn)sweep_group_kernel<COL, true, false, 0>;
+    return open ? (group_fn)sweep_group_kernel<COL, false, true, 0> : (group_fn)sweep_group_kernel<COL, false, false, 0>;
+}
+
+// rows per thread R for a member of a group: even, whole strips, whole CTAs per replica (the !SMALL kernels)
+static bool group_rows_valid(const bc_engine* e, int R) {
+    const int cpr = e->L / 32;
+    return R >= 2 && !(R & 1) && rows_valid(e->Ly, cpr, R) && (((long long)(e->Ly / R) * cpr) % FAST_THREADS) == 0;
+}
+
+static int group_best_rows(const bc_engine* e, int target) {
+    for (int R = target; R >= 2; R >>= 1)
+        if (group_rows_valid(e, R)) return R;
+    return 0;
+}
+
+struct GroupPlan {
+    int n = 0;
+    LaunchPlan plan[GROUP_MAX];
+    unsigned cta_end[GROUP_MAX];
+    bool pair = false, open = false;
+};
+
+// One half-sweep of every member: t = members' own counters + `s` (or + *t_ptr, the clock of member 0, in a graph)
+static void launch_group_half(bc_engine* const* es, const GroupPlan& gp, int col, bool measure, int64_t s, int64_t slot,
+                              const int64_t* t_ptr) {
+    bc_engine* e0 = es[0];
+    GroupParams G;
+    memset(&G, 0, sizeof(G));
+    G.n = gp.n;
+    for (int g = 0; g < gp.n; ++g) {
+        // with a clock the kernel adds member 0's absolute counter: pass this member's offset from it
+        const int64_t t = t_ptr ? s + (es[g]->t - e0->t) : es[g]->t + s;
+        G.p[g] = sweep_params(es[g], gp.plan[g], col, t, slot, t_ptr);
+        G.cta_end[g] = gp.cta_end[g];
+    }
+    group_fn fn = col == 0 ? pick_group<0>(measure, gp.open, gp.pair) : pick_group<1>(measure, gp.open, gp.pair);
+    const unsigned grid = gp.cta_end[gp.n - 1];
+    if (e0->opt_pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(FAST_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = e0->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, fn, G);
+    } else {
+        fn<<<grid, FAST_THREADS, 0, e0->stream>>>(G);
+    }
+    ++e0->launches;
+}
+
+// graph of `block` unmeasured group sweeps, cached on member 0 and keyed by everything baked into its kernels
+static int ensure_group_graph(bc_engine* const* es, const GroupPlan& gp, int block) {
+    bc_engine* e0 = es[0];
+    std::vector<uint64_t> sig;
+    sig.push_back((uint64_t)gp.n); sig.push_back((uint64_t)block); sig.push_back((uint64_t)gp.pair); sig.push_back((uint64_t)e0->opt_pdl);
+    for (int g = 0; g < gp.n; ++g) {
+        sig.push_back((uint64_t)(uintptr_t)es[g]->d_c[0]); sig.push_back((uint64_t)(uintptr_t)es[g]->d_tab16);
+        sig.push_back((uint64_t)es[g]->seed); sig.push_back((uint64_t)gp.plan[g].rows);
+        sig.push_back((uint64_t)(es[g]->t - e0->t)); sig.push_back((uint64_t)es[g]->n_rep);
+    }
+    if (e0->group_graph && sig == e0->group_sig) return BC_OK;
+    if (e0->group_graph) { cudaGraphExecDestroy(e0->group_graph); e0->group_graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    BC_CUDA(e0, cudaStreamBeginCapture(e0->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t launches_before = e0->launches;
+    for (int s = 0; s < block; ++s) {
+        launch_group_half(es, gp, 0, false, s, 0, e0->d_clock);
+        launch_group_half(es, gp, 1, false, s, 0, e0->d_clock);
+    }
+    clock_add_kernel<<<1, 1, 0, e0->stream>>>(e0->d_clock, (int64_t)block);
+    e0->launches = launches_before;  // capturing is not launching
+    cudaError_t st = cudaStreamEndCapture(e0->stream, &graph);
+    if (st != cudaSuccess) return fail(e0, BC_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(st));
+    st = cudaGraphInstantiate(&e0->group_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (st != cudaSuccess) { e0->group_graph = nullptr; return fail(e0, BC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(st)); }
+    e0->group_sig = sig;
+    return BC_OK;
+}
+
+extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int64_t n_sweeps, int64_t measure_every) {
+    if (!engines || n_engines < 1 || !engines[0]) return BC_ERR_ARG;
+    bc_engine* e0 = engines[0];
+    if (n_engines > GROUP_MAX) return fail(e0, BC_ERR_ARG, "bc_sweep_group: at most 8 handles per group");
+    if (n_sweeps < 0 || measure_every < 0) return fail(e0, BC_ERR_ARG, "bc_sweep_group: negative count");
+    for (int g = 0; g < n_engines; ++g) {
+        bc_engine* e = engines[g];
+        if (!e) return fail(e0, BC_ERR_ARG, "bc_sweep_group: null handle");
+        for (int h = 0; h < g; ++h)
+            if (engines[h] == e) return fail(e0, BC_ERR_ARG, "bc_sweep_group: a handle appears twice");
+        if (e->device != e0->device || e->boundary != e0->boundary)
+            return fail(e0, BC_ERR_ARG, "bc_sweep_group: the handles must share the device and the boundary condition");
+        if (e->ghost) return fail(e0, BC_ERR_UNSUPPORTED, "bc_sweep_group: slab handles cannot join a group");
+        if (e->L % 32 || !group_best_rows(e, 2 << 20))
+            return fail(e0, BC_ERR_UNSUPPORTED, "bc_sweep_group: a member needs L % 32 == 0 and L >= 128 (use bc_sweep for it)");
+        for (int r = 0; r < e->n_rep; ++r)
+            if (!e->params_set[r]) return fail(e0, BC_ERR_STATE, "bc_sweep_group: bc_set_params not called for every replica");
+        if (measure_every > 0 && e->t != e0->t)
+            return fail(e0, BC_ERR_STATE, "bc_sweep_group: measuring needs equal sweep counters on all handles");
+    }
+    BC_CUDA(e0, cudaSetDevice(e0->device));
+
+    // rows per thread: the longest strips (<= 32 rows, or member 0's "rows_per_thread") that still give the
+    // whole group enough threads to fill the chip
+    GroupPlan gp;
+    gp.n = n_engines;
+    gp.open = e0->boundary == BC_OPEN;
+    int target = 2;
+    if (e0->opt_rows > 0) {
+        target = e0->opt_rows;
+    } else {
+        const long long want = 148LL * 768;
+        for (int cand = 32; cand >= 2; cand >>= 1) {
+            long long threads = 0;
+            for (int g = 0; g < n_engines; ++g) {
+                const int R = group_best_rows(engines[g], cand);
+                threads += (long long)engines[g]->n_rep * (engines[g]->Ly / R) * (engines[g]->L / 32);
+            }
+            target = cand;
+            if (threads >= want) break;
+        }
+    }
+    unsigned long long ctas = 0;
+    long long sites_long = 0, sites_all = 0;  // the pair table pays for strips of >= pair_min_rows rows
+    bool have_tab2 = true;
+    for (int g = 0; g < n_engines; ++g) {
+        const bc_engine* e = engines[g];
+        LaunchPlan& p = gp.plan[g];
+        p.fast = true; p.small = false;
+        p.cpr = e->L / 32;
+        p.rows = group_best_rows(e, target);
+        p.strips = e->Ly / p.rows;
+        p.grid = (unsigned)(((long long)e->n_rep * p.strips * p.cpr) / FAST_THREADS);
+        ctas += p.grid;
+        if (ctas > 0x7FFFFFFFull) return fail(e0, BC_ERR_UNSUPPORTED, "bc_sweep_group: too many CTAs for one launch");
+        gp.cta_end[g] = (unsigned)ctas;
+        if (!e->d_tab2) have_tab2 = false;
+        sites_all += (long long)e->n_rep * e->Ly * e->L;
+        if (p.rows >= e0->opt_pair_min_rows) sites_long += (long long)e->n_rep * e->Ly * e->L;
+    }
+    // one instantiation per launch: pair-table kernels when the members that profit from them hold most of the sites
+    // (a member with shorter strips only stages the 11.4 KB table more often; the results do not depend on it)
+    gp.pair = have_tab2 && e0->opt_pair_min_rows > 0 && 2 * sites_long >= sites_all;
+
+    if (gp.pair) {  // 6 CTAs x 30 KB per SM need the large shared-memory carve-out
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            for (int m = 0; m < 2; ++m)
+                for (int o = 0; o < 2; ++o) {
+                    cudaFuncSetAttribute(pick_group<0>(m, o, true), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    cudaFuncSetAttribute(pick_group<1>(m, o, true), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                }
+            carveout_set = true;
+        }
+    }
+
+    // join: every member's earlier work (uploads, parameter tables, its obs memset) precedes the group's launches
+    for (int g = 0; g < n_engines; ++g) {
+        bc_engine* e = engines[g];
+        int rc = prepare_obs(e, n_sweeps, measure_every);
+        if (rc != BC_OK) { if (e != e0) e0->err = e->err; return rc; }
+        if (!e->ev_group) BC_CUDA(e0, cudaEventCreateWithFlags(&e->ev_group, cudaEventDisableTiming));
+        if (g > 0) {
+            BC_CUDA(e0, cudaEventRecord(e->ev_group, e->stream));
+            BC_CUDA(e0, cudaStreamWaitEvent(e0->stream, e->ev_group, 0));
+        }
+    }
+    const int64_t n_meas = (int64_t)e0->pending_sweeps.size();
+
+    BC_CUDA(e0, cudaEventRecord(e0->ev0, e0->stream));
+    int64_t done = 0;  // sweeps issued so far (offset from every member's counter)
+    const int block = e0->opt_graph_block;
+    for (int64_t slot = 0; slot <= n_meas; ++slot) {
+        const int64_t until = slot < n_meas ? e0->pending_sweeps[(size_t)slot] - e0->t : n_sweeps;
+        if (e0->opt_use_graph && block > 0 && until - done >= block) {
+            int rc = ensure_group_graph(engines, gp, block);
+            if (rc != BC_OK) return rc;
+            clock_set_kernel<<<1, 1, 0, e0->stream>>>(e0->d_clock, e0->t + done);
+            ++e0->launches;
+            for (; done + block <= until; done += block) {
+                BC_CUDA(e0, cudaGraphLaunch(e0->group_graph, e0->stream));
+                e0->launches += 2 * block + 1;
+            }
+        }
+        for (; done < until; ++done) {
+            launch_group_half(engines, gp, 0, false, done, 0, nullptr);
+            launch_group_half(engines, gp, 1, false, done, 0, nullptr);
+        }
+        if (slot < n_meas) {
+            launch_group_half(engines, gp, 0, true, done, slot, nullptr);
+            launch_group_half(engines, gp, 1, true, done, slot, nullptr);
+            ++done;
+        }
+    }
+    BC_CUDA(e0, cudaEventRecord(e0->ev1, e0->stream));
+    e0->have_timing = true;
+    BC_CUDA(e0, cudaGetLastError());
+    // fork: whatever a member does next on its own stream comes after the group's sweeps
+    BC_CUDA(e0, cudaEventRecord(e0->ev_group, e0->stream));
+    for (int g = 0; g < n_engines; ++g) {
+        bc_engine* e = engines[g];
+        if (g > 0) BC_CUDA(e0, cudaStreamWaitEvent(e->stream, e0->ev_group, 0));
+        e->t += n_sweeps;
+        e->pending_meas = (int64_t)e->pending_sweeps.size();
     }
     return 0;
 }
@@ -1085,30 +1340,23 @@ static int label_clusters(bc_engine* e, uint32_t thr, int64_t cstep, bool always
     if (rc != BC_OK) return rc;
     if (e->cluster_cap < (size_t)total) {
         BC_CUDA(e, cudaStreamSynchronize(e->stream));
-        cudaFree(e->d_parent); cudaFree(e->d_bonds);
-        e->d_parent = nullptr; e->d_bonds = nullptr; e->cluster_cap = 0;
+        cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_csize);
+        e->d_parent = nullptr; e->d_bonds = nullptr; e->d_csize = nullptr; e->cluster_cap = 0;
         BC_CUDA(e, cudaMalloc(&e->d_parent, (size_t)total * sizeof(int32_t)));
         BC_CUDA(e, cudaMalloc(&e->d_bonds, (size_t)total));
-        if (!e->d_changed) BC_CUDA(e, cudaMalloc(&e->d_changed, sizeof(int)));
         e->cluster_cap = (size_t)total;
     }
-    const unsigned blocks = (unsigned)((total + 255) / 256);
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
-    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), 0, e->n_rep);
-    sw_init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, e->n_rep,
-                                                  e->boundary == BC_OPEN, always ? 1 : 0, thr, k0, k1, c_lo, c_hi);
+    rc = stage_from_device(e, 0, e->n_rep);
+    if (rc != BC_OK) return rc;
+    const int tiles_x = (e->L + SW_TX - 1) / SW_TX, tiles_y = (e->L + SW_TY - 1) / SW_TY;
+    const long long ctas = (long long)tiles_x * tiles_y * e->n_rep;
+    if (ctas > 0x7FFFFFFFLL) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: too many tiles for one launch");
+    sw_local_kernel<<<(unsigned)ctas, SW_THREADS, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, tiles_x, tiles_y,
+                                                                  e->boundary == BC_OPEN, always ? 1 : 0, thr, k0, k1, c_lo, c_hi);
+    sw_border_kernel<<<(unsigned)ctas, SW_TX + SW_TY, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, tiles_x, tiles_y);
     e->launches += 2;
-    for (int iter = 0; iter < 64; ++iter) {  // hooking + pointer jumping until no root changes
-        int changed = 0;
-        BC_CUDA(e, cudaMemsetAsync(e->d_changed, 0, sizeof(int), e->stream));
-        sw_hook_kernel<<<blocks, 256, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, e->n_rep, e->d_changed);
-        sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
-        e->launches += 2;
-        BC_CUDA(e, cudaMemcpyAsync(&changed, e->d_changed, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-        BC_CUDA(e, cudaStreamSynchronize(e->stream));
-        if (!changed) break;
-    }
     BC_CUDA(e, cudaGetLastError());
     return BC_OK;
 }
@@ -1141,10 +1389,10 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
         if (rc != BC_OK) return rc;
         const uint32_t c_lo = (uint32_t)((uint64_t)e->cluster_step & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)e->cluster_step >> 32);
         sw_flip_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->L, e->n_rep, k0, k1, c_lo, c_hi);
-        const long long ptotal = (long long)e->n_rep * e->Ly * e->Wc;
-        pack_kernel<<<(unsigned)((ptotal + 255) / 256), 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), 0, e->n_rep);
-        e->launches += 2;
+        ++e->launches;
         BC_CUDA(e, cudaGetLastError());
+        rc = stage_to_device(e, 0, e->n_rep);
+        if (rc != BC_OK) return rc;
         ++e->cluster_step;
     }
     return BC_OK;
@@ -1170,22 +1418,22 @@ extern "C" int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_clus
     if (rc != BC_OK) return rc;
     const long long N = (long long)e->L * e->L, total = N * e->n_rep;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    int32_t* d_size = nullptr;
-    unsigned long long* d_out = nullptr;
-    BC_CUDA(e, cudaMalloc(&d_size, (size_t)total * sizeof(int32_t)));
-    cudaError_t st = cudaMalloc(&d_out, (size_t)e->n_rep * 3 * sizeof(unsigned long long));
-    if (st == cudaSuccess) st = cudaMemsetAsync(d_size, 0, (size_t)total * sizeof(int32_t), e->stream);
+    if (!e->d_csize) BC_CUDA(e, cudaMalloc(&e->d_csize, e->cluster_cap * sizeof(int32_t)));
+    if (!e->d_cmom) BC_CUDA(e, cudaMalloc(&e->d_cmom, (size_t)e->n_rep * 3 * sizeof(unsigned long long)));
+    int32_t* d_size = e->d_csize;
+    unsigned long long* d_out = e->d_cmom;
+    cudaError_t st = cudaMemsetAsync(d_size, 0, (size_t)total * sizeof(int32_t), e->stream);
     if (st == cudaSuccess) st = cudaMemsetAsync(d_out, 0, (size_t)e->n_rep * 3 * sizeof(unsigned long long), e->stream);
     std::vector<unsigned long long> h((size_t)e->n_rep * 3);
     if (st == cudaSuccess) {
+        sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
         sw_count_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, d_size, e->L, e->n_rep);
-        sw_moments_kernel<<<blocks, 256, 0, e->stream>>>(d_size, e->L, e->n_rep, d_out);
-        e->launches += 2;
+        sw_moments_kernel<<<(unsigned)((total + SW_MOM_PER_CTA - 1) / SW_MOM_PER_CTA), 256, 0, e->stream>>>(d_size, e->L, e->n_rep, d_out);
+        e->launches += 3;
         st = cudaGetLastError();
     }
     if (st == cudaSuccess) st = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
     if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
-    cudaFree(d_size); cudaFree(d_out);
     if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_cluster_moments: ") + cudaGetErrorString(st));
     for (int r = 0; r < e->n_rep; ++r) {
         out[r].sum_size_sq = (int64_t)h[(size_t)r * 3]; out[r].max_size = (int64_t)h[(size_t)r * 3 + 1];

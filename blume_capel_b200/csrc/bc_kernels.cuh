@@ -285,9 +285,10 @@ struct FastMinBlocks {
         (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
 };
 
-template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, int PAIR = 0>
-__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR>::value)
-sweep_fast_kernel(const __grid_constant__ SweepParams P) {
+// The kernel body; `bid` is the CTA's index among the CTAs that work on P's lattices (blockIdx.x for an ordinary
+// launch, blockIdx.x minus the group's first CTA for a group launch, see sweep_group_kernel).
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO, int PAIR>
+__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid) {
     static_assert(!(PAIR && SMALL) && !(PAIR && HALO), "the pair table is one replica per CTA; HALO kernels use the per-site table");
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
@@ -305,7 +306,7 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const uint32_t ipr = (uint32_t)(P.strips * P.cpr);  // items per replica
-    const unsigned long long gid0 = (unsigned long long)blockIdx.x * FAST_THREADS;
+    const unsigned long long gid0 = (unsigned long long)bid * FAST_THREADS;
     const uint32_t rep0 = (uint32_t)(gid0 / ipr);
     for (int i = threadIdx.x; i < (SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS; i += FAST_THREADS) {
         const uint32_t r = rep0 + i / TAB16_WORDS;
@@ -509,6 +510,38 @@ sweep_fast_kernel(const __grid_constant__ SweepParams P) {
         }
     }
     if (n_ties && P.ties) atomicAdd(P.ties, (unsigned long long)n_ties);
+}
+
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, int PAIR = 0>
+__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR>::value)
+sweep_fast_kernel(const __grid_constant__ SweepParams P) {
+    sweep_fast_body<COL, SMALL, MEASURE, OPEN, HALO, PAIR>(P, blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Group launch: ONE grid updates the lattices of up to GROUP_MAX engine handles of different sizes (a
+// finite-size-scaling ladder, config 3; the open-boundary size series, config 5).  Each handle keeps its own
+// geometry, tables, Philox key, sweep counter and observable slots (its SweepParams); the CTAs are dealt out
+// handle after handle and a CTA finds its handle by comparing blockIdx.x with the prefix sums.  Per-handle
+// launches of small lattices are launch-latency-bound and, on separate streams, queue behind the big
+// lattice's CTAs; one grid has one tail.  Same body, same results as sweep_fast_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int GROUP_MAX = 8;
+struct GroupParams {
+    SweepParams p[GROUP_MAX];
+    unsigned cta_end[GROUP_MAX];  // exclusive prefix end of each handle's CTAs
+    int n;
+};
+
+template <int COL, bool MEASURE, bool OPEN, int PAIR>
+__global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
+sweep_group_kernel(const __grid_constant__ GroupParams G) {
+    int g = 0;
+#pragma unroll
+    for (int i = 0; i < GROUP_MAX - 1; ++i)
+        if (i + 1 < G.n && blockIdx.x >= G.cta_end[i]) g = i + 1;
+    const unsigned first = g ? G.cta_end[g - 1] : 0u;
+    sweep_fast_body<COL, false, MEASURE, OPEN, false, PAIR>(G.p[g], blockIdx.x - first);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1163,83 +1196,207 @@ __global__ void measure_kernel(const uint8_t* __restrict__ c0, const uint8_t* __
 // ------------------------------------------------------------------------------------------
 // Cluster move (Swendsen-Wang on the +-1 spins; zeros never join, like wolff() of main.cpp:113-154; bond
 // probability 1 - exp(-2J/T), main.cpp:115).  Works on the row-major int8 staging copy of the lattices:
-// bonds from Philox stream 3, connected components by min-root hooking + pointer jumping (the root of a
-// cluster is its smallest site index, so the result does not depend on the order of the unions), one
-// flip bit per cluster from Philox stream 4.
+// bonds from Philox stream 3, connected components by union-find where the larger root is always linked
+// under the smaller one (the root of a cluster is its smallest site index, so the result does not depend
+// on the order of the unions), one flip bit per cluster from Philox stream 4.
+//
+// Two levels: sw_local_kernel labels one SW_TX x SW_TY tile per CTA entirely in shared memory (bonds drawn
+// in the same kernel) and writes parent[site] = the tile-local root as a global site index; the bonds that
+// leave a tile (last column / last row of the tile, including the periodic wrap) are merged afterwards by
+// sw_border_kernel with global compare-and-swap.  A union only returns once its two trees are one, so a
+// single pass over the bonds is complete: no convergence loop, no host round trip.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int32_t sw_find(const int32_t* __restrict__ parent, int32_t a) {
+constexpr int SW_TX = 64, SW_TY = 64, SW_THREADS = 512;
+
+// find with path halving; every value ever stored in lab[a] is an ancestor of a, so concurrent finds and
+// unions only ever see valid (possibly longer) paths.  Roots are never written by the halving store.
+__device__ __forceinline__ int32_t sw_find_halve(volatile int32_t* lab, int32_t a) {
+    int32_t p = lab[a];
+    while (p != a) {
+        const int32_t g = lab[p];
+        if (g != p) lab[a] = g;
+        a = p;
+        p = g;
+    }
+    return a;
+}
+
+// link the larger root under the smaller one; retry from the current roots if the larger one stopped being a
+// root meanwhile (trees only ever merge)
+__device__ __forceinline__ void sw_union(volatile int32_t* lab, int32_t a, int32_t b) {
+    int32_t ra = sw_find_halve(lab, a), rb = sw_find_halve(lab, b);
+    while (ra != rb) {
+        if (ra < rb) { const int32_t t = ra; ra = rb; rb = t; }
+        const int32_t old = atomicCAS(const_cast<int32_t*>(lab) + ra, ra, rb);
+        if (old == ra) break;
+        ra = sw_find_halve(lab, old);
+        rb = sw_find_halve(lab, rb);
+    }
+}
+
+__device__ __forceinline__ int32_t sw_find(const int32_t* parent, int32_t a) {
     int32_t p = parent[a];
     while (p != a) { a = p; p = parent[a]; }
     return a;
 }
 
-// bonds[i]: bit 0 = bond to +x neighbour open, bit 1 = bond to +y neighbour open; parent[i] = i
-__global__ void sw_init_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, int32_t* __restrict__ parent,
-                               int L, int n_rep, int open, int always, uint32_t bond_thr, uint32_t key0, uint32_t key1,
-                               uint32_t c_lo, uint32_t c_hi) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * n_rep) return;
-    const int rep = (int)(gid / N);
-    const int32_t i = (int32_t)(gid - (long long)rep * N);
-    const int y = i / L, x = i - y * L;
-    const int8_t* sp = spins + (size_t)rep * N;
-    const int8_t s = sp[i];
-    parent[gid] = i;
-    uint32_t b = 0;
-    if (s != 0) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (!always) philox4x32_10((uint32_t)(i >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, key1 ^ (uint32_t)rep, w);
-#pragma unroll
-        for (int dir = 0; dir < 2; ++dir) {
-            int nx = x + (dir == 0), ny = y + (dir == 1);
-            if (nx == L || ny == L) {
-                if (open) continue;
-                nx = nx == L ? 0 : nx;
-                ny = ny == L ? 0 : ny;
-            }
-            const int32_t j = nx + ny * L;
-            if (j != i && sp[j] == s && (always || w[2 * (i & 1) + dir] < bond_thr)) b |= 1u << dir;
-        }
-    }
-    bonds[gid] = (uint8_t)b;
+// Root of site i once all unions are done (no concurrent linking): site -> tile-local root t (one hop) -> chain of
+// tile roots.  The chain above t is shared by the whole tile; whoever walks it points t straight at the root
+// (plain cached loads: a stale value is an older, still valid ancestor).
+__device__ __forceinline__ int32_t sw_root_shorten(int32_t* par, int32_t i) {
+    const int32_t t = par[i];
+    const int32_t pt = par[t];
+    if (pt == t) return t;
+    const int32_t root = sw_find(par, pt);
+    if (root != pt) par[t] = root;
+    return root;
 }
 
-// one hooking pass: for every open bond link the larger root under the smaller one
-__global__ void sw_hook_kernel(const uint8_t* __restrict__ bonds, int32_t* __restrict__ parent, int L, int n_rep,
-                               int* __restrict__ changed) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * n_rep) return;
-    const uint32_t b = bonds[gid];
-    if (!b) return;
-    const int rep = (int)(gid / N);
-    const int32_t i = (int32_t)(gid - (long long)rep * N);
-    const int y = i / L, x = i - y * L;
-    int32_t* par = parent + (size_t)rep * N;
+// bonds site (x, y) with spin s could have: bit 0 = +x neighbour equal, bit 1 = +y neighbour equal (periodic wrap
+// unless open; a site is never bonded to itself, which only matters for L = 1)
+__device__ __forceinline__ uint32_t sw_candidates(const int8_t* __restrict__ sp, int L, int open, int x, int y, int8_t s) {
+    uint32_t cand = 0;
+    if (s == 0) return 0;
+    const int32_t i = x + y * L;
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
-        if (!(b & (1u << dir))) continue;
-        const int nx = (x + (dir == 0)) % L, ny = (y + (dir == 1)) % L;
-        int32_t ra = sw_find(par, i), rb = sw_find(par, nx + ny * L);
-        while (ra != rb) {  // link the larger root under the smaller one; retry if it stopped being a root meanwhile
-            if (ra < rb) { const int32_t t = ra; ra = rb; rb = t; }
-            const int32_t old = atomicCAS(&par[ra], ra, rb);
-            *changed = 1;
-            if (old == ra) break;      // ra was still a root: linked (trees only ever merge)
-            ra = sw_find(par, old);    // ra had been linked elsewhere: continue from the current roots
-            rb = sw_find(par, rb);
+        int nx = x + (dir == 0), ny = y + (dir == 1);
+        if (nx == L || ny == L) {
+            if (open) continue;
+            nx = nx == L ? 0 : nx;
+            ny = ny == L ? 0 : ny;
+        }
+        const int32_t j = nx + ny * L;
+        if (j != i && sp[j] == s) cand |= 1u << dir;
+    }
+    return cand;
+}
+
+// grid = n_rep * tiles_x * tiles_y CTAs.  A warp owns whole tile rows (lane l = sites 2l, 2l+1 of the row):
+//  1. bonds: the two sites of a lane are the two halves of ONE Philox call when L is even (site i uses words
+//     2(i&1), 2(i&1)+1 of counter i>>1); bonds[] (bit 0 = bond to the +x neighbour open, bit 1 = +y) is only
+//     written for the sites of a tile's last column / last row, the ones sw_border_kernel reads;
+//  2. horizontal runs from two ballots: every site starts with the label of the first site of its run, so
+//     the horizontal bonds cost no union at all;
+//  3. vertical bonds: one union per bond unless the bond to its left joins the same two runs;
+//  4. parent[site] = the tile-local root as a global site index.
+__global__ void __launch_bounds__(SW_THREADS, 3)
+sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, int32_t* __restrict__ parent, int L,
+                int tiles_x, int tiles_y, int open, int always, uint32_t bond_thr, uint32_t key0, uint32_t key1,
+                uint32_t c_lo, uint32_t c_hi) {
+    static_assert(SW_TX == 64 && SW_THREADS % 32 == 0, "a warp covers one 64-site tile row");
+    __shared__ __align__(16) int32_t lab[SW_TX * SW_TY];
+    __shared__ __align__(16) uint8_t bnd[SW_TX * SW_TY];
+    constexpr int WARPS = SW_THREADS / 32;
+    const int tiles = tiles_x * tiles_y;
+    const int rep = (int)(blockIdx.x / (unsigned)tiles), tile = (int)(blockIdx.x - (unsigned)rep * tiles);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x0 = tx * SW_TX, y0 = ty * SW_TY;
+    const int w = min(SW_TX, L - x0), h = min(SW_TY, L - y0);
+    const size_t N = (size_t)L * L;
+    const int8_t* sp = spins + (size_t)rep * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = 2 * lane;
+    const bool v0 = lx < w, v1 = lx + 1 < w;
+    const uint32_t k1r = key1 ^ (uint32_t)rep;
+
+    for (int ly = warp; ly < h; ly += WARPS) {
+        const int x = x0 + lx, y = y0 + ly;
+        const int32_t i0 = x + y * L;
+        const int8_t s0 = v0 ? sp[i0] : (int8_t)0, s1 = v1 ? sp[i0 + 1] : (int8_t)0;
+        uint32_t b0 = v0 ? sw_candidates(sp, L, open, x, y, s0) : 0u;
+        uint32_t b1 = v1 ? sw_candidates(sp, L, open, x + 1, y, s1) : 0u;
+        if ((b0 | b1) && !always) {
+            uint32_t r[4];
+            if (!(i0 & 1)) {  // both sites in one call
+                philox4x32_10((uint32_t)(i0 >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, k1r, r);
+                b0 &= (r[0] < bond_thr ? 1u : 0u) | (r[1] < bond_thr ? 2u : 0u);
+                b1 &= (r[2] < bond_thr ? 1u : 0u) | (r[3] < bond_thr ? 2u : 0u);
+            } else {          // odd L, odd row start: i0 is the second half of one call, i0 + 1 the first of the next
+                if (b0) {
+                    philox4x32_10((uint32_t)(i0 >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, k1r, r);
+                    b0 &= (r[2] < bond_thr ? 1u : 0u) | (r[3] < bond_thr ? 2u : 0u);
+                }
+                if (b1) {
+                    philox4x32_10((uint32_t)((i0 + 1) >> 1), c_lo, c_hi, STREAM_BOND << 1, key0, k1r, r);
+                    b1 &= (r[0] < bond_thr ? 1u : 0u) | (r[1] < bond_thr ? 2u : 0u);
+                }
+            }
+        }
+        const int l0 = ly * SW_TX + lx;
+        *reinterpret_cast<uchar2*>(&bnd[l0]) = make_uchar2((uint8_t)b0, (uint8_t)b1);
+        const bool last_row = ly == h - 1;
+        if (v0 && (last_row || lx == w - 1)) bonds[(size_t)rep * N + i0] = (uint8_t)b0;
+        if (v1 && (last_row || lx + 1 == w - 1)) bonds[(size_t)rep * N + i0 + 1] = (uint8_t)b1;
+        // runs: E bit l = sites 2l and 2l+1 joined, A bit l = sites 2l-1 and 2l joined (inside the tile)
+        const uint32_t E = __ballot_sync(0xFFFFFFFFu, (b0 & 1u) && v1);
+        const uint32_t A = __ballot_sync(0xFFFFFFFFu, (b1 & 1u) && lx + 2 < w) << 1;
+        const uint32_t both = A & (E << 1);                 // bit l: site 2l joined to site 2l-2
+        const uint32_t stop = ~both & ((2u << lane) - 1u);   // bit 0 is always a stop
+        const int z = 31 - __clz(stop);                      // the run of site 2l reaches back to pair z
+        const int start0 = 2 * z - (int)((A >> z) & 1u);
+        const int start1 = ((E >> lane) & 1u) ? start0 : lx + 1;
+        *reinterpret_cast<int2*>(&lab[l0]) = make_int2(ly * SW_TX + start0, ly * SW_TX + start1);
+    }
+    __syncthreads();
+    for (int ly = warp; ly + 1 < h; ly += WARPS) {
+        const int l0 = ly * SW_TX + lx;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int l = l0 + k;
+            if (!(bnd[l] & 2u)) continue;
+            // the bond to the left already joins the same two runs
+            if (lx + k > 0 && (bnd[l - 1] & 3u) == 3u && (bnd[l + SW_TX - 1] & 1u)) continue;
+            sw_union(lab, l, l + SW_TX);
+        }
+    }
+    __syncthreads();
+    // local index order == global index order inside a tile, so the local root is the tile's smallest site
+    for (int ly = warp; ly < h; ly += WARPS) {
+        const int l0 = ly * SW_TX + lx;
+        int32_t* dst = parent + (size_t)rep * N + (size_t)(x0 + lx) + (size_t)(y0 + ly) * L;
+        if (v0) {
+            const int32_t r = sw_find(lab, l0);
+            dst[0] = (x0 + (r & (SW_TX - 1))) + (y0 + r / SW_TX) * L;
+        }
+        if (v1) {
+            const int32_t r = sw_find(lab, l0 + 1);
+            dst[1] = (x0 + (r & (SW_TX - 1))) + (y0 + r / SW_TX) * L;
         }
     }
 }
 
+// grid = n_rep * tiles_x * tiles_y CTAs of SW_TX + SW_TY threads: thread j < SW_TY owns the +x bond of row j of
+// the tile's last column, thread SW_TY + j the +y bond of column j of the tile's last row.
+__global__ void __launch_bounds__(SW_TX + SW_TY)
+sw_border_kernel(const uint8_t* __restrict__ bonds, int32_t* __restrict__ parent, int L, int tiles_x, int tiles_y) {
+    const int tiles = tiles_x * tiles_y;
+    const int rep = (int)(blockIdx.x / (unsigned)tiles), tile = (int)(blockIdx.x - (unsigned)rep * tiles);
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int x0 = tx * SW_TX, y0 = ty * SW_TY;
+    const int w = min(SW_TX, L - x0), h = min(SW_TY, L - y0);
+    const size_t N = (size_t)L * L;
+    const int t = threadIdx.x;
+    const int dir = t >= SW_TY;
+    const int lx = dir ? t - SW_TY : w - 1, ly = dir ? h - 1 : t;
+    if (lx >= w || ly >= h) return;
+    const int x = x0 + lx, y = y0 + ly;
+    const int32_t i = x + y * L;
+    if (!(bonds[(size_t)rep * N + i] & (1u << dir))) return;
+    const int nx = dir ? x : (x + 1 == L ? 0 : x + 1), ny = dir ? (y + 1 == L ? 0 : y + 1) : y;
+    sw_union(parent + (size_t)rep * N, i, nx + ny * L);
+}
+
+// parent[i] = root(i) for every site (needed by the size histogram; the flip kernel finds roots itself)
 __global__ void sw_compress_kernel(int32_t* __restrict__ parent, long long total, int L) {
     const long long N = (long long)L * L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     int32_t* par = parent + (gid / N) * N;
     const int32_t i = (int32_t)(gid % N);
-    par[i] = sw_find(par, i);
+    const int32_t p = par[i];  // tile-local root (or i itself)
+    const int32_t r = sw_root_shorten(par, i);
+    if (r != p) par[i] = r;
 }
 
 // cluster sizes: size[root] += 1 for every non-zero site (parent compressed), then per replica
@@ -1248,26 +1405,68 @@ __global__ void sw_count_kernel(const int8_t* __restrict__ spins, const int32_t*
                                 int32_t* __restrict__ size, int L, int n_rep) {
     const long long N = (long long)L * L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * n_rep) return;
-    if (spins[gid] == 0) return;
-    const long long rep = gid / N;
-    atomicAdd(&size[rep * N + parent[gid]], 1);
+    const bool live = gid < N * n_rep && spins[gid] != 0;
+    // neighbouring sites mostly share a root: one atomic per distinct root of a warp, not one per site
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+    if (!live) return;
+    const long long slot = (gid / N) * N + parent[gid];
+    const unsigned same = __match_any_sync(active, slot);
+    if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&size[slot], __popc(same));
 }
 
-__global__ void sw_moments_kernel(const int32_t* __restrict__ size, int L, int n_rep,
-                                  unsigned long long* __restrict__ out /* [rep][3]: sum sq, max, count */) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * n_rep) return;
-    const int32_t sz = size[gid];
-    if (sz == 0) return;
-    unsigned long long* o = out + (gid / N) * 3;
-    atomicAdd(o + 0, (unsigned long long)sz * (unsigned long long)sz);
-    atomicMax(o + 1, (unsigned long long)sz);
-    atomicAdd(o + 2, 1ull);
+// One CTA reduces SW_MOM_PER_CTA consecutive entries: per-thread partial sums, warp shuffles, shared atomics, then
+// three global atomics per CTA (a CTA whose range straddles two replicas falls back to one atomic per entry).
+constexpr int SW_MOM_PER_CTA = 256 * 16;
+__global__ void __launch_bounds__(256)
+sw_moments_kernel(const int32_t* __restrict__ size, int L, int n_rep,
+                  unsigned long long* __restrict__ out /* [rep][3]: sum sq, max, count */) {
+    __shared__ unsigned long long acc[3];
+    const long long N = (long long)L * L, total = N * n_rep;
+    const long long first = (long long)blockIdx.x * SW_MOM_PER_CTA;
+    const long long last = min(first + SW_MOM_PER_CTA, total) - 1;
+    const long long rep = first / N;
+    if (rep != last / N) {
+        for (long long g = first + threadIdx.x; g <= last; g += 256) {
+            const unsigned long long sz = (unsigned long long)size[g];
+            if (sz == 0) continue;
+            unsigned long long* o = out + (g / N) * 3;
+            atomicAdd(o + 0, sz * sz);
+            atomicMax(o + 1, sz);
+            atomicAdd(o + 2, 1ull);
+        }
+        return;
+    }
+    if (threadIdx.x < 3) acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long sq = 0, cnt = 0;
+    unsigned mx = 0;
+    for (long long g = first + threadIdx.x; g <= last; g += 256) {
+        const unsigned sz = (unsigned)size[g];
+        sq += (unsigned long long)sz * sz;
+        cnt += sz != 0;
+        mx = max(mx, sz);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        sq += __shfl_xor_sync(0xFFFFFFFFu, sq, d);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&acc[0], sq);
+        atomicMax(&acc[1], (unsigned long long)mx);
+        atomicAdd(&acc[2], cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && acc[2]) {
+        unsigned long long* o = out + rep * 3;
+        atomicAdd(o + 0, acc[0]);
+        atomicMax(o + 1, acc[1]);
+        atomicAdd(o + 2, acc[2]);
+    }
 }
 
-__global__ void sw_flip_kernel(int8_t* __restrict__ spins, const int32_t* __restrict__ parent, int L, int n_rep,
+__global__ void sw_flip_kernel(int8_t* __restrict__ spins, int32_t* __restrict__ parent, int L, int n_rep,
                                uint32_t key0, uint32_t key1, uint32_t c_lo, uint32_t c_hi) {
     const long long N = (long long)L * L;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1275,7 +1474,8 @@ __global__ void sw_flip_kernel(int8_t* __restrict__ spins, const int32_t* __rest
     const int8_t s = spins[gid];
     if (s == 0) return;
     const int rep = (int)(gid / N);
-    const int32_t root = sw_find(parent + (size_t)rep * N, (int32_t)(gid - (long long)rep * N));
+    int32_t* par = parent + (size_t)rep * N;
+    const int32_t root = sw_root_shorten(par, (int32_t)(gid - (long long)rep * N));
     uint32_t w[4];
     philox4x32_10((uint32_t)root, c_lo, c_hi, STREAM_FLIP << 1, key0, key1 ^ (uint32_t)rep, w);
     if (w[0] & 1u) spins[gid] = (int8_t)-s;

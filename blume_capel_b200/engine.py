@@ -56,6 +56,7 @@ SYMBOLS = {
     "bc_get_sweep_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_sweep_counter": (C.c_int, [_P, C.c_int64]),
     "bc_sweep": (C.c_int64, [_P, C.c_int64, C.c_int64, _P]),
+    "bc_sweep_group": (C.c_int64, [C.POINTER(_P), C.c_int, C.c_int64, C.c_int64]),
     "bc_cluster_update": (C.c_int, [_P, C.c_int64]),
     "bc_get_cluster_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_cluster_counter": (C.c_int, [_P, C.c_int64]),
@@ -101,6 +102,21 @@ def slab_unique_id() -> bytes:
     if rc != 0:
         raise BCError(rc, (lib.bc_last_error(None) or b"").decode())
     return buf.raw
+
+
+def sweep_group(engines, n_sweeps: int, measure_every: int = 0, fetch: bool = True):
+    """n_sweeps of several engines (different L, same device and boundary) with ONE kernel launch per half-sweep
+    (bc_sweep_group).  Returns one obs array (n_meas, n_replicas) per engine, or None."""
+    lib = load_library()
+    arr = (_P * len(engines))(*[e._h for e in engines])
+    t0 = engines[0].sweep_counter
+    rc = lib.bc_sweep_group(arr, len(engines), n_sweeps, measure_every)
+    if rc < 0:
+        raise BCError(rc, (lib.bc_last_error(engines[0]._h) or b"").decode())
+    if measure_every > 0 and fetch:
+        n_meas = (t0 + n_sweeps) // measure_every - t0 // measure_every
+        return [e.read_obs(n_meas) for e in engines]
+    return None
 
 
 class Engine:

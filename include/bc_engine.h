@@ -133,6 +133,19 @@ int bc_set_sweep_counter(bc_engine* e, int64_t t);
  * Returns the number of records written (>= 0) or a negative status. */
 int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_every, bc_obs* out);
 
+/* The same sweeps for SEVERAL handles of one device in ONE kernel launch per half-sweep: a finite-size-scaling
+ * ladder (BASELINE config 3: L = 256 ... 2048 at the same (T, D) points) or the open-boundary size series (config 5)
+ * as the reference runs them, one process per size (job_scripts/runner.sh:14-19), but without a launch -- and a
+ * launch tail -- per size: the CTAs of all members form one grid.  Members keep their own size, replicas, tables,
+ * seed and sweep counter, and the results are bit-identical to bc_sweep on each handle.  Requirements: 1..8 distinct
+ * handles, same device and boundary, no slab handles, every L a multiple of 32 and >= 128 (smaller lattices belong
+ * to bc_sweep's shared-memory-resident kernel); with measure_every > 0 all sweep counters must be equal.  The
+ * launches go to member 0's stream (its options "rows_per_thread", "pair_min_rows", "use_graph", "graph_block",
+ * "pdl" apply; bc_launch_count / bc_last_sweep_ms / bc_last_error report on member 0); the other members' streams are
+ * ordered before and after, so any later call on any member sees the swept lattices.  Observables: bc_read_obs on
+ * each member.  Returns 0 or a negative status. */
+int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int64_t n_sweeps, int64_t measure_every);
+
 /* Cluster move (the reference interleaves one Wolff cluster per 3L Metropolis attempts,
  * main.cpp:113-154,158-163): n_updates Swendsen-Wang updates of every replica -- bonds between equal non-zero
  * neighbours with probability 1 - exp(-2J/T) (main.cpp:115; zeros never join, main.cpp:123-130,144), every

@@ -43,6 +43,33 @@ def test_cluster_update_low_temperature_giant_cluster(bc, oracle):
     e.close()
 
 
+@pytest.mark.parametrize("L,boundary", [(320, 0), (200, 1), (70, 0)])
+def test_clusters_spanning_many_tiles(bc, oracle, L, boundary):
+    """The labelling works tile by tile (64 x 64 in shared memory) and merges across tile borders afterwards:
+    a spiral-like ordered configuration whose clusters cross every border, sizes that clip the last tiles."""
+    seed, T = 4242, 0.9
+    s = np.ones((2, L, L), np.int8)
+    s[0, ::7, : L - 3] = -1          # long horizontal stripes, connected to nothing else
+    s[0, 3::7, 5:] = 0
+    s[1, :, ::5] = -1                # vertical stripes
+    s[1, L // 2, :] = 1              # one row joins all the +1 columns
+    e = bc.Engine(L, boundary, 2, 0, seed)
+    e.set_params(T, 0.0, 1.0)
+    e.upload(s)
+    for kind in (0, 1):
+        got = e.cluster_moments(kind, mstep=3)
+        for r in range(2):
+            want = oracle.cluster_moments(s[r], kind, T, 1.0, seed, r, 3, boundary)
+            assert (got[r]["sum_size_sq"], got[r]["max_size"], got[r]["n_clusters"]) == want, (kind, r)
+    ref = s.copy()
+    for c in range(3):
+        e.cluster_update(1)
+        for r in range(2):
+            oracle.cluster_update(ref[r], T, 1.0, seed, r, c, boundary)
+        assert np.array_equal(e.download(), ref), c
+    e.close()
+
+
 def test_metropolis_plus_cluster_statistics_L4(bc):
     """Sweeps interleaved with cluster moves still sample the Boltzmann distribution (exact enumeration)."""
     exact = np.array([0.13644431, 0.65236652, 0.66068962])

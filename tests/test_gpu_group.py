@@ -1,0 +1,101 @@
+"""bc_sweep_group: several handles of different L in one launch per half-sweep must give exactly what bc_sweep
+gives on each handle (and hence what the oracle gives)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TC = (0.608, 1.966, 1.0)
+
+
+def make(bc, sizes, boundary, seed0, reps):
+    es = []
+    for i, (L, n) in enumerate(zip(sizes, reps)):
+        e = bc.Engine(L, boundary, n, 0, seed0 + i)
+        for r in range(n):  # per-replica (T, D) points like the ladder of config 3
+            e.set_params(0.58 + 0.01 * r, 1.94 + 0.005 * r, 1.0, replica=r)
+        e.init_random()
+        es.append(e)
+    return es
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+@pytest.mark.parametrize("sizes,reps,rows", [((128, 256, 512, 1024), (3, 2, 5, 1), 0),   # auto: short strips, per-site table
+                                             ((128, 256, 512, 1024), (3, 2, 5, 1), 8),   # L = 128 caps at 4 rows
+                                             ((256, 512, 1024), (2, 5, 1), 8),           # pair-table kernels
+                                             ((256, 2048), (9, 2), 16)])
+def test_group_equals_individual_sweeps(bc, boundary, sizes, reps, rows):
+    a = make(bc, sizes, boundary, 100, reps)
+    b = make(bc, sizes, boundary, 100, reps)
+    if rows:
+        a[0].set_option("rows_per_thread", rows)
+    # 37 sweeps, measured every 5: two graph-replayed blocks are impossible between measurements, so also a long
+    # unmeasured run (graph path) afterwards
+    obs_a = bc.sweep_group(a, 37, 5)
+    bc.sweep_group(a, 40, 0)
+    obs_a2 = bc.sweep_group(a, 3, 1)
+    for e, oa, oa2 in zip(b, obs_a, obs_a2):
+        ob = e.sweep(37, 5)
+        e.sweep(40)
+        ob2 = e.sweep(3, 1)
+        assert np.array_equal(oa, ob) and np.array_equal(oa2, ob2), e.L
+    for ea, eb in zip(a, b):
+        assert ea.sweep_counter == eb.sweep_counter == 80
+        assert np.array_equal(ea.download(), eb.download()), ea.L
+        assert ea.tie_count == eb.tie_count
+    for e in a + b:
+        e.close()
+
+
+def test_group_member_matches_oracle(bc, oracle):
+    sizes, reps = (128, 256), (1, 1)
+    es = make(bc, sizes, 0, 7, reps)
+    obs = bc.sweep_group(es, 6, 2)
+    for i, e in enumerate(es):
+        ref = oracle.init_random(e.L, 7 + i, 0)
+        tab = oracle.build_table(0.58, 1.94, 1.0)
+        ro = oracle.sweep(ref, tab, 7 + i, 0, 0, 6, 2)
+        assert np.array_equal(e.download(0), ref)
+        for f in ("M", "Q", "B"):
+            assert np.array_equal(obs[i][:, 0][f], ro[f])
+        e.close()
+
+
+def test_group_with_different_counters_and_later_calls(bc):
+    """Unmeasured group sweeps work from unequal counters; calls on a member afterwards see the group's result."""
+    a = make(bc, (256, 512), 0, 55, (2, 2))
+    b = make(bc, (256, 512), 0, 55, (2, 2))
+    a[0].set_option("rows_per_thread", 16)  # pair-table group kernel
+    a[1].sweep(3)
+    b[1].sweep(3)
+    bc.sweep_group(a, 20)
+    a[1].sweep(2)          # on the member's own stream, ordered after the group
+    for e in b:
+        e.sweep(20)
+    b[1].sweep(2)
+    for ea, eb in zip(a, b):
+        assert np.array_equal(ea.download(), eb.download())
+    with pytest.raises(bc.BCError):
+        bc.sweep_group(a, 4, 2)  # measuring needs equal counters
+    for e in a + b:
+        e.close()
+
+
+def test_group_argument_errors(bc):
+    e64 = bc.Engine(64, 0, 1, 0, 1)
+    e256 = bc.Engine(256, 0, 1, 0, 1)
+    e256o = bc.Engine(256, 1, 1, 0, 1)
+    for e in (e64, e256, e256o):
+        e.set_params(*TC)
+    with pytest.raises(bc.BCError):
+        bc.sweep_group([e256, e64], 2)      # too small for the streaming kernel
+    with pytest.raises(bc.BCError):
+        bc.sweep_group([e256, e256], 2)     # twice the same handle
+    with pytest.raises(bc.BCError):
+        bc.sweep_group([e256, e256o], 2)    # mixed boundaries
+    unset = bc.Engine(256, 0, 1, 0, 2)
+    with pytest.raises(bc.BCError):
+        bc.sweep_group([e256, unset], 2)    # parameters missing
+    assert bc.sweep_group([e256], 2) is None  # a group of one is fine
+    assert e256.sweep_counter == 2
+    for e in (e64, e256, e256o, unset):
+        e.close()
