@@ -137,7 +137,7 @@ struct bc_engine {
     int wave_grid[2] = {0, 0};
     int opt_pdl = 1;  // programmatic dependent launch between consecutive half-sweeps
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
-    bool resident_attr_set[2] = {false, false};
+    bool resident_attr_set[4] = {false, false, false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
     int opt_swp_min_rows = 32;  // ... with software-pipelined Philox draws from this many rows on (0 = never)
@@ -957,8 +957,8 @@ struct ResidentPlan {
 static ResidentPlan resident_plan(const bc_engine* e) {
     ResidentPlan r;
     const int L = e->L;
-    if (L % 32 || e->ghost || e->opt_resident == 0 || e->opt_force_generic) return r;
-    const int items = L * (L / 32);
+    if (e->ghost || e->opt_resident == 0 || e->opt_force_generic) return r;
+    const int items = L * (e->Wc / 16);  // 16-byte chunks of the padded rows (L % 32 != 0: the ANY instantiation)
     // 512 threads per replica shorten a half-sweep when there are too few replicas to fill the chip
     r.T = items <= 32 ? 32 : (items <= 128 ? 128 : ((items <= 256 || e->n_rep >= 2 * 148) ? 256 : 512));
     r.reps_per_cta = r.T < 128 ? 128 / r.T : 1;
@@ -974,17 +974,19 @@ static ResidentPlan resident_plan(const bc_engine* e) {
 
 static int launch_resident(bc_engine* e, const ResidentPlan& rp, int64_t t0, int64_t n, int64_t measure_every) {
     const bool open = e->boundary == BC_OPEN;
-    auto fn = open ? sweep_resident_kernel<true> : sweep_resident_kernel<false>;
-    if (!e->resident_attr_set[open]) {
+    const bool any = e->L % 32 != 0;  // padded rows, wrap patches, masked stores
+    auto fn = any ? (open ? sweep_resident_kernel<true, true> : sweep_resident_kernel<false, true>)
+                  : (open ? sweep_resident_kernel<true, false> : sweep_resident_kernel<false, false>);
+    if (!e->resident_attr_set[2 * any + open]) {
         BC_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        e->resident_attr_set[open] = true;
+        e->resident_attr_set[2 * any + open] = true;
     }
     ResidentParams P;
     P.c0 = e->d_c[0]; P.c1 = e->d_c[1];
     P.tab16 = e->d_tab16; P.tab31 = e->d_tab31;
     P.obs = e->d_obs; P.ties = e->d_ties;
     P.t0 = t0; P.n_sweeps = n; P.measure_every = measure_every;
-    P.L = e->L; P.Wc = e->Wc; P.cpr = e->L / 32; P.n_replicas = e->n_rep;
+    P.L = e->L; P.Wc = e->Wc; P.cpr = e->Wc / 16; P.n_replicas = e->n_rep;
     P.threads_per_rep = rp.T; P.reps_per_cta = rp.reps_per_cta;
     P.key0 = (uint32_t)e->seed; P.key1 = (uint32_t)(e->seed >> 32);
     fn<<<rp.grid, rp.T * rp.reps_per_cta, rp.smem, e->stream>>>(P);

@@ -734,7 +734,12 @@ struct ResidentParams {
     uint32_t key0, key1;
 };
 
-template <bool OPEN>
+//   ANY = true : any lattice size (the reference's 8, 12, 16, 24, 48, 96: gen_files.py:11, runner.sh:4; odd L with
+//                open edges).  Rows are padded to 16-byte chunks with spin-0 bytes that must never change: the
+//                chunk is updated as a whole and only its real sites are stored; on a torus the wrap-around
+//                neighbours of a row's first / last site are patched in; the observables are summed here over
+//                the real sites only (update_chunk16 would count the pad sites).
+template <bool OPEN, bool ANY = false>
 __global__ void __launch_bounds__(512)
 sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -782,24 +787,74 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
             const int y = item / cpr, j = item - y * cpr;
             const int par = (y + COL) & 1;
             const uint32_t rowo = (uint32_t)y * Wc, co = (uint32_t)j * 16;
+            // same-colour sites of this row: x = 2k + par < L (L/2 on a torus; odd L: one more where par == 0)
+            const int nk = ANY ? (L - par + 1) >> 1 : 0;
+            const int nreal = ANY ? min(16, nk - 16 * j) : 16;  // real sites in this chunk
+            if (ANY && nreal <= 0) continue;                    // a chunk of pad bytes only (odd L)
             uint4 upv, dnv;
             if (y == 0) upv = OPEN ? ones4 : *reinterpret_cast<const uint4*>(oth + (arr - Wc) + co);
             else upv = *reinterpret_cast<const uint4*>(oth + rowo - Wc + co);
             if (y == L - 1) dnv = OPEN ? ones4 : *reinterpret_cast<const uint4*>(oth + co);
             else dnv = *reinterpret_cast<const uint4*>(oth + rowo + Wc + co);
-            const uint4 midv = *reinterpret_cast<const uint4*>(oth + rowo + co);
+            uint4 midv = *reinterpret_cast<const uint4*>(oth + rowo + co);
             uint32_t side;
             if (par) {
                 if (j + 1 == cpr) side = OPEN ? 0x00000001u : *reinterpret_cast<const uint32_t*>(oth + rowo);
                 else side = *reinterpret_cast<const uint32_t*>(oth + rowo + co + 16);
+                if (ANY && !OPEN && nreal < 16) {
+                    // torus: the right neighbour of the row's last site is x = 0, not the pad byte behind it
+                    const uint32_t sh = 8u * ((uint32_t)nreal & 3u), w0 = (uint32_t)oth[rowo] << sh, keep = ~(0xFFu << sh);
+                    const int wi = nreal >> 2;
+                    if (wi == 0) midv.x = (midv.x & keep) | w0;
+                    if (wi == 1) midv.y = (midv.y & keep) | w0;
+                    if (wi == 2) midv.z = (midv.z & keep) | w0;
+                    if (wi == 3) midv.w = (midv.w & keep) | w0;
+                }
             } else {
-                if (j == 0) side = OPEN ? 0x01000000u : *reinterpret_cast<const uint32_t*>(oth + rowo + (cpr - 1) * 16 + 12);
-                else side = *reinterpret_cast<const uint32_t*>(oth + rowo + co - 4);
+                if (j == 0) {
+                    if (OPEN) side = 0x01000000u;
+                    else if (ANY) side = (uint32_t)oth[rowo + (L >> 1) - 1] << 24;  // torus: left neighbour of x = 0 is x = L-1
+                    else side = *reinterpret_cast<const uint32_t*>(oth + rowo + (cpr - 1) * 16 + 12);
+                } else {
+                    side = *reinterpret_cast<const uint32_t*>(oth + rowo + co - 4);
+                }
             }
             const uint4 ownv = *reinterpret_cast<const uint4*>(own + rowo + co);
             ctx.j = (uint32_t)j;
-            *reinterpret_cast<uint4*>(own + rowo + co) =
-                update_chunk16<COL, MEAS>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            if (!ANY) {
+                *reinterpret_cast<uint4*>(own + rowo + co) =
+                    update_chunk16<COL, MEAS>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            } else {
+                uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+                const uint4 nv = update_chunk16<COL, false>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, d0, d1, d2, d3, n_ties);
+                // byte masks of the real sites, word by word
+                uint32_t mk[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int n = nreal - 4 * w;
+                    mk[w] = n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : (1u << (8 * n)) - 1u);
+                }
+                const uint4 st = make_uint4((nv.x & mk[0]) | (ownv.x & ~mk[0]), (nv.y & mk[1]) | (ownv.y & ~mk[1]),
+                                            (nv.z & mk[2]) | (ownv.z & ~mk[2]), (nv.w & mk[3]) | (ownv.w & ~mk[3]));
+                *reinterpret_cast<uint4*>(own + rowo + co) = st;
+                if (MEAS) {
+                    const uint32_t v[4] = {nv.x & mk[0], nv.y & mk[1], nv.z & mk[2], nv.w & mk[3]};
+                    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w}, d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
+                    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        a_c = __dp4a(v[w], ONES, a_c);
+                        a_c2 = __dp4a(v[w], v[w], a_c2);
+                        if (COL == 1) {  // neighbour sums as in update_half8 (main.cpp:97-103)
+                            const uint32_t sr = __funnelshift_r(m[w], w < 3 ? m[w + 1] : side, 8);
+                            const uint32_t sl = __funnelshift_l(w > 0 ? m[w - 1] : side, m[w], 8);
+                            const uint32_t S4 = u[w] + d[w] + m[w] + (par ? sr : sl);
+                            a_cS = __dp4a(v[w], S4, a_cS);
+                            a_S = __dp4a(S4 & mk[w], ONES, a_S);
+                        }
+                    }
+                }
+            }
         }
     };
 

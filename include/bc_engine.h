@@ -190,7 +190,7 @@ int bc_timer_stop(bc_engine* e, float* ms);
  *   "pair_min_rows" n     streaming kernel: use the 54 x 54 pair table (one threshold lookup per two sites)
  *                         when a thread marches over >= n rows (default 8; 0 = never)
  *   "swp_min_rows" n      ... with software-pipelined Philox draws when it marches over >= n rows (default 32)
- *   "resident" -1|0|1     shared-memory-resident kernel for L <= 448 (auto / off / force)
+ *   "resident" -1|0|1     shared-memory-resident kernel for L <= 448, any L (auto: L <= 128 / off / force)
  *   "use_graph" 0|1, "graph_block" n   CUDA-graph replay of blocks of n unmeasured sweeps
  *   "pdl" 0|1             programmatic dependent launch between half-sweeps
  *   "wave" 0|1            experimental single-launch wavefront kernel (off by default)

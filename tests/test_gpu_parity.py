@@ -40,7 +40,7 @@ def run_pair(bc, oracle, L, boundary, n_rep, n_sweeps, seed, params=TC, opts=(),
 
 @pytest.mark.parametrize("L", [2, 4, 6, 8, 12, 16, 24, 48])
 def test_generic_kernel_periodic(bc, oracle, L):
-    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, 3, 20, 0xBC00 + L)
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, 3, 20, 0xBC00 + L, opts=(("resident", 0),))
     assert not plan["fast"]
     assert np.array_equal(got, ref)
     for r in range(3):
@@ -50,7 +50,8 @@ def test_generic_kernel_periodic(bc, oracle, L):
 
 @pytest.mark.parametrize("L", [3, 5, 8, 17, 33])
 def test_generic_kernel_open(bc, oracle, L):
-    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.OPEN, 2, 15, 0x0BE0 + L)
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.OPEN, 2, 15, 0x0BE0 + L, opts=(("resident", 0),))
+    assert not plan["fast"]
     assert np.array_equal(got, ref)
     for r in range(2):
         for f in ("M", "Q", "B"):
@@ -278,6 +279,23 @@ def test_resident_kernel(bc, oracle, L, n_rep, force, boundary):
             assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
 
 
+@pytest.mark.parametrize("L,boundary,n_rep,force", [(2, 0, 5, -1), (4, 0, 3, -1), (6, 0, 9, -1), (8, 0, 4, -1), (12, 0, 5, -1),
+                                                    (16, 0, 1, -1), (24, 0, 3, -1), (48, 0, 2, -1), (100, 0, 2, -1),
+                                                    (200, 0, 2, 1), (34, 0, 3, -1), (62, 0, 2, -1),
+                                                    (3, 1, 5, -1), (5, 1, 2, -1), (8, 1, 3, -1), (17, 1, 4, -1), (33, 1, 2, -1),
+                                                    (31, 1, 2, -1), (48, 1, 2, -1), (65, 1, 2, -1), (127, 1, 1, -1)])
+def test_resident_kernel_any_size(bc, oracle, L, boundary, n_rep, force):
+    """Sizes that are not a multiple of 32 (the reference's 8, 12, 16, 24, 48, 96 of gen_files.py:11; odd L with open
+    edges) also stay in shared memory: padded rows, wrap-around patches, masked stores and observables."""
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, 11, 0xA11 + L, measure_every=1,
+                                            opts=(("resident", force),), start="random" if L % 2 == 0 else "upload")
+    assert plan["resident"], plan
+    assert np.array_equal(got, ref)
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
+
+
 def test_resident_is_one_launch_and_equals_streaming(bc):
     res = []
     for resident in (1, 0):
@@ -351,8 +369,8 @@ def test_randomised_configurations(bc, oracle):
     rng = np.random.default_rng(20261020)
     for case in range(40):
         boundary = int(rng.integers(0, 2))
-        kind = rng.choice(["generic", "stream", "resident", "slab"])
-        if kind == "generic":
+        kind = rng.choice(["generic", "stream", "resident", "slab", "resident_any"])
+        if kind in ("generic", "resident_any"):
             L = int(rng.choice([2, 4, 6, 10, 14, 18, 22, 30, 34, 50]) if boundary == 0 else rng.integers(2, 60))
         else:
             L = int(rng.choice([32, 64, 96, 128, 160, 256]))
@@ -370,6 +388,8 @@ def test_randomised_configurations(bc, oracle):
             e.set_option("pair_min_rows", int(rng.choice([0, 2, 8])))
         if kind == "resident":
             e.set_option("resident", 1)
+        if kind == "generic":
+            e.set_option("resident", 0)  # one thread per site instead of the padded shared-memory kernel
         e.set_params(T, D, J)
         e.init_random()
         e.sweep_counter = t0
