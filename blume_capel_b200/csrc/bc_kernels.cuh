@@ -858,9 +858,12 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
         }
     };
 
+    // sweeps left until the next measured one (a 64-bit modulo per sweep would cost more than a small half-sweep)
+    int64_t to_meas = P.measure_every > 0 ? P.measure_every - 1 - (P.t0 % P.measure_every) : -1;
     for (int64_t s = 0; s < P.n_sweeps; ++s) {
         const int64_t t = P.t0 + s;
-        const bool measure = P.measure_every > 0 && ((t + 1) % P.measure_every) == 0;
+        const bool measure = to_meas == 0;
+        to_meas = measure ? P.measure_every - 1 : to_meas - 1;
         ctx.t = t;
         ctx.ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
