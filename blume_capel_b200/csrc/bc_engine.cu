@@ -119,6 +119,10 @@ struct bc_engine {
     cudaGraphExec_t group_graph = nullptr;
     std::vector<uint64_t> group_sig;
     cudaEvent_t ev_group = nullptr;  // joins / forks the members' streams around a group sweep
+    // persistent kernel (all half-sweeps of an unmeasured run in one cooperative launch)
+    int opt_persist = 0;             // 0 never (default: measured slower than graph replay + PDL), 1 whenever possible
+    unsigned* d_bar = nullptr;       // [0] arrivals, [1] generation, [2] abort
+    int persist_cap[2] = {0, 0};     // resident CTAs of sweep_persist_kernel<OPEN> on this device
     unsigned graph_grid = 0;
     // cluster move scratch
     int32_t* d_parent = nullptr;
@@ -228,6 +232,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->halo_stream) cudaStreamDestroy(e->halo_stream);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->group_graph) cudaGraphExecDestroy(e->group_graph);
+    cudaFree(e->d_bar);
     if (e->ev_group) cudaEventDestroy(e->ev_group);
     cudaFree(e->d_clock);
     cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_csize); cudaFree(e->d_cmom);
@@ -918,9 +923,123 @@ static int run_wave(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n)
     return BC_OK;
 }
 
+// ---- persistent kernel: a whole run of unmeasured sweeps in one cooperative launch -------------------------
+// rows per thread R for a member of a multi-handle launch: even, whole strips, whole CTAs per replica (!SMALL body)
+static bool group_rows_valid(const bc_engine* e, int R) {
+    const int cpr = e->L / 32;
+    return e->L % 32 == 0 && R >= 2 && !(R & 1) && rows_valid(e->Ly, cpr, R) &&
+           (((long long)(e->Ly / R) * cpr) % FAST_THREADS) == 0;
+}
+
+static int group_best_rows(const bc_engine* e, int target) {
+    for (int R = target; R >= 2; R >>= 1)
+        if (group_rows_valid(e, R)) return R;
+    return 0;
+}
+
+struct GroupPlan {
+    int n = 0;
+    LaunchPlan plan[GROUP_MAX];
+    unsigned cta_end[GROUP_MAX];
+    bool pair = false, open = false;
+};
+
+static void fill_group_plan(bc_engine* const* es, int n, int target, GroupPlan* gp) {
+    gp->n = n;
+    gp->open = es[0]->boundary == BC_OPEN;
+    unsigned long long ctas = 0;
+    for (int g = 0; g < n; ++g) {
+        const bc_engine* e = es[g];
+        LaunchPlan& p = gp->plan[g];
+        p.fast = true; p.small = false; p.pair = 0;
+        p.cpr = e->L / 32;
+        p.rows = group_best_rows(e, target);
+        p.strips = e->Ly / p.rows;
+        p.grid = (unsigned)(((long long)e->n_rep * p.strips * p.cpr) / FAST_THREADS);
+        ctas += p.grid;
+        gp->cta_end[g] = (unsigned)std::min<unsigned long long>(ctas, 0xFFFFFFFFull);
+    }
+}
+
+static int persist_capacity(bc_engine* e0) {
+    const int open = e0->boundary == BC_OPEN;
+    if (!e0->persist_cap[open]) {
+        auto fn = open ? sweep_persist_kernel<true> : sweep_persist_kernel<false>;
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        int per_sm = 0, sms = 0, coop = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, FAST_THREADS, 0) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e0->device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e0->device) != cudaSuccess || !coop)
+            e0->persist_cap[open] = -1;
+        else
+            e0->persist_cap[open] = per_sm * sms;
+    }
+    return e0->persist_cap[open];
+}
+
+// Decide whether a run of unmeasured sweeps of these handles goes to the persistent kernel, and with which strips:
+// the strip height that needs the fewest rounds of resident CTAs per half-sweep (a round costs its rows plus a
+// prologue worth about two rows).  Only on request ("persist" 1): measured slower than graph replay + PDL.
+static bool persist_plan(bc_engine* const* es, int n, int64_t n_sweeps, GroupPlan* gp) {
+    bc_engine* e0 = es[0];
+    if (e0->opt_persist <= 0 || n_sweeps < 2) return false;
+    for (int g = 0; g < n; ++g)
+        if (es[g]->ghost || es[g]->opt_force_generic || !group_best_rows(es[g], 2)) return false;
+    const int cap = persist_capacity(e0);
+    if (cap <= 0) return false;
+    long long best_cost = -1;
+    int best = 0;
+    const int cand[5] = {32, 16, 8, 4, 2};
+    for (int target : cand) {
+        if (e0->opt_rows > 0 && target != e0->opt_rows) continue;
+        fill_group_plan(es, n, target, gp);
+        const long long blocks = gp->cta_end[n - 1];
+        const long long cost = ((blocks + cap - 1) / cap) * (target + 2);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = target; }
+    }
+    if (!best) return false;
+    fill_group_plan(es, n, best, gp);
+    return true;
+}
+
+// n_sweeps unmeasured sweeps of every member, starting `s0` sweeps after the members' counters; on member 0's stream
+static int run_persist(bc_engine* const* es, const GroupPlan& gp, int64_t s0, int64_t n_sweeps) {
+    bc_engine* e0 = es[0];
+    if (!e0->d_bar) BC_CUDA(e0, cudaMalloc(&e0->d_bar, 4 * sizeof(unsigned)));
+    auto fn = gp.open ? sweep_persist_kernel<true> : sweep_persist_kernel<false>;
+    const unsigned blocks = gp.cta_end[gp.n - 1];
+    const unsigned grid = std::min<unsigned>(blocks, (unsigned)persist_capacity(e0));
+    int64_t done = 0;
+    while (done < n_sweeps) {
+        const int64_t chunk = std::min<int64_t>(n_sweeps - done, 1 << 19);  // arrivals stay below 2^32
+        PersistParams P;
+        memset(&P, 0, sizeof(P));
+        for (int col = 0; col < 2; ++col) {
+            P.g[col].n = gp.n;
+            for (int g = 0; g < gp.n; ++g) {
+                P.g[col].p[g] = sweep_params(es[g], gp.plan[g], col, es[g]->t + s0 + done, 0, nullptr);
+                P.g[col].cta_end[g] = gp.cta_end[g];
+            }
+        }
+        P.bar = e0->d_bar;
+        P.n_half = (int)(2 * chunk);
+        BC_CUDA(e0, cudaMemsetAsync(e0->d_bar, 0, 4 * sizeof(unsigned), e0->stream));
+        void* args[1] = {&P};
+        BC_CUDA(e0, cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(FAST_THREADS), args, 0, e0->stream));
+        ++e0->launches;
+        done += chunk;
+    }
+    return BC_OK;
+}
+
 // n unmeasured sweeps starting at sweep index t0
 static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n) {
     if (wave_eligible(e, plan, n)) return run_wave(e, plan, t0, n);
+    if (plan.fast) {
+        GroupPlan gp;
+        bc_engine* one[1] = {e};
+        if (persist_plan(one, 1, n, &gp)) return run_persist(one, gp, t0 - e->t, n);
+    }
     int64_t done = 0;
     const int block = e->opt_graph_block;
     if (e->opt_use_graph && !e->ghost && block > 0 && n >= block) {
@@ -1086,25 +1205,6 @@ static group_fn pick_group(bool meas, bool open, bool pair) {
     return open ? (group_fn)sweep_group_kernel<COL, false, true, 0> : (group_fn)sweep_group_kernel<COL, false, false, 0>;
 }
 
-// rows per thread R for a member of a group: even, whole strips, whole CTAs per replica (the !SMALL kernels)
-static bool group_rows_valid(const bc_engine* e, int R) {
-    const int cpr = e->L / 32;
-    return R >= 2 && !(R & 1) && rows_valid(e->Ly, cpr, R) && (((long long)(e->Ly / R) * cpr) % FAST_THREADS) == 0;
-}
-
-static int group_best_rows(const bc_engine* e, int target) {
-    for (int R = target; R >= 2; R >>= 1)
-        if (group_rows_valid(e, R)) return R;
-    return 0;
-}
-
-struct GroupPlan {
-    int n = 0;
-    LaunchPlan plan[GROUP_MAX];
-    unsigned cta_end[GROUP_MAX];
-    bool pair = false, open = false;
-};
-
 // One half-sweep of every member: t = members' own counters + `s` (or + *t_ptr, the clock of member 0, in a graph)
 static void launch_group_half(bc_engine* const* es, const GroupPlan& gp, int col, bool measure, int64_t s, int64_t slot,
                               const int64_t* t_ptr) {
@@ -1258,6 +1358,12 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
     const int block = e0->opt_graph_block;
     for (int64_t slot = 0; slot <= n_meas; ++slot) {
         const int64_t until = slot < n_meas ? e0->pending_sweeps[(size_t)slot] - e0->t : n_sweeps;
+        GroupPlan pp;
+        if (until > done && persist_plan(engines, n_engines, until - done, &pp)) {
+            int rc = run_persist(engines, pp, done, until - done);
+            if (rc != BC_OK) return rc;
+            done = until;
+        }
         if (e0->opt_use_graph && block > 0 && until - done >= block) {
             int rc = ensure_group_graph(engines, gp, block);
             if (rc != BC_OK) return rc;
@@ -1464,6 +1570,11 @@ extern "C" int bc_sync(bc_engine* e) {
         BC_CUDA(e, cudaMemcpy(flags, e->d_wave, sizeof(flags), cudaMemcpyDeviceToHost));
         if (flags[1]) return fail(e, BC_ERR_STATE, "bc_sync: the wavefront kernel timed out waiting for a dependency");
     }
+    if (e->d_bar) {
+        unsigned bar[3] = {0, 0, 0};
+        BC_CUDA(e, cudaMemcpy(bar, e->d_bar, sizeof(bar), cudaMemcpyDeviceToHost));
+        if (bar[2]) return fail(e, BC_ERR_STATE, "bc_sync: the persistent kernel timed out at a grid barrier");
+    }
     if (e->d_halo_err) {
         int err = 0;
         BC_CUDA(e, cudaMemcpy(&err, e->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1558,6 +1669,7 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (n == "fused_halo") { e->opt_fused_halo = value != 0; return BC_OK; }
     if (n == "overlap") { e->opt_overlap = value != 0; return BC_OK; }
     if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
+    if (n == "persist") { e->opt_persist = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
     if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }

@@ -288,7 +288,7 @@ struct FastMinBlocks {
 // The kernel body; `bid` is the CTA's index among the CTAs that work on P's lattices (blockIdx.x for an ordinary
 // launch, blockIdx.x minus the group's first CTA for a group launch, see sweep_group_kernel).
 template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO, int PAIR>
-__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid) {
+__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid, const int64_t t_add = 0) {
     static_assert(!(PAIR && SMALL) && !(PAIR && HALO), "the pair table is one replica per CTA; HALO kernels use the per-site table");
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
@@ -340,7 +340,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     const uint32_t Wc = (uint32_t)P.Wc;
     constexpr bool open = OPEN;
 
-    int64_t t = P.t;
+    int64_t t = P.t + t_add;
     if (P.t_ptr) t += *P.t_ptr;
     const uint32_t k0 = P.key0, k1 = P.key1 ^ rep;
     const uint32_t ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
@@ -542,6 +542,78 @@ sweep_group_kernel(const __grid_constant__ GroupParams G) {
         if (i + 1 < G.n && blockIdx.x >= G.cta_end[i]) g = i + 1;
     const unsigned first = g ? G.cta_end[g - 1] : 0u;
     sweep_fast_body<COL, false, MEASURE, OPEN, false, PAIR>(G.p[g], blockIdx.x - first);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent kernel -- experimental, off by default (a measured negative result): ALL half-sweeps of a
+// run of unmeasured sweeps in ONE cooperative launch, with a grid-wide barrier between half-sweeps instead of a
+// kernel boundary.  The idea: for lattices that do not fill the chip for long (one L = 4096 lattice is 4.3 us of
+// work per half-sweep) the floor of a dependent launch -- about 3 us even from a CUDA graph with programmatic
+// dependent launch -- is most of the time.  The measurement: a software barrier is four serialised L2 round trips
+// (the stores' fence, the arrival atomic, the poll that sees the release, the first loads after it), and nothing
+// overlaps them, while programmatic dependent launch runs the next grid's prologue under the previous grid's tail:
+// one L = 4096 lattice 761 vs 1090 updates/ns, L = 2048 358 vs 588 (profiles/r01_tune_persist.log).
+// The grid is exactly the number of CTAs that are resident at once (cooperative launch: co-residency is
+// guaranteed or the launch fails); a CTA takes the 128-item work blocks b = blockIdx.x, blockIdx.x + gridDim.x, ...
+// of every half-sweep and runs the streaming kernel's body on them (same results).  Handles several lattice sizes
+// like sweep_group_kernel (n = 1: a single handle).  The barrier: a monotonically increasing arrival counter (the
+// g-th barrier is complete at count g * gridDim.x), the last arriver publishes the generation with a release
+// store, the others poll it with acquire loads (which also drop stale L1 lines before the next half-sweep reads
+// its neighbours); the wait is bounded (~2 s) and raises bar[2] instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+struct PersistParams {
+    GroupParams g[2];   // members' parameters for the colour-0 and the colour-1 half-sweep (own / other swapped)
+    unsigned* bar;      // [0] arrivals, [1] generation, [2] abort; zeroed by the host before the launch
+    int n_half;         // half-sweeps to run, starting with colour 0 of the members' sweep counters
+};
+
+__device__ __forceinline__ bool persist_barrier(unsigned* bar, const unsigned gen) {
+    __shared__ int s_abort;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int give_up = 0;
+        __threadfence();
+        const unsigned arrived = atomicAdd(&bar[0], 1u) + 1u;
+        if (arrived == gen * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
+        } else {
+            const long long c0 = clock64();
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+                if (v < gen && clock64() - c0 > 4000000000LL) { atomicExch(&bar[2], 1u); give_up = 1; break; }
+            } while (v < gen);
+        }
+        if (*reinterpret_cast<volatile unsigned*>(bar + 2)) give_up = 1;
+        __threadfence();
+        s_abort = give_up;
+    }
+    __syncthreads();
+    return s_abort == 0;
+}
+
+#ifndef BC_PERSIST_MIN_BLOCKS
+#define BC_PERSIST_MIN_BLOCKS 7
+#endif
+template <bool OPEN>
+__global__ void __launch_bounds__(FAST_THREADS, BC_PERSIST_MIN_BLOCKS)
+sweep_persist_kernel(const __grid_constant__ PersistParams P) {
+    const int n = P.g[0].n;
+    const unsigned n_blocks = P.g[0].cta_end[n - 1];
+    for (int h = 0; h < P.n_half; ++h) {
+        const GroupParams& G = P.g[h & 1];
+        for (unsigned b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+            int g = 0;
+#pragma unroll
+            for (int i = 0; i < GROUP_MAX - 1; ++i)
+                if (i + 1 < n && b >= G.cta_end[i]) g = i + 1;
+            const unsigned first = g ? G.cta_end[g - 1] : 0u;
+            if (h & 1) sweep_fast_body<1, false, false, OPEN, false, 0>(G.p[g], b - first, (int64_t)(h >> 1));
+            else sweep_fast_body<0, false, false, OPEN, false, 0>(G.p[g], b - first, (int64_t)(h >> 1));
+            __syncthreads();  // the table and the staging slots are reused by the next block
+        }
+        if (h + 1 < P.n_half && !persist_barrier(P.bar, (unsigned)(h + 1))) return;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -194,6 +194,8 @@ int bc_timer_stop(bc_engine* e, float* ms);
  *   "use_graph" 0|1, "graph_block" n   CUDA-graph replay of blocks of n unmeasured sweeps
  *   "pdl" 0|1             programmatic dependent launch between half-sweeps
  *   "wave" 0|1            experimental single-launch wavefront kernel (off by default)
+ *   "persist" 0|1         experimental persistent kernel: a run of unmeasured sweeps in one cooperative launch with
+ *                         grid barriers between half-sweeps (off by default: slower than graph replay)
  *   "overlap" 0|1         slab handles: boundary strips + halo exchange concurrent with the interior
  *   "fused_halo" 0|1      peer-memory slabs: halo stores issued by the boundary-strip kernel itself
  *   "force_generic" 0|1   one-thread-per-site kernel for every size (second implementation, for tests) */

@@ -46,6 +46,27 @@ def test_group_equals_individual_sweeps(bc, boundary, sizes, reps, rows):
         e.close()
 
 
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_group_persistent_equals_individual_sweeps(bc, boundary):
+    """The group's unmeasured runs in one cooperative launch (grid barriers between half-sweeps)."""
+    sizes, reps = (128, 512, 256), (2, 1, 3)
+    a = make(bc, sizes, boundary, 300, reps)
+    b = make(bc, sizes, boundary, 300, reps)
+    a[0].set_option("persist", 1)
+    a[2].sweep(2)
+    b[2].sweep(2)
+    l0 = a[0].launch_count
+    bc.sweep_group(a, 21)
+    assert a[0].launch_count - l0 == 1
+    for e in b:
+        e.set_option("persist", 0)
+        e.sweep(21)
+    for ea, eb in zip(a, b):
+        assert np.array_equal(ea.download(), eb.download()), ea.L
+    for e in a + b:
+        e.close()
+
+
 def test_group_member_matches_oracle(bc, oracle):
     sizes, reps = (128, 256), (1, 1)
     es = make(bc, sizes, 0, 7, reps)

@@ -296,6 +296,38 @@ def test_resident_kernel_any_size(bc, oracle, L, boundary, n_rep, force):
             assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
 
 
+@pytest.mark.parametrize("L,n_rep,boundary,rows", [(128, 1, 0, 0), (128, 5, 1, 2), (256, 2, 0, 0), (256, 1, 1, 4), (512, 1, 0, 0),
+                                                   (512, 3, 1, 8), (1024, 1, 0, 0), (1024, 2, 1, 2)])
+def test_persistent_kernel_matches_oracle(bc, oracle, L, n_rep, boundary, rows):
+    """Runs of unmeasured sweeps in one cooperative launch with grid barriers between half-sweeps."""
+    e_opts = (("resident", 0), ("persist", 1), ("rows_per_thread", rows))
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, boundary, n_rep, 14, 0x9E25 + L, measure_every=5, opts=e_opts)
+    assert np.array_equal(got, ref)
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f)
+
+
+def test_persistent_kernel_is_one_launch_and_equals_graph_replay(bc):
+    res = []
+    for persist in (1, 0):
+        e = bc.Engine(2048, 0, 1, 0, 31)
+        e.set_option("persist", persist)
+        e.set_params(*TC)
+        e.init_random()
+        e.sync()
+        l0 = e.launch_count
+        e.sweep(50)
+        n_launch = e.launch_count - l0
+        e.sweep(7, 7)
+        res.append((e.download(), n_launch, e.tie_count, e.measure()))
+        e.sync()
+        e.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][2] == res[1][2]
+    assert np.array_equal(res[0][3], res[1][3])
+    assert res[0][1] == 1 and res[1][1] >= 100
+
+
 def test_resident_is_one_launch_and_equals_streaming(bc):
     res = []
     for resident in (1, 0):
