@@ -263,6 +263,9 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #ifndef BC_DEEP_PREFETCH
 #define BC_DEEP_PREFETCH 1  // 0: one row ahead everywhere, 1: two rows ahead where it pays (see DEEP), 2: everywhere
 #endif
+#ifndef BC_PAIR_TMA
+#define BC_PAIR_TMA 1  // pair table staged by one cp.async.bulk + mbarrier (0: by cp.async from all threads)
+#endif
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
@@ -314,12 +317,32 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
     }
+#if BC_PAIR_TMA
+    // Pair table by ONE bulk copy (TMA engine, UBLKCP): thread 0 arms an mbarrier with the byte count and issues the
+    // copy; it completes in the background while the CTA computes its indices, waits for the previous grid and
+    // requests its first rows -- every thread waits on the mbarrier just before the first lookup.  (The tables are
+    // written by bc_set_params, never by a sweep: safe before griddepcontrol.wait.)
+    __shared__ __align__(8) unsigned long long s_mbar;
+    if (PAIR && threadIdx.x == 0) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar), dst = (uint32_t)__cvta_generic_to_shared(s_tab2);
+        const uint32_t* src = P.tab2 + (size_t)rep0 * TAB2_WORDS;
+        constexpr uint32_t bytes = TAB2_WORDS * 4;
+        static_assert(bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+#else
     if (PAIR) {  // the tables are written by bc_set_params, never by a sweep: safe before griddepcontrol.wait
         const uint4* src = reinterpret_cast<const uint4*>(P.tab2 + (size_t)rep0 * TAB2_WORDS);
         for (int i = threadIdx.x; i < TAB2_WORDS / 4; i += FAST_THREADS) cp_async16(&s_tab2[4 * i], src + i);
         cp_async_commit();
         cp_async_wait<0>();
     }
+#endif
     __syncthreads();
 
     uint32_t rep, rem;
@@ -414,6 +437,24 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous half-sweep (other colour) is complete
     uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
+#if BC_PAIR_TMA
+    auto wait_pair_table = [&]() {  // phase 0 of the mbarrier: the body runs once per CTA in the PAIR kernels
+        if (PAIR) {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "PAIR_TABLE_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                "@p bra PAIR_TABLE_READY;\n"
+                "bra PAIR_TABLE_WAIT;\n"
+                "PAIR_TABLE_READY:\n"
+                "}\n" ::"r"(mb) : "memory");
+        }
+    };
+#else
+    auto wait_pair_table = [&]() {};
+#endif
     if (!DEEP) {
         if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
         else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
@@ -421,6 +462,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
         stage_other(2, off + Wc);
         stage_row_inputs(0, off, (int)((yg0 + COL) & 1u));
         cp_async_commit();
+        wait_pair_table();
 
         // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
         auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
@@ -465,6 +507,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
             stage_row_inputs(1, off + Wc, 1 - par0);
         }
         cp_async_commit();  // G_{-1}
+        wait_pair_table();
 
         auto march = [&](const uint32_t r, const int par, const bool more, const int sl) {
             if (more) {  // row r+2 exists (same parity as row r)
