@@ -151,6 +151,61 @@ def workload_config(n_gpus):
             "parallelism": f"replicas x{n_gpus}", "l2": "working set > L2"}
 
 
+def other_configs(bc, device):
+    """Device-resident rates of BASELINE.json configs 3 and 5 on one GPU and of the cluster move (not the headline)."""
+    out = {}
+
+    def series(sizes, boundary, n_rep, points, sweeps, seed):
+        engines = []
+        for Ls in sizes:
+            e = bc.Engine(Ls, boundary, n_rep, device, seed + Ls)
+            for r in range(n_rep):
+                t, d = points[r % len(points)]
+                e.set_params(t, d, J, replica=r)
+            e.init_random()
+            e.sweep(4)
+            engines.append(e)
+        small = [e for e in engines if e.L < 128]
+        group = sorted((e for e in engines if e.L >= 128), key=lambda e: -e.L)
+        bc.sweep_group(group, 16)
+        for e in engines:
+            e.sync()
+        t0 = time.perf_counter()
+        for e in small:
+            e.sweep(sweeps, 0, fetch=False)
+        bc.sweep_group(group, sweeps, 0)
+        for e in engines:
+            e.sync()
+        wall = time.perf_counter() - t0
+        sites = sum(e.L * e.L * n_rep for e in engines)
+        for e in engines:
+            e.close()
+        return sites * sweeps / (wall * 1e9)
+
+    pts = [(0.58 + 0.06 * i / 7, 1.94 + 0.05 * (i % 8) / 7) for i in range(8)]
+    out["config3_fss_ladder"] = {
+        "workload": "L=32..2048 x 8 (T,D) points (one GPU's share of the 64-point grid), periodic, 400 sweeps; "
+                    "L>=128 in one launch per half-sweep (bc_sweep_group), L=32,64 shared-memory resident",
+        "updates_per_ns": series([32, 64, 128, 256, 512, 1024, 2048], bc.PERIODIC, 8, pts, 400, 0x5EED0003)}
+    out["config5_open_boundary"] = {
+        "workload": "open boundary, L=64..1024 x 64 replicas, 200 sweeps; L>=128 in one launch per half-sweep",
+        "updates_per_ns": series([64, 128, 256, 512, 1024], bc.OPEN, 64, [(T, D)], 200, 0x5EED0005)}
+    e = bc.Engine(L, bc.PERIODIC, 1, device, SEED)
+    e.set_params(T, D, J)
+    e.init_random()
+    e.sweep(50)
+    e.cluster_update(2)
+    e.sync()
+    t0 = time.perf_counter()
+    e.cluster_update(20)
+    e.sync()
+    dt = (time.perf_counter() - t0) / 20
+    e.close()
+    out["cluster_move"] = {"workload": f"bc_cluster_update on one L={L} lattice (Swendsen-Wang on the +-1 spins)",
+                           "ms_per_update": dt * 1e3, "sites_per_ns": L * L / (dt * 1e9)}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -208,6 +263,15 @@ def run_ours(args, rank, world, local_rank):
         e1.sweep(1024)
         single = float(L) * L * 1024 / (e1.timer_stop() * 1e6)
         e1.close()
+
+    # ---- for the record as well (N = 1 only, outside every timed region of the headline): BASELINE configs 3 and 5
+    # ---- with bc_sweep_group (one launch per half-sweep for all sizes >= 128) and the cluster move
+    others = None
+    if rank == 0 and world == 1:
+        try:
+            others = other_configs(bc, local_rank)
+        except Exception as ex:  # informational: never fail the bench line over it
+            others = {"error": str(ex)}
 
     # ---- end to end through the C ABI from pinned host buffers.  Several handles (streams) are used the way a
     # ---- caller with many batches would: while one batch is swept, other batches' lattices are uploaded /
@@ -314,6 +378,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "single_lattice": {"workload": f"one L={L} lattice (16 MiB, L2-resident; CUDA-graph replay + PDL)",
                                "updates_per_ns": single},
+            "other_configs": others,
             "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
                       "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": ties_resident},
         }
