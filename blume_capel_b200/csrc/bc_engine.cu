@@ -1442,8 +1442,15 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
 // ---------------------------------------------------------------------------------------------
 // shared by the cluster move and the cluster-size measurement: stage the lattices row-major, draw the bonds
 // (threshold thr on Philox stream 3 at counter `cstep`), label connected components (root = smallest site)
+// grid of the per-site cluster kernels: x = 256-site blocks of one replica, y = replicas (stride loop beyond 65535)
+static dim3 site_grid(const bc_engine* e) {
+    const long long N = (long long)e->L * e->L;
+    return dim3((unsigned)((N + 255) / 256), (unsigned)std::min(e->n_rep, 65535));
+}
+
 static int label_clusters(bc_engine* e, uint32_t thr, int64_t cstep, bool always = false) {
     const long long N = (long long)e->L * e->L, total = N * e->n_rep;
+    if (N > 0x7FFFFFFFLL) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: site indices are 32-bit (L <= 46340)");
     int rc = ensure_stage(e, (size_t)total);
     if (rc != BC_OK) return rc;
     if (e->cluster_cap < (size_t)total) {
@@ -1489,15 +1496,19 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
     int rc = bond_threshold_of(e, "bc_cluster_update", &thr);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaSetDevice(e->device));
-    const long long N = (long long)e->L * e->L, total = N * e->n_rep;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const long long N = (long long)e->L * e->L;
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     for (int64_t u = 0; u < n_updates; ++u) {
         rc = label_clusters(e, thr, e->cluster_step);
         if (rc != BC_OK) return rc;
         const uint32_t c_lo = (uint32_t)((uint64_t)e->cluster_step & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)e->cluster_step >> 32);
-        sw_flip_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->L, e->n_rep, k0, k1, c_lo, c_hi);
-        ++e->launches;
+        // the bond bytes have served their purpose (border merge): the array now takes one flip bit per cluster root
+        const dim3 rgrid((unsigned)((N + 8LL * SW_ROOT_SPAN - 1) / (8LL * SW_ROOT_SPAN)), (unsigned)std::min(e->n_rep, 65535));
+        sw_rootbit_kernel<<<rgrid, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->d_bonds, e->L, e->n_rep, k0, k1, c_lo, c_hi);
+        dim3 fgrid = site_grid(e);
+        if ((N & 3) == 0) fgrid.x = (unsigned)((N / 4 + 255) / 256);  // four sites per thread
+        sw_flip_kernel<<<fgrid, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->d_bonds, e->L, e->n_rep);
+        e->launches += 2;
         BC_CUDA(e, cudaGetLastError());
         rc = stage_to_device(e, 0, e->n_rep);
         if (rc != BC_OK) return rc;
@@ -1525,7 +1536,6 @@ extern "C" int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_clus
     int rc = label_clusters(e, thr, ((int64_t)1 << 62) + mstep, always);
     if (rc != BC_OK) return rc;
     const long long N = (long long)e->L * e->L, total = N * e->n_rep;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
     if (!e->d_csize) BC_CUDA(e, cudaMalloc(&e->d_csize, e->cluster_cap * sizeof(int32_t)));
     if (!e->d_cmom) BC_CUDA(e, cudaMalloc(&e->d_cmom, (size_t)e->n_rep * 3 * sizeof(unsigned long long)));
     int32_t* d_size = e->d_csize;
@@ -1534,8 +1544,10 @@ extern "C" int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_clus
     if (st == cudaSuccess) st = cudaMemsetAsync(d_out, 0, (size_t)e->n_rep * 3 * sizeof(unsigned long long), e->stream);
     std::vector<unsigned long long> h((size_t)e->n_rep * 3);
     if (st == cudaSuccess) {
-        sw_compress_kernel<<<blocks, 256, 0, e->stream>>>(e->d_parent, total, e->L);
-        sw_count_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_parent, d_size, e->L, e->n_rep);
+        dim3 cgrid = site_grid(e);
+        if ((N & 3) == 0) cgrid.x = (unsigned)((N / 4 + 255) / 256);  // four sites per thread
+        sw_compress_kernel<<<cgrid, 256, 0, e->stream>>>(e->d_parent, e->L, e->n_rep);
+        sw_count_kernel<<<site_grid(e), 256, 0, e->stream>>>(e->d_stage, e->d_parent, d_size, e->L, e->n_rep);
         sw_moments_kernel<<<(unsigned)((total + SW_MOM_PER_CTA - 1) / SW_MOM_PER_CTA), 256, 0, e->stream>>>(d_size, e->L, e->n_rep, d_out);
         e->launches += 3;
         st = cudaGetLastError();

@@ -1476,9 +1476,27 @@ sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, i
     for (int ly = warp; ly < h; ly += WARPS) {
         const int x = x0 + lx, y = y0 + ly;
         const int32_t i0 = x + y * L;
-        const int8_t s0 = v0 ? sp[i0] : (int8_t)0, s1 = v1 ? sp[i0 + 1] : (int8_t)0;
-        uint32_t b0 = v0 ? sw_candidates(sp, L, open, x, y, s0) : 0u;
-        uint32_t b1 = v1 ? sw_candidates(sp, L, open, x + 1, y, s1) : 0u;
+        uint32_t b0, b1;
+        if (!(L & 1)) {
+            // even L: x and i0 are even, a lane's two sites and the two below them are aligned 16-bit loads, the right
+            // neighbour of the second site is the next lane's first site (a load only at the tile's last pair);
+            // an absent neighbour (open edge) reads as spin 0, which never equals a non-zero spin
+            const uint32_t own = v0 ? *reinterpret_cast<const uint16_t*>(sp + i0) : 0u;
+            const int yd = y + 1 == L ? 0 : y + 1;
+            const uint32_t dn = (v0 && !(open && y + 1 == L)) ? *reinterpret_cast<const uint16_t*>(sp + yd * L + x) : 0u;
+            const uint32_t s0 = own & 0xFFu, s1 = own >> 8;
+            uint32_t r1 = __shfl_down_sync(0xFFFFFFFFu, s0, 1);
+            if (v0 && lx + 2 >= w) {
+                const int xr = x + 2;
+                r1 = xr < L ? (uint32_t)(uint8_t)sp[y * L + xr] : (open ? 0u : (uint32_t)(uint8_t)sp[y * L]);
+            }
+            b0 = (s0 != 0 && s1 == s0 ? 1u : 0u) | (s0 != 0 && (dn & 0xFFu) == s0 ? 2u : 0u);
+            b1 = (s1 != 0 && r1 == s1 ? 1u : 0u) | (s1 != 0 && (dn >> 8) == s1 ? 2u : 0u);
+        } else {
+            const int8_t s0 = v0 ? sp[i0] : (int8_t)0, s1 = v1 ? sp[i0 + 1] : (int8_t)0;
+            b0 = v0 ? sw_candidates(sp, L, open, x, y, s0) : 0u;
+            b1 = v1 ? sw_candidates(sp, L, open, x + 1, y, s1) : 0u;
+        }
         if ((b0 | b1) && !always) {
             uint32_t r[4];
             if (!(i0 & 1)) {  // both sites in one call
@@ -1528,6 +1546,12 @@ sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, i
     for (int ly = warp; ly < h; ly += WARPS) {
         const int l0 = ly * SW_TX + lx;
         int32_t* dst = parent + (size_t)rep * N + (size_t)(x0 + lx) + (size_t)(y0 + ly) * L;
+        if (v0 && v1 && !(L & 1)) {  // even L: the pair is one aligned 8-byte store
+            const int32_t ra = sw_find(lab, l0), rb = sw_find(lab, l0 + 1);
+            *reinterpret_cast<int2*>(dst) = make_int2((x0 + (ra & (SW_TX - 1))) + (y0 + ra / SW_TX) * L,
+                                                      (x0 + (rb & (SW_TX - 1))) + (y0 + rb / SW_TX) * L);
+            continue;
+        }
         if (v0) {
             const int32_t r = sw_find(lab, l0);
             dst[0] = (x0 + (r & (SW_TX - 1))) + (y0 + r / SW_TX) * L;
@@ -1561,30 +1585,60 @@ sw_border_kernel(const uint8_t* __restrict__ bonds, int32_t* __restrict__ parent
 }
 
 // parent[i] = root(i) for every site (needed by the size histogram; the flip kernel finds roots itself)
-__global__ void sw_compress_kernel(int32_t* __restrict__ parent, long long total, int L) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    int32_t* par = parent + (gid / N) * N;
-    const int32_t i = (int32_t)(gid % N);
-    const int32_t p = par[i];  // tile-local root (or i itself)
-    const int32_t r = sw_root_shorten(par, i);
-    if (r != p) par[i] = r;
+// (The per-site kernels below run on a 2-D grid: x = site index inside a replica in 32 bits, y = replica with a
+// stride loop -- a 64-bit division per thread to split a flat index costs more than the rest of these kernels.)
+__global__ void __launch_bounds__(256) sw_compress_kernel(int32_t* __restrict__ parent, int L, int n_rep) {
+    const uint32_t N = (uint32_t)L * (uint32_t)L;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((N & 3u) == 0) {  // four sites per thread: the dependent loads of four chains in flight (see sw_flip_kernel)
+        const uint32_t i = 4u * tid;
+        if (i >= N) return;
+        for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+            int32_t* par = parent + (size_t)rep * N;
+            const int4 t4 = *reinterpret_cast<const int4*>(par + i);
+            const int32_t t[4] = {t4.x, t4.y, t4.z, t4.w};
+            int32_t pt[4], root[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) pt[b] = par[t[b]];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                root[b] = pt[b];
+                if (pt[b] != t[b]) {
+                    root[b] = sw_find(par, pt[b]);
+                    if (root[b] != pt[b]) par[t[b]] = root[b];
+                }
+            }
+            if (root[0] != t[0] || root[1] != t[1] || root[2] != t[2] || root[3] != t[3])
+                *reinterpret_cast<int4*>(par + i) = make_int4(root[0], root[1], root[2], root[3]);
+        }
+    } else {
+        if (tid >= N) return;
+        for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+            int32_t* par = parent + (size_t)rep * N;
+            const int32_t p = par[tid];  // tile-local root (or the site itself)
+            const int32_t r = sw_root_shorten(par, (int32_t)tid);
+            if (r != p) par[tid] = r;
+        }
+    }
 }
 
 // cluster sizes: size[root] += 1 for every non-zero site (parent compressed), then per replica
 // sum of size^2, largest size and number of clusters (gamma_nu.cpp:35-60 needs sum size^2 - max^2)
 __global__ void sw_count_kernel(const int8_t* __restrict__ spins, const int32_t* __restrict__ parent,
                                 int32_t* __restrict__ size, int L, int n_rep) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = gid < N * n_rep && spins[gid] != 0;
-    // neighbouring sites mostly share a root: one atomic per distinct root of a warp, not one per site
-    const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
-    if (!live) return;
-    const long long slot = (gid / N) * N + parent[gid];
-    const unsigned same = __match_any_sync(active, slot);
-    if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&size[slot], __popc(same));
+    const uint32_t N = (uint32_t)L * (uint32_t)L;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+        const size_t base = (size_t)rep * N;
+        const bool live = i < N && spins[base + i] != 0;
+        // neighbouring sites mostly share a root: one atomic per distinct root of a warp, not one per site
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
+        if (live) {
+            const int32_t root = parent[base + i];
+            const unsigned same = __match_any_sync(active, root);
+            if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&size[base + root], __popc(same));
+        }
+    }
 }
 
 // One CTA reduces SW_MOM_PER_CTA consecutive entries: per-thread partial sums, warp shuffles, shared atomics, then
@@ -1639,19 +1693,117 @@ sw_moments_kernel(const int32_t* __restrict__ size, int L, int n_rep,
     }
 }
 
-__global__ void sw_flip_kernel(int8_t* __restrict__ spins, int32_t* __restrict__ parent, int L, int n_rep,
-                               uint32_t key0, uint32_t key1, uint32_t c_lo, uint32_t c_hi) {
-    const long long N = (long long)L * L;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= N * n_rep) return;
-    const int8_t s = spins[gid];
-    if (s == 0) return;
-    const int rep = (int)(gid / N);
-    int32_t* par = parent + (size_t)rep * N;
-    const int32_t root = sw_root_shorten(par, (int32_t)(gid - (long long)rep * N));
-    uint32_t w[4];
-    philox4x32_10((uint32_t)root, c_lo, c_hi, STREAM_FLIP << 1, key0, key1 ^ (uint32_t)rep, w);
-    if (w[0] & 1u) spins[gid] = (int8_t)-s;
+// Flip decisions, one per CLUSTER: the cluster's root draws Philox(root) on stream 4 and leaves the bit in
+// flipbit[root].  Roots are a few per cent of the sites, so a warp first compacts the roots of SW_ROOT_SPAN
+// consecutive sites into a shared-memory list (ballot + popc) and then draws for 32 roots at a time -- every lane
+// of a Philox call works, instead of one call per site in which all lanes of a cluster repeat the same draw.
+constexpr int SW_ROOT_SPAN = 512;  // sites per warp
+__global__ void __launch_bounds__(256)
+sw_rootbit_kernel(const int8_t* __restrict__ spins, const int32_t* __restrict__ parent, uint8_t* __restrict__ flipbit,
+                  int L, int n_rep, uint32_t key0, uint32_t key1, uint32_t c_lo, uint32_t c_hi) {
+    __shared__ uint16_t s_list[8][SW_ROOT_SPAN];  // offsets of the warp's roots from its first site
+    const uint32_t N = (uint32_t)L * (uint32_t)L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t first = (blockIdx.x * 8u + (uint32_t)warp) * SW_ROOT_SPAN;
+    if (first >= N) return;
+    uint16_t* list = s_list[warp];
+    for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+        const size_t base = (size_t)rep * N;
+        int count = 0;
+        if ((N & 3u) == 0) {
+            // four groups of 128 sites, a lane owns 4 consecutive sites of each: all 8 vector loads are issued before
+            // the first ballot (the scan is pure memory latency otherwise)
+            uint32_t sp4[4];
+            int4 pa4[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t i = first + 128u * g + 4u * lane;
+                const bool in = i < N;
+                sp4[g] = in ? *reinterpret_cast<const uint32_t*>(spins + base + i) : 0u;
+                pa4[g] = in ? *reinterpret_cast<const int4*>(parent + base + i) : make_int4(-1, -1, -1, -1);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int32_t i = (int32_t)(first + 128u * g + 4u * lane);
+                const int32_t pv[4] = {pa4[g].x, pa4[g].y, pa4[g].z, pa4[g].w};
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const bool root = ((sp4[g] >> (8 * b)) & 0xFFu) != 0 && pv[b] == i + b;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, root);
+                    if (root) list[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(128 * g + 4 * lane + b);
+                    count += __popc(m);
+                }
+            }
+        } else {
+            for (int k = 0; k < SW_ROOT_SPAN; k += 32) {
+                const uint32_t i = first + k + lane;
+                const bool root = i < N && spins[base + i] != 0 && parent[base + i] == (int32_t)i;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, root);
+                if (root) list[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(k + lane);
+                count += __popc(m);
+            }
+        }
+        __syncwarp();
+        for (int j = lane; j < count; j += 32) {
+            const uint32_t i = first + list[j];
+            uint32_t w[4];
+            philox4x32_10(i, c_lo, c_hi, STREAM_FLIP << 1, key0, key1 ^ (uint32_t)rep, w);
+            flipbit[base + i] = (uint8_t)(w[0] & 1u);
+        }
+        __syncwarp();
+    }
+}
+
+// Every non-zero site looks its cluster's bit up: site -> tile root -> cluster root -> bit, three dependent loads.
+// A thread owns four consecutive sites and keeps the four chains in flight side by side (one site per thread ran at
+// a quarter of the speed, all warps parked on the long scoreboard).  grid.x covers N / 4 threads (N % 4 == 0) or N.
+__global__ void __launch_bounds__(256)
+sw_flip_kernel(int8_t* __restrict__ spins, int32_t* __restrict__ parent, const uint8_t* __restrict__ flipbit, int L, int n_rep) {
+    const uint32_t N = (uint32_t)L * (uint32_t)L;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((N & 3u) == 0) {
+        const uint32_t i = 4u * tid;
+        if (i >= N) return;
+        for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+            const size_t base = (size_t)rep * N;
+            int32_t* par = parent + base;
+            const uint32_t s4 = *reinterpret_cast<const uint32_t*>(spins + base + i);
+            if (s4 == 0) continue;
+            const int4 t4 = *reinterpret_cast<const int4*>(par + i);
+            const int32_t t[4] = {t4.x, t4.y, t4.z, t4.w};
+            int32_t pt[4], root[4];
+            uint32_t bit[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) pt[b] = par[t[b]];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                root[b] = pt[b];
+                if (pt[b] != t[b]) {  // the tile root is not the cluster root: walk on and point it there
+                    root[b] = sw_find(par, pt[b]);
+                    if (root[b] != pt[b]) par[t[b]] = root[b];
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bit[b] = flipbit[base + root[b]];
+            uint32_t out = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t sb = (s4 >> (8 * b)) & 0xFFu;
+                const uint32_t nb = (bit[b] && sb) ? ((0u - sb) & 0xFFu) : sb;  // -1 <-> +1, 0 stays
+                out |= nb << (8 * b);
+            }
+            if (out != s4) *reinterpret_cast<uint32_t*>(spins + base + i) = out;
+        }
+    } else {
+        if (tid >= N) return;
+        for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
+            const size_t base = (size_t)rep * N;
+            const int8_t s = spins[base + tid];
+            if (s == 0) continue;
+            const int32_t root = sw_root_shorten(parent + base, (int32_t)tid);
+            if (flipbit[base + root]) spins[base + tid] = (int8_t)-s;
+        }
+    }
 }
 
 }  // namespace bc
