@@ -1460,6 +1460,8 @@ sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, i
     static_assert(SW_TX == 64 && SW_THREADS % 32 == 0, "a warp covers one 64-site tile row");
     __shared__ __align__(16) int32_t lab[SW_TX * SW_TY];
     __shared__ __align__(16) uint8_t bnd[SW_TX * SW_TY];
+    __shared__ int s_next_row;
+    if (threadIdx.x == 0) s_next_row = 0;
     constexpr int WARPS = SW_THREADS / 32;
     const int tiles = tiles_x * tiles_y;
     const int rep = (int)(blockIdx.x / (unsigned)tiles), tile = (int)(blockIdx.x - (unsigned)rep * tiles);
@@ -1530,7 +1532,13 @@ sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, i
         *reinterpret_cast<int2*>(&lab[l0]) = make_int2(ly * SW_TX + start0, ly * SW_TX + start1);
     }
     __syncthreads();
-    for (int ly = warp; ly + 1 < h; ly += WARPS) {
+    // rows are handed out dynamically: the cost of a row's unions varies (the ncu source page showed a fifth of the
+    // kernel's stall samples at the barrier behind this phase with a static row assignment)
+    for (;;) {
+        int ly = 0;
+        if (lane == 0) ly = atomicAdd(&s_next_row, 1);
+        ly = __shfl_sync(0xFFFFFFFFu, ly, 0);
+        if (ly + 1 >= h) break;
         const int l0 = ly * SW_TX + lx;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -1547,7 +1555,9 @@ sw_local_kernel(const int8_t* __restrict__ spins, uint8_t* __restrict__ bonds, i
         const int l0 = ly * SW_TX + lx;
         int32_t* dst = parent + (size_t)rep * N + (size_t)(x0 + lx) + (size_t)(y0 + ly) * L;
         if (v0 && v1 && !(L & 1)) {  // even L: the pair is one aligned 8-byte store
-            const int32_t ra = sw_find(lab, l0), rb = sw_find(lab, l0 + 1);
+            // site -> first site of its run (one hop) -> root; whoever walks the chain above a run start points the
+            // run start at the root for the rest of the run (sw_root_shorten on the shared-memory labels)
+            const int32_t ra = sw_root_shorten(lab, l0), rb = sw_root_shorten(lab, l0 + 1);
             *reinterpret_cast<int2*>(dst) = make_int2((x0 + (ra & (SW_TX - 1))) + (y0 + ra / SW_TX) * L,
                                                       (x0 + (rb & (SW_TX - 1))) + (y0 + rb / SW_TX) * L);
             continue;
