@@ -1634,20 +1634,34 @@ __global__ void __launch_bounds__(256) sw_compress_kernel(int32_t* __restrict__ 
 
 // cluster sizes: size[root] += 1 for every non-zero site (parent compressed), then per replica
 // sum of size^2, largest size and number of clusters (gamma_nu.cpp:35-60 needs sum size^2 - max^2)
-__global__ void sw_count_kernel(const int8_t* __restrict__ spins, const int32_t* __restrict__ parent,
-                                int32_t* __restrict__ size, int L, int n_rep) {
+__global__ void __launch_bounds__(256)
+sw_count_kernel(const int8_t* __restrict__ spins, const int32_t* __restrict__ parent, int32_t* __restrict__ size, int L, int n_rep) {
+    __shared__ int32_t s_root;  // one root per CTA is counted in shared memory first (a spanning cluster would
+    __shared__ int s_count;     // otherwise take one global atomic per warp on a single address)
     const uint32_t N = (uint32_t)L * (uint32_t)L;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     for (int rep = blockIdx.y; rep < n_rep; rep += gridDim.y) {
         const size_t base = (size_t)rep * N;
+        if (threadIdx.x == 0) { s_root = -1; s_count = 0; }
+        __syncthreads();
         const bool live = i < N && spins[base + i] != 0;
-        // neighbouring sites mostly share a root: one atomic per distinct root of a warp, not one per site
-        const unsigned active = __ballot_sync(0xFFFFFFFFu, live);
-        if (live) {
-            const int32_t root = parent[base + i];
-            const unsigned same = __match_any_sync(active, root);
-            if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&size[base + root], __popc(same));
+        // consecutive sites mostly share a root: one atomic per run of equal roots inside a warp (the first lane of a
+        // run adds the run's length), not one per site; -1 marks zero spins and never equals a root
+        const int32_t root = live ? parent[base + i] : -1;
+        const int32_t prev = __shfl_up_sync(0xFFFFFFFFu, root, 1);
+        const bool head = lane == 0 || root != prev;
+        const unsigned heads = __ballot_sync(0xFFFFFFFFu, head);
+        const unsigned later = heads & ~((2u << lane) - 1u);  // run heads behind this lane
+        const int run = (later ? __ffs(later) - 1 : 32) - lane;
+        if (head && live && run >= 16) atomicCAS(&s_root, -1, root);  // the first long run names the CTA's root
+        __syncthreads();
+        if (head && live) {
+            if (root == s_root) atomicAdd(&s_count, run);
+            else atomicAdd(&size[base + root], run);
         }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) atomicAdd(&size[base + s_root], s_count);
     }
 }
 
