@@ -15,7 +15,8 @@ def pytest_configure(config):
 def _ensure_built():
     """Built artefacts are git-ignored; if a checkout arrives without them, build once (nvcc, g++, make)."""
     needed = [os.path.join(ROOT, "blume_capel_b200", "libbc_engine.so"), os.path.join(ROOT, "oracle", "libbc_oracle.so"),
-              os.path.join(ROOT, "blume_capel_b200", "host", "bc_run"), os.path.join(ROOT, "blume_capel_b200", "host", "bc_gaptool"),
+              os.path.join(ROOT, "blume_capel_b200", "host", "bc_run"), os.path.join(ROOT, "blume_capel_b200", "host", "bc_runner"),
+              os.path.join(ROOT, "blume_capel_b200", "host", "bc_gaptool"),
               os.path.join(ROOT, "blume_capel_b200", "host", "bc_magnet"), os.path.join(ROOT, "blume_capel_b200", "host", "bc_gamma_nu"),
               os.path.join(ROOT, "blume_capel_b200", "host", "bc_gap_stats")]
     if not all(os.path.exists(p) for p in needed):

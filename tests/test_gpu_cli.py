@@ -79,3 +79,72 @@ def test_bc_run_exact_checkpoint(tmp_path):
         fa = (a / "d" / "spin" / "64" / "0" / f"{i}.txt").read_bytes()
         fb = (b / "d" / "spin" / "64" / "0" / f"{i}.txt").read_bytes()
         assert fa == fb, i
+
+
+BC_RUNNER = os.path.join(ROOT, "blume_capel_b200", "host", "bc_runner")
+
+
+def _tree(base):
+    out = {}
+    for d, _, files in os.walk(base):
+        for f in files:
+            p = os.path.join(d, f)
+            out[os.path.relpath(p, base)] = open(p, "rb").read()
+    return out
+
+
+@pytest.mark.parametrize("cluster_every", [0, 3])
+def test_bc_runner_equals_one_bc_run_per_size_and_run(tmp_path, cluster_every):
+    """The whole campaign of job_scripts/runner.sh in one process: every (size, run) must produce the files
+    bc_run r ... --L L --seed (seed ^ (r << 32)) produces."""
+    seed = 0x1234ABCD5678
+    flags = ["--burn-sweeps", "30", "--sweeps-per-sample", "8", "--mkdir"]
+    if cluster_every:
+        flags += ["--cluster-every", str(cluster_every)]
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    r = subprocess.run([BC_RUNNER, "data", "0.608", "1.966", "1.0", "--L", "8,12,32", "--runs", "3,2,2", "--nsamples", "2",
+                        "--seed", str(seed), "--obs"] + flags, cwd=a, check=True, capture_output=True, text=True)
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    assert [x["L"] for x in lines] == [8, 12, 32] and [x["runs"] for x in lines] == [3, 2, 2]
+    for L, runs in ((8, 3), (12, 2), (32, 2)):
+        for run in range(runs):
+            subprocess.run([BC_RUN, str(run), "data", "2", "2", "0.608", "1.966", "1.0", "--L", str(L), "--seed",
+                            str(seed ^ (run << 32))] + flags, cwd=b, check=True, capture_output=True)
+    ta, tb = _tree(a / "data" / "spin"), _tree(b / "data" / "spin")
+    assert sorted(ta) == sorted(tb) and len(ta) == (3 + 2 + 2) * 2
+    assert ta == tb
+    assert _tree(a / "data" / "fk") == _tree(b / "data" / "fk")
+    # the burn file is run 0's lattice; bc_run wrote it last for its last run, so compare with a fresh run 0
+    rows = open(a / "data" / "obs" / "32.csv").read().strip().splitlines()
+    assert rows[0] == "run,sample,sweep,M,Q,B" and len(rows) == 1 + 2 * 2
+
+
+def test_bc_runner_lockstep_and_burn_file_start(tmp_path):
+    """--burn 1 writes the burn files, --burn 0 starts every run from them; --lockstep (one launch per half-sweep for
+    all sizes) gives the same files as one thread per size."""
+    common = ["data", "0.608", "1.966", "1.0", "--L", "128,256", "--runs", "2", "--seed", "77", "--burn-sweeps", "12",
+              "--sweeps-per-sample", "20", "--no-fk", "--mkdir"]
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    for d in (a, b):
+        subprocess.run([BC_RUNNER] + common + ["--burn", "1", "--nsamples", "0"], cwd=d, check=True, capture_output=True)
+        assert os.path.exists(d / "data" / "burn" / "128_burn.txt") and not os.path.exists(d / "data" / "spin" / "128" / "0" / "0.txt")
+    subprocess.run([BC_RUNNER] + common + ["--burn", "0", "--nsamples", "3"], cwd=a, check=True, capture_output=True)
+    subprocess.run([BC_RUNNER] + common + ["--burn", "0", "--nsamples", "3", "--lockstep"], cwd=b, check=True, capture_output=True)
+    ta, tb = _tree(a / "data"), _tree(b / "data")
+    assert len(ta) == 2 + 2 * 2 * 3 and ta == tb
+    # same start, different keys: the two runs of a size differ after the first sample
+    assert ta["spin/128/0/0.txt"] != ta["spin/128/1/0.txt"]
+
+
+def test_bc_runner_argument_errors(tmp_path):
+    r = subprocess.run([BC_RUNNER, "d", "0.6", "1.9", "1.0", "--L", "64,128", "--sweeps-per-sample", "4", "--lockstep"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 2 and "lockstep" in r.stderr
+    r = subprocess.run([BC_RUNNER, "d", "0.6", "1.9", "1.0", "--L", "8,12", "--runs", "1,2,3"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 2
+    r = subprocess.run([BC_RUNNER, "d", "0.6", "1.9", "1.0", "--L", "8", "--runs", "1", "--nsamples", "1", "--burn", "0"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "burn file" in r.stderr
