@@ -67,3 +67,27 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "bc_oracle" not in text and "oracle." not in text and "from oracle" not in text, f
+
+
+def test_host_campaign_driver_arguments_and_no_fallback(tmp_path, bc):
+    """bc_runner (the runner.sh campaign in one process): argument errors need no GPU, and without a GPU it fails
+    loudly instead of computing anything on the CPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "blume_capel_b200", "host", "bc_runner")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: bc_runner root T D J" in r.stderr
+    r = subprocess.run([exe, "d", "0.6", "1.9", "1.0", "--L", "64,128", "--sweeps-per-sample", "4", "--lockstep"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 2 and "lockstep" in r.stderr
+    r = subprocess.run([exe, "d", "0.6", "1.9", "1.0", "--L", "8,12", "--runs", "1,2,3"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "--runs" in r.stderr
+    lib = bc.load_library()
+    h = C.c_void_p()
+    if lib.bc_create(C.byref(h), 32, 0, 1, 0, 0, 0) == 0:
+        lib.bc_destroy(h)
+        return  # a CUDA device is present: the GPU tests cover the rest
+    r = subprocess.run([exe, "d", "0.6", "1.9", "1.0", "--L", "8", "--runs", "2", "--nsamples", "1", "--mkdir"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+    assert not os.path.exists(tmp_path / "d" / "spin" / "8" / "0" / "0.txt")
