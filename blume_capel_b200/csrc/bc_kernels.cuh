@@ -892,6 +892,7 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     uint32_t n_ties = 0;
     int64_t slot = 0;
 
+    const int y_first = ltid / cpr, j_first = ltid - y_first * cpr;
     // one half-sweep of colour COL over this replica's rows
     auto half_sweep = [&](auto colc, auto measc, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S) {
         constexpr int COL = decltype(colc)::value;
@@ -899,7 +900,10 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
         uint8_t* own = COL ? s_c1 : s_c0;
         const uint8_t* oth = COL ? s_c0 : s_c1;
         for (int item = ltid; item < items; item += T) {
-            const int y = item / cpr, j = item - y * cpr;
+            // a thread's first item (its only one when T >= items, the latency-bound case) never changes: its row and
+            // chunk are computed once per launch, not with an integer division per half-sweep
+            int y = y_first, j = j_first;
+            if (item != ltid) { y = item / cpr; j = item - y * cpr; }
             const int par = (y + COL) & 1;
             const uint32_t rowo = (uint32_t)y * Wc, co = (uint32_t)j * 16;
             // same-colour sites of this row: x = 2k + par < L (L/2 on a torus; odd L: one more where par == 0)
