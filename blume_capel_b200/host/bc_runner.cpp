@@ -21,7 +21,13 @@
 //   reference's attempt counts (1500*N resp. 9*N step() calls of 3 sweeps each, main.cpp:342,362,159).
 //   --lockstep (needs --sweeps-per-sample, every L >= 128 and a multiple of 32, equal --nsamples): the sizes
 //   advance together with ONE kernel launch per half-sweep (bc_sweep_group) instead of one thread per size.
-//   --obs writes ./{root}/obs/{L}.csv (run,sample,sweep,M,Q,B).  One JSON line per size goes to stdout.
+//   --obs writes ./{root}/obs/{L}.csv (run,sample,sweep,M,Q,B).  One JSON line per size (and point) goes to stdout.
+//   --T-list a,b,... / --D-list x,y,...: a grid of (T, D) points instead of the positional pair (BASELINE config 3:
+//   the finite-size-scaling ladder over a grid around the tricritical point); every point gets its own tree
+//   ./{root}/p{k}/... (k = index in the T-major grid), the replicas of a size are points x runs (replica =
+//   point * runs + run), and --shard k/n keeps the points with index % n == k for this process (one process per
+//   GPU, --device k; the Philox keys follow the process's own replica numbering, so a sharded campaign is
+//   reproducible for the same --shard, not file-identical to the unsharded one).  --cluster-every needs one common T (the bond probability is per handle).
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -71,7 +77,14 @@ std::vector<long long> int_list(const std::string& s) {
     return v;
 }
 
+struct Point {
+    double T, D;
+    int index;          // position in the full T-major grid (names the point's directory)
+    std::string root;   // ./{root} for a single point, ./{root}/p{index} on a grid
+};
+
 struct Options {
+    std::vector<Point> points;
     std::string root = "NONE";
     double T = 0.608, D = 1.966, J = 1.0;  // main.cpp:325-333
     std::vector<long long> sizes{8, 12, 16, 24, 32, 48, 64}, runs{100, 100, 50, 50, 50, 50, 50},
@@ -89,8 +102,8 @@ struct Size {
     bc_engine* eng = nullptr;
     std::vector<int8_t> spins;   // n_runs lattices, replica-major
     std::vector<bc_obs> obs;     // n_runs records
-    FILE* obs_file = nullptr;
-    double sE = 0, sAm = 0, sQ = 0, sM2 = 0, sM4 = 0;
+    std::vector<FILE*> obs_file;                 // per point
+    std::vector<double> sE, sAm, sQ, sM2, sM4;   // per point
     std::string error;
 };
 
@@ -111,50 +124,67 @@ bool evolve(const Options& o, Size& s, long long n) {
     return true;
 }
 
-std::string burn_path(const Options& o, int L) { return "./" + o.root + "/burn/" + std::to_string(L) + "_burn.txt"; }
+std::string burn_path(const Point& pt, int L) { return "./" + pt.root + "/burn/" + std::to_string(L) + "_burn.txt"; }
 
 bool setup(const Options& o, Size& s) {
     const long long N = (long long)s.L * s.L;
     s.burn_sweeps = o.burn_sweeps >= 0 ? o.burn_sweeps : 3 * 1500 * N;               // main.cpp:342
     s.sweeps_per_sample = o.sweeps_per_sample >= 0 ? o.sweeps_per_sample : 3 * 9 * N;  // main.cpp:362
-    if (bc_create(&s.eng, s.L, o.boundary, s.n_runs, BC_STORAGE_INT8, o.device, o.seed) != BC_OK) {
+    const int n_points = (int)o.points.size(), n_rep = n_points * s.n_runs;
+    if (bc_create(&s.eng, s.L, o.boundary, n_rep, BC_STORAGE_INT8, o.device, o.seed) != BC_OK) {
         s.error = std::string("bc_create: ") + bc_last_error(nullptr);
         return false;
     }
-    if (bc_set_params(s.eng, -1, o.T, o.D, o.J) != BC_OK) return fail(s, "bc_set_params");
-    s.spins.resize((size_t)s.n_runs * N);
-    s.obs.resize((size_t)s.n_runs);
+    if (n_points == 1) {
+        if (bc_set_params(s.eng, -1, o.points[0].T, o.points[0].D, o.J) != BC_OK) return fail(s, "bc_set_params");
+    } else {
+        for (int p = 0; p < n_points; ++p)
+            for (int r = 0; r < s.n_runs; ++r)
+                if (bc_set_params(s.eng, p * s.n_runs + r, o.points[p].T, o.points[p].D, o.J) != BC_OK) return fail(s, "bc_set_params");
+    }
+    s.spins.resize((size_t)n_rep * N);
+    s.obs.resize((size_t)n_rep);
+    s.obs_file.assign((size_t)n_points, nullptr);
+    s.sE.assign((size_t)n_points, 0.0); s.sAm = s.sQ = s.sM2 = s.sM4 = s.sE;
     if (o.do_mkdir) {  // gen_files.py:5-22 creates these for the reference
-        mkdirs("./" + o.root + "/burn");
-        for (int r = 0; r < s.n_runs; ++r) {
-            mkdirs("./" + o.root + "/spin/" + std::to_string(s.L) + "/" + std::to_string(r));
-            if (o.write_fk) mkdirs("./" + o.root + "/fk/" + std::to_string(s.L) + "/" + std::to_string(r));
+        for (const Point& pt : o.points) {
+            mkdirs("./" + pt.root + "/burn");
+            for (int r = 0; r < s.n_runs; ++r) {
+                mkdirs("./" + pt.root + "/spin/" + std::to_string(s.L) + "/" + std::to_string(r));
+                if (o.write_fk) mkdirs("./" + pt.root + "/fk/" + std::to_string(s.L) + "/" + std::to_string(r));
+            }
+            if (o.obs) mkdirs("./" + pt.root + "/obs");
         }
-        if (o.obs) mkdirs("./" + o.root + "/obs");
     }
     const bool periodic = o.boundary == BC_PERIODIC;
     if (o.burn >= 1) {
         if (bc_init_random(s.eng, -1) != BC_OK) return fail(s, "bc_init_random");
         if (!evolve(o, s, s.burn_sweeps)) return false;
-        if (bc_download(s.eng, 0, s.spins.data()) != BC_OK) return fail(s, "bc_download");
-        if (!bcgap::write_file(burn_path(o, s.L), bcgap::spin_clusters_to_gap(s.spins.data(), s.L, periodic)))
-            std::cerr << "bc_runner: cannot write " << burn_path(o, s.L) << std::endl;
+        for (int p = 0; p < n_points; ++p) {  // the burn file of a point is its run 0
+            if (bc_download(s.eng, p * s.n_runs, s.spins.data()) != BC_OK) return fail(s, "bc_download");
+            if (!bcgap::write_file(burn_path(o.points[p], s.L), bcgap::spin_clusters_to_gap(s.spins.data(), s.L, periodic)))
+                std::cerr << "bc_runner: cannot write " << burn_path(o.points[p], s.L) << std::endl;
+        }
     } else {
         // every run starts from the size's burn file, like the reference's array tasks (main.cpp:358); the sweep
         // counter continues after the nominal burn-in so that no run replays the burn-in's random numbers
-        std::string text;
-        if (!bcgap::read_file(burn_path(o, s.L), text) || !bcgap::gap_to_lattice(text, s.L, s.spins.data())) {
-            s.error = "cannot read burn file " + burn_path(o, s.L);
-            return false;
+        for (int p = 0; p < n_points; ++p) {
+            int8_t* first = &s.spins[(size_t)p * s.n_runs * N];
+            std::string text;
+            if (!bcgap::read_file(burn_path(o.points[p], s.L), text) || !bcgap::gap_to_lattice(text, s.L, first)) {
+                s.error = "cannot read burn file " + burn_path(o.points[p], s.L);
+                return false;
+            }
+            for (int r = 1; r < s.n_runs; ++r) std::memcpy(first + (size_t)r * N, first, (size_t)N);
         }
-        for (int r = 1; r < s.n_runs; ++r) std::memcpy(&s.spins[(size_t)r * N], s.spins.data(), (size_t)N);
         if (bc_upload_all(s.eng, s.spins.data()) != BC_OK) return fail(s, "bc_upload_all");
         if (bc_set_sweep_counter(s.eng, s.burn_sweeps) != BC_OK) return fail(s, "bc_set_sweep_counter");
     }
-    if (o.obs) {
-        s.obs_file = std::fopen(("./" + o.root + "/obs/" + std::to_string(s.L) + ".csv").c_str(), "w");
-        if (s.obs_file) std::fprintf(s.obs_file, "run,sample,sweep,M,Q,B\n");
-    }
+    if (o.obs)
+        for (int p = 0; p < n_points; ++p) {
+            s.obs_file[(size_t)p] = std::fopen(("./" + o.points[p].root + "/obs/" + std::to_string(s.L) + ".csv").c_str(), "w");
+            if (s.obs_file[(size_t)p]) std::fprintf(s.obs_file[(size_t)p], "run,sample,sweep,M,Q,B\n");
+        }
     return true;
 }
 
@@ -164,31 +194,35 @@ bool record(const Options& o, Size& s, int i) {
     const bool periodic = o.boundary == BC_PERIODIC;
     if (bc_measure(s.eng, s.obs.data()) != BC_OK) return fail(s, "bc_measure");
     if (o.dumps && bc_download_all(s.eng, s.spins.data()) != BC_OK) return fail(s, "bc_download_all");
-    const double p_fk = 1 - std::exp(-2 * (1 / o.T) * o.J);  // main.cpp:371
-    const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
     const std::string name = std::to_string(i) + ".txt", sL = std::to_string(s.L);
-    for (int r = 0; r < s.n_runs; ++r) {
-        const bc_obs& ob = s.obs[(size_t)r];
-        const double E = (-o.J * (double)ob.B + o.D * (double)ob.Q) / (double)N, m = (double)ob.M / (double)N,
-                     q = (double)ob.Q / (double)N;
-        s.sE += E; s.sAm += std::fabs(m); s.sQ += q; s.sM2 += m * m; s.sM4 += m * m * m * m;
-        if (s.obs_file)
-            std::fprintf(s.obs_file, "%d,%d,%lld,%lld,%lld,%lld\n", r, i, (long long)ob.sweep, (long long)ob.M,
-                         (long long)ob.Q, (long long)ob.B);
-        if (!o.dumps) continue;
-        const int8_t* lat = &s.spins[(size_t)r * N];
-        const std::string sRun = std::to_string(r);
-        bcgap::write_file("./" + o.root + "/spin/" + sL + "/" + sRun + "/" + name,
-                          bcgap::spin_clusters_to_gap(lat, s.L, periodic));  // main.cpp:369-370
-        if (o.write_fk) {                                                      // main.cpp:371-372
-            const uint32_t k0 = (uint32_t)o.seed, k1 = (uint32_t)(o.seed >> 32) ^ (uint32_t)r;  // the run's key
-            auto bond = [&](int64_t site, int dir) {
-                uint32_t w[4];
-                philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)i, (3u << 1) | (uint32_t)dir, k0, k1, w);
-                return w[0] < thr;
-            };
-            bcgap::write_file("./" + o.root + "/fk/" + sL + "/" + sRun + "/" + name,
-                              bcgap::clusters_to_gap(lat, s.L, periodic, bond));
+    for (int p = 0; p < (int)o.points.size(); ++p) {
+        const Point& pt = o.points[(size_t)p];
+        const double p_fk = 1 - std::exp(-2 * (1 / pt.T) * o.J);  // main.cpp:371
+        const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
+        for (int r = 0; r < s.n_runs; ++r) {
+            const int replica = p * s.n_runs + r;
+            const bc_obs& ob = s.obs[(size_t)replica];
+            const double E = (-o.J * (double)ob.B + pt.D * (double)ob.Q) / (double)N, m = (double)ob.M / (double)N,
+                         q = (double)ob.Q / (double)N;
+            s.sE[p] += E; s.sAm[p] += std::fabs(m); s.sQ[p] += q; s.sM2[p] += m * m; s.sM4[p] += m * m * m * m;
+            if (s.obs_file[(size_t)p])
+                std::fprintf(s.obs_file[(size_t)p], "%d,%d,%lld,%lld,%lld,%lld\n", r, i, (long long)ob.sweep, (long long)ob.M,
+                             (long long)ob.Q, (long long)ob.B);
+            if (!o.dumps) continue;
+            const int8_t* lat = &s.spins[(size_t)replica * N];
+            const std::string sRun = std::to_string(r);
+            bcgap::write_file("./" + pt.root + "/spin/" + sL + "/" + sRun + "/" + name,
+                              bcgap::spin_clusters_to_gap(lat, s.L, periodic));  // main.cpp:369-370
+            if (o.write_fk) {                                                      // main.cpp:371-372
+                const uint32_t k0 = (uint32_t)o.seed, k1 = (uint32_t)(o.seed >> 32) ^ (uint32_t)replica;  // the run's key
+                auto bond = [&](int64_t site, int dir) {
+                    uint32_t w[4];
+                    philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)i, (3u << 1) | (uint32_t)dir, k0, k1, w);
+                    return w[0] < thr;
+                };
+                bcgap::write_file("./" + pt.root + "/fk/" + sL + "/" + sRun + "/" + name,
+                                  bcgap::clusters_to_gap(lat, s.L, periodic, bond));
+            }
         }
     }
     return true;
@@ -197,12 +231,15 @@ bool record(const Options& o, Size& s, int i) {
 void summary(const Options& o, const Size& s) {
     const double n = (double)s.n_samples * s.n_runs;
     if (n <= 0) return;
-    const double m2 = s.sM2 / n, am = s.sAm / n, N = (double)s.L * s.L;
-    std::printf("{\"L\": %d, \"T\": %.10g, \"D\": %.10g, \"J\": %.10g, \"runs\": %d, \"samples\": %d, "
-                "\"sweeps_per_sample\": %lld, \"E_per_site\": %.10g, \"abs_m\": %.10g, \"q\": %.10g, \"U4\": %.10g, "
-                "\"chi\": %.10g, \"seed\": %llu}\n",
-                s.L, o.T, o.D, o.J, s.n_runs, s.n_samples, s.sweeps_per_sample, s.sE / n, am, s.sQ / n,
-                1 - (s.sM4 / n) / (3 * m2 * m2), N * (m2 - am * am), (unsigned long long)o.seed);
+    for (size_t p = 0; p < o.points.size(); ++p) {
+        const double m2 = s.sM2[p] / n, am = s.sAm[p] / n, N = (double)s.L * s.L;
+        std::printf("{\"L\": %d, \"point\": %d, \"T\": %.10g, \"D\": %.10g, \"J\": %.10g, \"runs\": %d, \"samples\": %d, "
+                    "\"sweeps_per_sample\": %lld, \"E_per_site\": %.10g, \"abs_m\": %.10g, \"q\": %.10g, \"U4\": %.10g, "
+                    "\"chi\": %.10g, \"seed\": %llu}\n",
+                    s.L, o.points[p].index, o.points[p].T, o.points[p].D, o.J, s.n_runs, s.n_samples, s.sweeps_per_sample,
+                    s.sE[p] / n, am, s.sQ[p] / n, 1 - (s.sM4[p] / n) / (3 * m2 * m2), N * (m2 - am * am),
+                    (unsigned long long)o.seed);
+    }
 }
 
 }  // namespace
@@ -213,11 +250,13 @@ int main(int argc, const char* argv[]) {
         std::cerr << "usage: bc_runner root T D J [--L a,b,...] [--runs n|a,b,...] [--nsamples n|a,b,...] [--burn 0|1|2]\n"
                      "                 [--burn-sweeps n] [--sweeps-per-sample n] [--cluster-every k] [--seed s]\n"
                      "                 [--boundary periodic|open] [--device d] [--mkdir] [--no-fk] [--no-dumps] [--obs]\n"
-                     "                 [--lockstep]\n";
+                     "                 [--lockstep] [--T-list a,b,...] [--D-list x,y,...] [--shard k/n]\n";
         return 2;
     }
     o.root = argv[1]; o.T = std::atof(argv[2]); o.D = std::atof(argv[3]); o.J = std::atof(argv[4]);
     bool have_seed = false, have_runs = false, have_nsamples = false;
+    std::string t_list, d_list;
+    int shard_k = 0, shard_n = 1;
     for (int argi = 5; argi < argc; ++argi) {
         const std::string a = argv[argi];
         auto next = [&]() -> const char* { return argi + 1 < argc ? argv[++argi] : ""; };
@@ -236,9 +275,32 @@ int main(int argc, const char* argv[]) {
         else if (a == "--no-dumps") o.dumps = false;
         else if (a == "--obs") o.obs = true;
         else if (a == "--lockstep") o.lockstep = true;
+        else if (a == "--T-list") t_list = next();
+        else if (a == "--D-list") d_list = next();
+        else if (a == "--shard") { if (std::sscanf(next(), "%d/%d", &shard_k, &shard_n) != 2) shard_n = 0; }
         else { std::cerr << "bc_runner: unknown flag " << a << std::endl; return 2; }
     }
     if (!have_seed) { std::random_device rd; o.seed = ((uint64_t)rd() << 32) | rd(); }  // like main.cpp:307-309
+    {  // the (T, D) points of this process
+        std::vector<double> Ts, Ds;
+        auto dbl_list = [](const std::string& str, std::vector<double>& v) {
+            std::stringstream ss(str);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) v.push_back(std::atof(tok.c_str()));
+        };
+        dbl_list(t_list, Ts); dbl_list(d_list, Ds);
+        if (Ts.empty()) Ts.push_back(o.T);
+        if (Ds.empty()) Ds.push_back(o.D);
+        if (shard_n < 1 || shard_k < 0 || shard_k >= shard_n) { std::cerr << "bc_runner: --shard k/n needs 0 <= k < n" << std::endl; return 2; }
+        const bool grid = Ts.size() * Ds.size() > 1;
+        int index = 0;
+        for (double t : Ts)
+            for (double d : Ds) {
+                if (index % shard_n == shard_k) o.points.push_back({t, d, index, grid ? o.root + "/p" + std::to_string(index) : o.root});
+                ++index;
+            }
+        if (o.points.empty()) { std::cerr << "bc_runner: no (T, D) point falls to shard " << shard_k << "/" << shard_n << std::endl; return 2; }
+    }
     const size_t n_sizes = o.sizes.size();
     if (!have_runs || !have_nsamples) {  // per-size defaults of runner.sh:4-6; other sizes as its largest one
         static const long long table[7][3] = {{8, 100, 15000}, {12, 100, 15000}, {16, 50, 15000}, {24, 50, 15000},
@@ -286,7 +348,7 @@ int main(int argc, const char* argv[]) {
     auto finish = [&](int rc) {
         for (Size& s : sizes) {
             if (!s.error.empty()) std::cerr << "bc_runner: L=" << s.L << ": " << s.error << std::endl;
-            if (s.obs_file) std::fclose(s.obs_file);
+            for (FILE* f : s.obs_file) if (f) std::fclose(f);
             if (s.eng) bc_destroy(s.eng);
         }
         return rc;

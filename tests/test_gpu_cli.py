@@ -148,3 +148,33 @@ def test_bc_runner_argument_errors(tmp_path):
     r = subprocess.run([BC_RUNNER, "d", "0.6", "1.9", "1.0", "--L", "8", "--runs", "1", "--nsamples", "1", "--burn", "0"],
                        cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "burn file" in r.stderr
+
+
+def test_bc_runner_grid_of_points_and_shards(tmp_path):
+    """--T-list / --D-list: every (T, D) point gets its own tree, replica = point * runs + run; with 2 runs per point
+    the runs of point k are the runs of a single-point campaign with seed ^ ((2 k) << 32).  --shard k/n splits the
+    points over processes (one per GPU)."""
+    seed = 99
+    base = ["--L", "8,32", "--runs", "2", "--nsamples", "2", "--burn-sweeps", "20", "--sweeps-per-sample", "6", "--mkdir", "--obs"]
+    a, b, c = tmp_path / "a", tmp_path / "b", tmp_path / "c"
+    for d in (a, b, c):
+        d.mkdir()
+    grid = ["--T-list", "0.6,0.7", "--D-list", "1.9,1.95"]
+    r = subprocess.run([BC_RUNNER, "data", "0", "0", "1.0", "--seed", str(seed)] + grid + base, cwd=a, check=True,
+                       capture_output=True, text=True)
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    assert [(x["L"], x["point"]) for x in lines] == [(8, 0), (8, 1), (8, 2), (8, 3), (32, 0), (32, 1), (32, 2), (32, 3)]
+    assert (lines[1]["T"], lines[1]["D"]) == (0.6, 1.95) and (lines[2]["T"], lines[2]["D"]) == (0.7, 1.9)
+    # point 2 = (0.7, 1.9): the same files as a single-point campaign whose replicas 0, 1 carry the keys of replicas 4, 5
+    subprocess.run([BC_RUNNER, "data", "0.7", "1.9", "1.0", "--seed", str(seed ^ (4 << 32))] + base, cwd=b, check=True,
+                   capture_output=True)
+    assert _tree(a / "data" / "p2") == _tree(b / "data")
+    # two shards (one process per GPU) cover the same points and files between them; the Philox keys follow a process's
+    # own replica numbering, so a sharded campaign is reproducible for the same --shard, not identical to the unsharded one
+    for k in (0, 1):
+        r = subprocess.run([BC_RUNNER, "data", "0", "0", "1.0", "--seed", str(seed), "--shard", f"{k}/2"] + grid + base,
+                           cwd=c, check=True, capture_output=True, text=True)
+        assert sorted({json.loads(x)["point"] for x in r.stdout.strip().splitlines()}) == [k, k + 2]
+    assert sorted(_tree(a / "data")) == sorted(_tree(c / "data"))
+    # shard 0 starts with point 0 at replicas 0, 1 like the unsharded run: those files are identical
+    assert _tree(a / "data" / "p0") == _tree(c / "data" / "p0")
