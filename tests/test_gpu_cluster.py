@@ -104,3 +104,24 @@ def test_cluster_update_errors(bc):
     with pytest.raises(bc.BCError):
         s.cluster_update(1)
     s.close()
+
+
+def test_cluster_moves_match_the_committed_vectors(bc):
+    """tests/golden/cluster_moves.npz (written by make_cluster_golden.py from the oracle): the GPU reproduces the
+    lattices after interleaved sweeps and cluster moves and the cluster-size moments, without the oracle in the loop."""
+    import json
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cluster_moves.npz"))
+    for i, m in enumerate(json.loads(str(z["meta"]))):
+        n_rep = m["replica"] + 1  # the fixture's replica index selects the Philox key
+        e = bc.Engine(m["L"], m["boundary"], n_rep, 0, m["seed"])
+        e.set_params(m["T"], m["D"], m["J"])
+        e.init_random()
+        for c in range(m["rounds"]):
+            e.sweep(m["sweeps"])
+            e.cluster_update(1)
+        assert np.array_equal(e.download(m["replica"]), z[f"final_{i}"]), i
+        for kind in (0, 1):
+            got = e.cluster_moments(kind, mstep=5)[m["replica"]]
+            assert (got["sum_size_sq"], got["max_size"], got["n_clusters"]) == tuple(z[f"moments_{i}"][kind]), (i, kind)
+        e.close()

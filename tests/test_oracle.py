@@ -187,3 +187,18 @@ def test_cluster_move_never_touches_zeros_and_only_flips_signs(oracle):
     t = np.ones((64, 64), np.int8)
     oracle.cluster_update(t, 1.0, 0.0, 11, 0, 0)
     assert 0.4 < (t == -1).mean() < 0.6
+
+
+def test_cluster_move_golden_fixture(oracle):
+    """The cluster-move spec (bond / flip streams, smallest-site roots) is pinned by committed vectors."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_cluster_golden", os.path.join(GOLD, "make_cluster_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    z = np.load(os.path.join(GOLD, "cluster_moves.npz"))
+    cases = json.loads(str(z["meta"]))
+    assert cases == gen.CASES
+    for i, m in enumerate(cases):
+        s, mom = gen.run_case(m)
+        assert np.array_equal(s, z[f"final_{i}"]), i
+        assert np.array_equal(mom, z[f"moments_{i}"]), i
