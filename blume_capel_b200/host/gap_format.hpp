@@ -36,9 +36,9 @@ struct UnionFind {
     }
 };
 
-// bond_open(site, dir) with dir 0 = +x, 1 = +y decides whether a same-sign bond is kept.
-inline std::string clusters_to_gap(const int8_t* spins, int L, bool periodic,
-                                   const std::function<bool(int64_t, int)>& bond_open) {
+// bond_open(site, dir) with dir 0 = +x, 1 = +y decides whether a same-sign bond is kept (any callable).
+template <class BondOpen>
+inline std::string clusters_to_gap(const int8_t* spins, int L, bool periodic, const BondOpen& bond_open) {
     const int64_t N = (int64_t)L * L;
     UnionFind uf((size_t)N);
     for (int y = 0; y < L; ++y)
@@ -60,14 +60,14 @@ inline std::string clusters_to_gap(const int8_t* spins, int L, bool periodic,
             }
         }
     // roots are the smallest site of each cluster -> clusters ordered by root, members ascending
-    std::vector<int32_t> count((size_t)N, 0), start((size_t)N, 0);
+    std::vector<int32_t> root((size_t)N, -1), count((size_t)N, 0), start((size_t)N, 0);
     for (int64_t i = 0; i < N; ++i)
-        if (spins[i] != 0) ++count[(size_t)uf.find((int32_t)i)];
+        if (spins[i] != 0) ++count[(size_t)(root[(size_t)i] = uf.find((int32_t)i))];
     int64_t acc = 0;
     for (int64_t i = 0; i < N; ++i) { start[(size_t)i] = (int32_t)acc; acc += count[(size_t)i]; }
     std::vector<int32_t> members((size_t)acc), fill(start);
     for (int64_t i = 0; i < N; ++i)
-        if (spins[i] != 0) members[(size_t)fill[(size_t)uf.find((int32_t)i)]++] = (int32_t)i;
+        if (root[(size_t)i] >= 0) members[(size_t)fill[(size_t)root[(size_t)i]]++] = (int32_t)i;
     std::string out;
     out.reserve((size_t)acc * 3 + 16);
     char buf[16];
@@ -77,8 +77,12 @@ inline std::string clusters_to_gap(const int8_t* spins, int L, bool periodic,
         int32_t prev = 0;
         for (int32_t k = 0; k < count[(size_t)r]; ++k) {
             const int32_t p = members[(size_t)(start[(size_t)r] + k)];
-            const int n = std::snprintf(buf, sizeof buf, "%d ", p - prev);
-            out.append(buf, (size_t)n);
+            // decimal digits of the gap (>= 0: members ascend from 0) followed by one space, written backwards
+            uint32_t v = (uint32_t)(p - prev);
+            char* e = buf + sizeof buf;
+            *--e = ' ';
+            do { *--e = (char)('0' + v % 10); v /= 10; } while (v);
+            out.append(e, (size_t)(buf + sizeof buf - e));
             prev = p;
         }
         out += '\n';
