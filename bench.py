@@ -117,6 +117,17 @@ def reference_sample(n_procs, L_ref=32, nsteps=1):
     return n, wall, "port", "oracle literal port of main.cpp:89-112, L=64, 1e8 attempts, 1 thread"
 
 
+def cpu_model():
+    """Model name of the host CPU (state what the reference was timed on)."""
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -135,7 +146,8 @@ def run_reference_arm(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "spin-updates/ns", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "spin-updates/ns", "cores": cores, "kind": kind, "sample": sample,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "spin-updates/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference cannot be built for L >= 512 (main.cpp:57-59); its per-attempt rate is size independent",
     }
@@ -358,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             a, w, kind, sample = reference_sample(1, 32, 2)
-            cpu = {"value": a / w / 1e9, "unit": "spin-updates/ns", "cores": 1, "kind": kind, "sample": sample}
+            cpu = {"value": a / w / 1e9, "unit": "spin-updates/ns", "cores": 1, "kind": kind, "sample": sample,
+                   "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
         N = L * L
         line = {
             "metric": "spin-updates/ns", "value": value, "unit": "spin-updates/ns", "n_gpus": world,
