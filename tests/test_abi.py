@@ -91,3 +91,22 @@ def test_host_campaign_driver_arguments_and_no_fallback(tmp_path, bc):
                        cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
     assert not os.path.exists(tmp_path / "d" / "spin" / "8" / "0" / "0.txt")
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/bc_engine.h compiles as C99 (what a cgo / JNI / ctypes-free binding would include) and every entry
+    point it declares resolves against libbc_engine.so at link time."""
+    import subprocess
+    names = declared_symbols()
+    src = tmp_path / "abi.c"
+    body = "\n".join(f"    p[{i}] = (void*)&{n};" for i, n in enumerate(names))
+    src.write_text('#include "bc_engine.h"\n#include <stdio.h>\nint main(void) {\n'
+                   f"    void* p[{len(names)}];\n{body}\n"
+                   f"    printf(\"%d %p\\n\", bc_abi_version(), p[{len(names) - 1}]);\n    return 0;\n}}\n")
+    lib_dir = os.path.join(ROOT, "blume_capel_b200")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"),
+                    "-o", str(exe), str(src), "-L", lib_dir, "-lbc_engine", f"-Wl,-rpath,{lib_dir}"], check=True,
+                   capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == "1"
