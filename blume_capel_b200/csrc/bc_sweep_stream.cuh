@@ -1,0 +1,427 @@
+// bc_sweep_stream.cuh -- the streaming kernel (L % 32 == 0), its group launch for several lattice sizes and the experimental persistent variant.
+// Part of the sm_100a Blume-Capel engine; included through bc_kernels.cuh.
+#pragma once
+#include "bc_update.cuh"
+
+namespace bc {
+
+// ------------------------------------------------------------------------------------------
+// Fast kernel: L % 32 == 0.  One thread = one 16-byte chunk column j, marching down the
+// L/strips rows of its strip with the three rows of the other colour held in registers and the
+// loads of the NEXT row (other-colour row y+2, side word, own chunk) issued before the current
+// row is computed (software prefetch: the kernel is instruction-bound, so exposed load latency
+// is pure loss).
+// Work item id = blockIdx.x*128 + threadIdx.x -> (replica, strip, j), j fastest, so a warp
+// reads 512 contiguous bytes per row; items/replica is a multiple of 32 (host guarantees),
+// so a warp never spans replicas.
+//   SMALL = false: rows per strip is even (row parity static per unrolled row) and
+//                  items/replica is a multiple of 128 (one replica, one table per CTA).
+//   SMALL = true : any strip height, up to 4 replicas per CTA (small lattices).
+// Per-site compare: table offsets extracted with IDP.4A (FMA-heavy pipe), LDS.U16
+// from a 27-word conflict-free table, two sites per packed 16-bit subtract, reject masks by PRMT sign
+// replication, ties (coarse draw == coarse threshold) by a packed signed minimum (VIMNMX3.S16x2).  The
+// two half-rate integer pipes (ALU: LOP3/PRMT/SHF, FMA-heavy: IMAD/IDP, quarter-rate IMAD.WIDE) bound
+// this kernel, not HBM; the instruction mix is balanced between them (tools/microbench/pipes.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int FAST_THREADS = 128;
+constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
+#ifndef BC_DEEP_PREFETCH
+#define BC_DEEP_PREFETCH 1  // 0: one row ahead everywhere, 1: two rows ahead where it pays (see DEEP), 2: everywhere
+#endif
+#ifndef BC_PAIR_TMA
+#define BC_PAIR_TMA 1  // pair table staged by one cp.async.bulk + mbarrier (0: by cp.async from all threads)
+#endif
+#ifndef BC_FAST_MIN_BLOCKS
+#define BC_FAST_MIN_BLOCKS 6
+#endif
+
+//   HALO  = true : slab boundary-strip launch in peer-memory mode: the thread that produces a chunk of the
+//                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank
+//                  above / below (peer pointers over NVLink): compute and halo transfer are one kernel.
+//   PAIR >= 1    : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
+//                  thresholds of two sites up with one IDP.4A + one LDS.32; pays when a CTA marches over enough
+//                  rows to amortise the staging (host: LaunchPlan::pair).
+//   PAIR == 2    : additionally the software-pipelined Philox draws (plain periodic kernel only; long strips).
+// Software pipelining of the Philox draws (update_chunk16_sp) needs ~8 more registers: it pays for the plain
+// periodic pair-table kernel at 6 CTAs/SM (80 registers: 1778 -> 1813 updates/ns) and loses wherever it spills
+// (72 registers) or drops the measuring / open variants to 5 CTAs/SM.
+template <bool MEASURE, bool OPEN, int PAIR>
+struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; };
+template <bool SMALL, bool MEASURE, bool OPEN, int PAIR>
+struct FastMinBlocks {
+    static constexpr int value =
+        (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+};
+
+// The kernel body; `bid` is the CTA's index among the CTAs that work on P's lattices (blockIdx.x for an ordinary
+// launch, blockIdx.x minus the group's first CTA for a group launch, see sweep_group_kernel).
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO, int PAIR>
+__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid, const int64_t t_add = 0) {
+    static_assert(!(PAIR && SMALL) && !(PAIR && HALO), "the pair table is one replica per CTA; HALO kernels use the per-site table");
+    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
+    __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
+    __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
+    // DEEP: inputs are requested two rows ahead instead of one (the row above is then carried in registers and
+    // the ring holds rows y, y+1 and the two rows in flight).  Measured (tools/tune_libs2.sh): +1..3 % for the
+    // periodic pair-table kernels at 8..16 rows per thread, -1 % for the pipelined kernel, -2 % with open edges.
+    constexpr bool DEEP = BC_DEEP_PREFETCH == 2 || (BC_DEEP_PREFETCH == 1 && PAIR == 1 && !OPEN);
+    __shared__ uint4 s_own[DEEP ? 4 : 2][FAST_THREADS];     // thread-private own chunks (current / next rows)
+    __shared__ uint32_t s_side[DEEP ? 4 : 2][FAST_THREADS];  // thread-private side words
+
+    // Programmatic dependent launch: let the next half-sweep's grid be scheduled as soon as SMs free up; its
+    // CTAs run their prologue (table staging, index arithmetic) and then block in griddepcontrol.wait until
+    // this grid has completed and its writes are visible.  Both are no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const uint32_t ipr = (uint32_t)(P.strips * P.cpr);  // items per replica
+    const unsigned long long gid0 = (unsigned long long)bid * FAST_THREADS;
+    const uint32_t rep0 = (uint32_t)(gid0 / ipr);
+    for (int i = threadIdx.x; i < (SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS; i += FAST_THREADS) {
+        const uint32_t r = rep0 + i / TAB16_WORDS;
+        s_tab[i] = (r < (uint32_t)P.n_replicas)
+                       ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
+                       : 0u;
+    }
+#if BC_PAIR_TMA
+    // Pair table by ONE bulk copy (TMA engine, UBLKCP): thread 0 arms an mbarrier with the byte count and issues the
+    // copy; it completes in the background while the CTA computes its indices, waits for the previous grid and
+    // requests its first rows -- every thread waits on the mbarrier just before the first lookup.  (The tables are
+    // written by bc_set_params, never by a sweep: safe before griddepcontrol.wait.)
+    __shared__ __align__(8) unsigned long long s_mbar;
+    if (PAIR && threadIdx.x == 0) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar), dst = (uint32_t)__cvta_generic_to_shared(s_tab2);
+        const uint32_t* src = P.tab2 + (size_t)rep0 * TAB2_WORDS;
+        constexpr uint32_t bytes = TAB2_WORDS * 4;
+        static_assert(bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+#else
+    if (PAIR) {  // the tables are written by bc_set_params, never by a sweep: safe before griddepcontrol.wait
+        const uint4* src = reinterpret_cast<const uint4*>(P.tab2 + (size_t)rep0 * TAB2_WORDS);
+        for (int i = threadIdx.x; i < TAB2_WORDS / 4; i += FAST_THREADS) cp_async16(&s_tab2[4 * i], src + i);
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+#endif
+    __syncthreads();
+
+    uint32_t rep, rem;
+    if (SMALL) {
+        const unsigned long long gid = gid0 + threadIdx.x;
+        rep = (uint32_t)(gid / ipr);
+        if (rep >= (uint32_t)P.n_replicas) return;  // whole warps only (ipr % 32 == 0)
+        rem = (uint32_t)(gid - (unsigned long long)rep * ipr);
+    } else {
+        rep = rep0;  // ipr % 128 == 0: the CTA lies inside one replica
+        rem = (uint32_t)(gid0 - (unsigned long long)rep0 * ipr) + threadIdx.x;
+    }
+    const uint32_t strip = rem / (uint32_t)P.cpr;
+    const uint32_t j = rem - strip * (uint32_t)P.cpr;
+    const uint32_t rows = (uint32_t)P.rows_per_strip;
+    const uint32_t y0 = (uint32_t)P.row_first + ((uint32_t)P.strip_base + strip * (uint32_t)P.strip_stride) * rows;  // array row
+    const uint32_t yg0 = y0 + (uint32_t)P.y_rng_off;
+    const uint32_t Wc = (uint32_t)P.Wc;
+    constexpr bool open = OPEN;
+
+    int64_t t = P.t + t_add;
+    if (P.t_ptr) t += *P.t_ptr;
+    const uint32_t k0 = P.key0, k1 = P.key1 ^ rep;
+    const uint32_t ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
+    const uint32_t ctr3 = ctr3_of(t, STREAM_COARSE, COL);
+
+    // shared-memory table of this thread's replica: uniform for !SMALL
+    const char* tab = reinterpret_cast<const char*>(s_tab) + (SMALL ? (rep - rep0) * (TAB16_WORDS * 4) : 0u);
+    const size_t rep_base = (size_t)rep * (size_t)P.rows_arr * (size_t)Wc;
+    uint8_t* own_col = P.own + rep_base + (size_t)j * 16;            // + y*Wc
+    const uint8_t* oth_col = P.other + rep_base + (size_t)j * 16;    // + y*Wc
+    const uint8_t* oth_rep = P.other + rep_base;
+    const uint32_t jr = (j + 1 == (uint32_t)P.cpr) ? 0u : j + 1;     // chunk holding k+1 of our last site
+    const uint32_t jl = (j == 0) ? (uint32_t)P.cpr - 1 : j - 1;      // chunk holding k-1 of our first site
+    const uint32_t side_r = jr * 16, side_l = jl * 16 + 12;          // byte offsets inside a row
+    const bool edge_r = open && (j + 1 == (uint32_t)P.cpr), edge_l = open && (j == 0);
+
+    const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
+    const uint32_t total = (uint32_t)P.rows_arr * Wc;  // bytes of one replica's colour array (< 2^32)
+
+    uint32_t a_c = 0, a_c2 = 0, a_cS = 0, a_S = 0, n_ties = 0;
+
+    // The 18*(f+1) term of the table offset is computed with f+1 instead of f: bias the base by -18.
+    const char* tabm = tab - 18;
+
+    RowCtx ctx;
+    ctx.j = j; ctx.ctr2 = ctr2; ctx.ctr3 = ctr3; ctx.k0 = k0; ctx.k1 = k1; ctx.t = t; ctx.tabm = tabm;
+    ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
+    ctx.tab2s = PAIR ? (uint32_t)__cvta_generic_to_shared(s_tab2) - TAB2_BIAS : 0u;
+    constexpr bool SWP = FastSwp<MEASURE, OPEN, PAIR>::value;
+    uint32_t qn[4];
+    if (SWP) coarse_draw(ctx, yg0, 0u, qn);
+    auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
+                          const uint4& dnv, const uint32_t side, const uint4& ownv) {
+        if (SWP) {
+            *reinterpret_cast<uint4*>(own_col + off) = update_chunk16_sp<COL, MEASURE, (PAIR > 0)>(
+                ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, n_ties);
+        } else if (!HALO) {
+            *reinterpret_cast<uint4*>(own_col + off) =
+                update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+        } else {
+            const uint4 nv = update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+            *reinterpret_cast<uint4*>(own_col + off) = nv;
+            // fused halo transfer: first owned row -> bottom ghost row of the rank above, last owned row -> top
+            // ghost row of the rank below (same array geometry on every rank)
+            if (P.peer_prev && off == (uint32_t)P.row_first * Wc)
+                *reinterpret_cast<uint4*>(P.peer_prev + rep_base + (size_t)(P.Ly + 1) * Wc + (size_t)j * 16) = nv;
+            if (P.peer_next && off == (uint32_t)(P.row_first + P.Ly - 1) * Wc)
+                *reinterpret_cast<uint4*>(P.peer_next + rep_base + (size_t)j * 16) = nv;
+        }
+    };
+
+    // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour
+    // ---- rows, two own chunks, two side words) filled by cp.async one row ahead: the inputs of row
+    // ---- y+1 are in flight while row y is computed, and they cost no registers while in flight.
+    const uint32_t tid = threadIdx.x;
+    auto stage_other = [&](const int slot, uint32_t o) {  // other-colour row at byte offset o (== total: wrap/open)
+        if (o == total) {
+            if (open) { s_rows[slot][tid] = ones4; return; }
+            o = 0;
+        }
+        cp_async16(&s_rows[slot][tid], oth_col + o);
+    };
+    auto stage_row_inputs = [&](const int slot2, const uint32_t off_row, const int par) {  // own chunk + side word
+        cp_async16(&s_own[slot2][tid], own_col + off_row);
+        if (par) {
+            if (edge_r) s_side[slot2][tid] = 0x00000001u; else cp_async4(&s_side[slot2][tid], oth_rep + off_row + side_r);
+        } else {
+            if (edge_l) s_side[slot2][tid] = 0x01000000u; else cp_async4(&s_side[slot2][tid], oth_rep + off_row + side_l);
+        }
+    };
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous half-sweep (other colour) is complete
+    uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
+#if BC_PAIR_TMA
+    auto wait_pair_table = [&]() {  // phase 0 of the mbarrier: the body runs once per CTA in the PAIR kernels
+        if (PAIR) {
+            const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "PAIR_TABLE_WAIT:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                "@p bra PAIR_TABLE_READY;\n"
+                "bra PAIR_TABLE_WAIT;\n"
+                "PAIR_TABLE_READY:\n"
+                "}\n" ::"r"(mb) : "memory");
+        }
+    };
+#else
+    auto wait_pair_table = [&]() {};
+#endif
+    if (!DEEP) {
+        if (y0 == 0) { if (open) s_rows[0][tid] = ones4; else cp_async16(&s_rows[0][tid], oth_col + (total - Wc)); }
+        else cp_async16(&s_rows[0][tid], oth_col + (off - Wc));
+        cp_async16(&s_rows[1][tid], oth_col + off);
+        stage_other(2, off + Wc);
+        stage_row_inputs(0, off, (int)((yg0 + COL) & 1u));
+        cp_async_commit();
+        wait_pair_table();
+
+        // row r of the strip: ring slots up = r&3, mid = (r+1)&3, dn = (r+2)&3, next = (r+3)&3
+        auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
+            if (!last) {
+                stage_other((sl + 3) & 3, off + 2 * Wc);
+                stage_row_inputs((sl + 1) & 1, off + Wc, 1 - par);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();  // everything but the group just committed has landed: row r is ready
+            const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
+            const uint4 ownv = s_own[sl & 1][tid];
+            const uint32_t side = s_side[sl & 1][tid];
+            update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
+            off += Wc;
+        };
+
+        if (SMALL || (rows & 3u)) {
+            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
+        } else {
+            // yg0 is even and rows is a multiple of 4: parities alternate COL, 1-COL statically; static ring slots
+            for (uint32_t r = 0; r < rows; r += 4) {
+                march(r, COL, false, 0);
+                march(r + 1, 1 - COL, false, 1);
+                march(r + 2, COL, false, 2);
+                march(r + 3, 1 - COL, r + 4 == rows, 3);
+            }
+        }
+    } else {
+        // Strip row r lives in ring slot r&3 (other colour) and r&3 (own chunk, side word).  Group G_r, committed at
+        // the top of row r, holds other row r+3 and the own chunk / side word of row r+2; row r needs G_{r-2}, so
+        // two groups stay in flight (wait_group 2).  Row r-1 of the other colour is carried in registers.
+        const int par0 = (int)((yg0 + COL) & 1u);
+        uint4 upv;
+        if (y0 == 0) upv = open ? ones4 : __ldcg(reinterpret_cast<const uint4*>(oth_col + (total - Wc)));
+        else upv = __ldcg(reinterpret_cast<const uint4*>(oth_col + (off - Wc)));
+        cp_async16(&s_rows[0][tid], oth_col + off);
+        stage_other(1, off + Wc);
+        stage_row_inputs(0, off, par0);
+        cp_async_commit();  // G_{-2}
+        if (rows > 1) {
+            stage_other(2, off + 2 * Wc);
+            stage_row_inputs(1, off + Wc, 1 - par0);
+        }
+        cp_async_commit();  // G_{-1}
+        wait_pair_table();
+
+        auto march = [&](const uint32_t r, const int par, const bool more, const int sl) {
+            if (more) {  // row r+2 exists (same parity as row r)
+                stage_other((sl + 3) & 3, off + 3 * Wc);
+                stage_row_inputs((sl + 2) & 3, off + 2 * Wc, par);
+            }
+            cp_async_commit();
+            cp_async_wait<2>();
+            const uint4 midv = s_rows[sl & 3][tid], dnv = s_rows[(sl + 1) & 3][tid];
+            const uint4 ownv = s_own[sl & 3][tid];
+            const uint32_t side = s_side[sl & 3][tid];
+            update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
+            upv = midv;
+            off += Wc;
+        };
+
+        if (SMALL || (rows & 3u)) {
+            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 3 <= rows, (int)(r & 3u));
+        } else {
+            for (uint32_t r = 0; r < rows; r += 4) {
+                const bool more = r + 4 != rows;
+                march(r, COL, true, 0);
+                march(r + 1, 1 - COL, true, 1);
+                march(r + 2, COL, more, 2);
+                march(r + 3, 1 - COL, more, 3);
+            }
+        }
+    }
+
+    if (MEASURE && P.obs) {
+        int64_t slot = P.slot;
+        if (P.slot_ptr) slot += *P.slot_ptr;
+        unsigned long long* dst = P.obs + ((size_t)slot * P.n_replicas + rep) * OBS_RAW;
+        const uint32_t s_c = warp_sum(a_c), s_c2 = warp_sum(a_c2);
+        const uint32_t s_cS = (COL == 1) ? warp_sum(a_cS) : 0u, s_S = (COL == 1) ? warp_sum(a_S) : 0u;
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(dst + 2 * COL + 0, (unsigned long long)s_c);
+            atomicAdd(dst + 2 * COL + 1, (unsigned long long)s_c2);
+            if (COL == 1) {
+                atomicAdd(dst + 4, (unsigned long long)s_cS);
+                atomicAdd(dst + 5, (unsigned long long)s_S);
+            }
+        }
+    }
+    if (n_ties && P.ties) atomicAdd(P.ties, (unsigned long long)n_ties);
+}
+
+template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, int PAIR = 0>
+__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR>::value)
+sweep_fast_kernel(const __grid_constant__ SweepParams P) {
+    sweep_fast_body<COL, SMALL, MEASURE, OPEN, HALO, PAIR>(P, blockIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Group launch: ONE grid updates the lattices of up to GROUP_MAX engine handles of different sizes (a
+// finite-size-scaling ladder, config 3; the open-boundary size series, config 5).  Each handle keeps its own
+// geometry, tables, Philox key, sweep counter and observable slots (its SweepParams); the CTAs are dealt out
+// handle after handle and a CTA finds its handle by comparing blockIdx.x with the prefix sums.  Per-handle
+// launches of small lattices are launch-latency-bound and, on separate streams, queue behind the big
+// lattice's CTAs; one grid has one tail.  Same body, same results as sweep_fast_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int GROUP_MAX = 8;
+struct GroupParams {
+    SweepParams p[GROUP_MAX];
+    unsigned cta_end[GROUP_MAX];  // exclusive prefix end of each handle's CTAs
+    int n;
+};
+
+template <int COL, bool MEASURE, bool OPEN, int PAIR>
+__global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
+sweep_group_kernel(const __grid_constant__ GroupParams G) {
+    int g = 0;
+#pragma unroll
+    for (int i = 0; i < GROUP_MAX - 1; ++i)
+        if (i + 1 < G.n && blockIdx.x >= G.cta_end[i]) g = i + 1;
+    const unsigned first = g ? G.cta_end[g - 1] : 0u;
+    sweep_fast_body<COL, false, MEASURE, OPEN, false, PAIR>(G.p[g], blockIdx.x - first);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent kernel -- experimental, off by default (a measured negative result): ALL half-sweeps of a
+// run of unmeasured sweeps in ONE cooperative launch, with a grid-wide barrier between half-sweeps instead of a
+// kernel boundary.  The idea: for lattices that do not fill the chip for long (one L = 4096 lattice is 4.3 us of
+// work per half-sweep) the floor of a dependent launch -- about 3 us even from a CUDA graph with programmatic
+// dependent launch -- is most of the time.  The measurement: a software barrier is four serialised L2 round trips
+// (the stores' fence, the arrival atomic, the poll that sees the release, the first loads after it), and nothing
+// overlaps them, while programmatic dependent launch runs the next grid's prologue under the previous grid's tail:
+// one L = 4096 lattice 761 vs 1090 updates/ns, L = 2048 358 vs 588 (profiles/r01_tune_persist.log).
+// The grid is exactly the number of CTAs that are resident at once (cooperative launch: co-residency is
+// guaranteed or the launch fails); a CTA takes the 128-item work blocks b = blockIdx.x, blockIdx.x + gridDim.x, ...
+// of every half-sweep and runs the streaming kernel's body on them (same results).  Handles several lattice sizes
+// like sweep_group_kernel (n = 1: a single handle).  The barrier: a monotonically increasing arrival counter (the
+// g-th barrier is complete at count g * gridDim.x), the last arriver publishes the generation with a release
+// store, the others poll it with acquire loads (which also drop stale L1 lines before the next half-sweep reads
+// its neighbours); the wait is bounded (~2 s) and raises bar[2] instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+struct PersistParams {
+    GroupParams g[2];   // members' parameters for the colour-0 and the colour-1 half-sweep (own / other swapped)
+    unsigned* bar;      // [0] arrivals, [1] generation, [2] abort; zeroed by the host before the launch
+    int n_half;         // half-sweeps to run, starting with colour 0 of the members' sweep counters
+};
+
+__device__ __forceinline__ bool persist_barrier(unsigned* bar, const unsigned gen) {
+    __shared__ int s_abort;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int give_up = 0;
+        __threadfence();
+        const unsigned arrived = atomicAdd(&bar[0], 1u) + 1u;
+        if (arrived == gen * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
+        } else {
+            const long long c0 = clock64();
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1) : "memory");
+                if (v < gen && clock64() - c0 > 4000000000LL) { atomicExch(&bar[2], 1u); give_up = 1; break; }
+            } while (v < gen);
+        }
+        if (*reinterpret_cast<volatile unsigned*>(bar + 2)) give_up = 1;
+        __threadfence();
+        s_abort = give_up;
+    }
+    __syncthreads();
+    return s_abort == 0;
+}
+
+#ifndef BC_PERSIST_MIN_BLOCKS
+#define BC_PERSIST_MIN_BLOCKS 7
+#endif
+template <bool OPEN>
+__global__ void __launch_bounds__(FAST_THREADS, BC_PERSIST_MIN_BLOCKS)
+sweep_persist_kernel(const __grid_constant__ PersistParams P) {
+    const int n = P.g[0].n;
+    const unsigned n_blocks = P.g[0].cta_end[n - 1];
+    for (int h = 0; h < P.n_half; ++h) {
+        const GroupParams& G = P.g[h & 1];
+        for (unsigned b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+            int g = 0;
+#pragma unroll
+            for (int i = 0; i < GROUP_MAX - 1; ++i)
+                if (i + 1 < n && b >= G.cta_end[i]) g = i + 1;
+            const unsigned first = g ? G.cta_end[g - 1] : 0u;
+            if (h & 1) sweep_fast_body<1, false, false, OPEN, false, 0>(G.p[g], b - first, (int64_t)(h >> 1));
+            else sweep_fast_body<0, false, false, OPEN, false, 0>(G.p[g], b - first, (int64_t)(h >> 1));
+            __syncthreads();  // the table and the staging slots are reused by the next block
+        }
+        if (h + 1 < P.n_half && !persist_barrier(P.bar, (unsigned)(h + 1))) return;
+    }
+}
+
+}  // namespace bc
