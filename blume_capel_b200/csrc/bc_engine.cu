@@ -954,6 +954,7 @@ static void fill_group_plan(bc_engine* const* es, int n, int target, GroupPlan* 
         p.fast = true; p.small = false; p.pair = 0;
         p.cpr = e->L / 32;
         p.rows = group_best_rows(e, target);
+        if (!p.rows) p.rows = group_best_rows(e, 32);
         p.strips = e->Ly / p.rows;
         p.grid = (unsigned)(((long long)e->n_rep * p.strips * p.cpr) / FAST_THREADS);
         ctas += p.grid;
@@ -1299,7 +1300,7 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
         for (int cand = 32; cand >= 2; cand >>= 1) {
             long long threads = 0;
             for (int g = 0; g < n_engines; ++g) {
-                const int R = group_best_rows(engines[g], cand);
+                const int R = group_best_rows(engines[g], cand);  // > 0: 2 rows are valid (checked above) and cand is 2^k
                 threads += (long long)engines[g]->n_rep * (engines[g]->Ly / R) * (engines[g]->L / 32);
             }
             target = cand;
@@ -1315,6 +1316,7 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
         p.fast = true; p.small = false;
         p.cpr = e->L / 32;
         p.rows = group_best_rows(e, target);
+        if (!p.rows) p.rows = group_best_rows(e, 32);  // a "rows_per_thread" that fits no strip of this member
         p.strips = e->Ly / p.rows;
         p.grid = (unsigned)(((long long)e->n_rep * p.strips * p.cpr) / FAST_THREADS);
         ctas += p.grid;

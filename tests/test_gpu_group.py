@@ -22,7 +22,8 @@ def make(bc, sizes, boundary, seed0, reps):
 @pytest.mark.parametrize("sizes,reps,rows", [((128, 256, 512, 1024), (3, 2, 5, 1), 0),   # auto: short strips, per-site table
                                              ((128, 256, 512, 1024), (3, 2, 5, 1), 8),   # L = 128 caps at 4 rows
                                              ((256, 512, 1024), (2, 5, 1), 8),           # pair-table kernels
-                                             ((256, 2048), (9, 2), 16)])
+                                             ((256, 2048), (9, 2), 16),
+                                             ((256, 512), (2, 2), 6)])                    # fits no strip: falls back
 def test_group_equals_individual_sweeps(bc, boundary, sizes, reps, rows):
     a = make(bc, sizes, boundary, 100, reps)
     b = make(bc, sizes, boundary, 100, reps)
