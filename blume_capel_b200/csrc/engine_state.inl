@@ -1,0 +1,128 @@
+// engine_state.inl -- lattice state: initialisation, uploads / downloads in the reference layout, sweep counter.
+// Part of bc_engine.cu (included there once; not a stand-alone translation unit).
+
+// ---------------------------------------------------------------------------------------------
+// lattice state
+// ---------------------------------------------------------------------------------------------
+static int ensure_stage(bc_engine* e, size_t bytes) {
+    if (e->stage_cap >= bytes) return BC_OK;
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->d_stage) BC_CUDA(e, cudaFree(e->d_stage));
+    e->d_stage = nullptr; e->stage_cap = 0;
+    BC_CUDA(e, cudaMalloc(&e->d_stage, bytes));
+    e->stage_cap = bytes;
+    return BC_OK;
+}
+
+extern "C" int bc_init_random(bc_engine* e, int replica) {
+    if (!e) return BC_ERR_ARG;
+    if (replica < -1 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_init_random: replica out of range");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const int r0 = replica < 0 ? 0 : replica, n = replica < 0 ? e->n_rep : 1;
+    const long long total = (long long)n * e->Ly * e->L;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], geom_of(e), r0, n, (uint32_t)e->seed,
+                                               (uint32_t)(e->seed >> 32));
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return exchange_both(e);
+}
+
+// 16-byte conversion kernels: rows 16-byte aligned on both sides, one grid row per replica
+static bool vector_layout(const bc_engine* e, int n) {
+    return e->L % 32 == 0 && e->Wc == e->L / 2 && n <= 65535 && (long long)e->Ly * (e->L / 32) < (1LL << 31);
+}
+
+// reference layout (row-major int8 in d_stage, replicas r0 .. r0+n-1 at the start of the buffer) <-> compact colour arrays
+static int stage_to_device(bc_engine* e, int r0, int n) {
+    if (vector_layout(e, n)) {
+        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
+        pack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
+    } else {
+        const long long total = (long long)n * e->Ly * e->Wc;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        pack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    }
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int stage_from_device(bc_engine* e, int r0, int n) {
+    if (vector_layout(e, n)) {
+        const dim3 grid((unsigned)(((long long)e->Ly * (e->L / 32) + 255) / 256), (unsigned)n);
+        unpack16_kernel<<<grid, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0);
+    } else {
+        const long long total = (long long)n * e->Ly * e->L;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->d_stage, e->d_c[0], e->d_c[1], geom_of(e), r0, n);
+    }
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool wait = true) {
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * e->Ly * e->L;
+    int rc = ensure_stage(e, bytes);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
+    rc = stage_to_device(e, r0, n);
+    if (rc != BC_OK) return rc;
+    rc = exchange_both(e);
+    if (rc != BC_OK) return rc;
+    if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));  // the caller may reuse `spins` on return
+    return BC_OK;
+}
+
+static int download_range(bc_engine* e, int r0, int n, int8_t* spins, bool wait = true) {
+    BC_CUDA(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)n * e->Ly * e->L;
+    int rc = ensure_stage(e, bytes);
+    if (rc != BC_OK) return rc;
+    rc = stage_from_device(e, r0, n);
+    if (rc != BC_OK) return rc;
+    BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    return BC_OK;
+}
+
+extern "C" int bc_upload(bc_engine* e, int replica, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_upload: replica out of range");
+    return upload_range(e, replica, 1, spins);
+}
+extern "C" int bc_download(bc_engine* e, int replica, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_download: replica out of range");
+    return download_range(e, replica, 1, spins);
+}
+extern "C" int bc_upload_all(bc_engine* e, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return upload_range(e, 0, e->n_rep, spins);
+}
+extern "C" int bc_download_all(bc_engine* e, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return download_range(e, 0, e->n_rep, spins);
+}
+
+extern "C" int bc_upload_all_async(bc_engine* e, const int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return upload_range(e, 0, e->n_rep, spins, false);
+}
+extern "C" int bc_download_all_async(bc_engine* e, int8_t* spins) {
+    if (!e || !spins) return BC_ERR_ARG;
+    return download_range(e, 0, e->n_rep, spins, false);
+}
+
+extern "C" int bc_get_sweep_counter(const bc_engine* e, int64_t* t) {
+    if (!e || !t) return BC_ERR_ARG;
+    *t = e->t;
+    return BC_OK;
+}
+extern "C" int bc_set_sweep_counter(bc_engine* e, int64_t t) {
+    if (!e || t < 0) return BC_ERR_ARG;
+    e->t = t;
+    return BC_OK;
+}
