@@ -128,6 +128,21 @@ def cpu_model():
     return "unknown"
 
 
+def loop_only_sample(n_threads, attempts=30_000_000):
+    """the Metropolis attempt loop alone (main.cpp:89-112 / the inner loop of step(),
+    main.cpp:159-161), without Wolff clusters and without the mt19937 refills -- the oracle's literal port of that
+    function (bc_oracle_reference_metropolis; the reference has no way to time it without editing main.cpp), one
+    independent L = 64 lattice per thread.  Returns (attempts, wall seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    lats = [np.ones((64, 64), np.int32) for _ in range(n_threads)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=n_threads) as ex:  # ctypes releases the GIL
+        list(ex.map(lambda i: oracle.reference_metropolis(lats[i], T, D, J, attempts, 1 + i), range(n_threads)))
+    return n_threads * attempts, time.perf_counter() - t0
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -141,15 +156,35 @@ def run_reference_arm(args, rank, world):
         attempts += a
         wall += w
     value = attempts / wall / 1e9
+    # the nominal L = 64 run (config 1: 36 864 step() calls per sample, about two minutes per
+    # process) once, one process per core, and the attempt loop in isolation
+    extra = {}
+    if not args.no_l64:
+        try:
+            a64, w64, k64, s64 = reference_sample(cores, 64, 1)
+            extra["l64_nominal"] = {"value": a64 / w64 / 1e9, "unit": "spin-updates/ns", "cores": cores, "kind": k64,
+                                    "wall_s": w64, "sample": s64}
+        except Exception as ex:
+            extra["l64_nominal"] = {"error": str(ex)}
+    try:
+        al, wl = loop_only_sample(cores)
+        extra["loop_only"] = {"value": al / wl / 1e9, "per_core": al / wl / 1e9 / cores, "unit": "spin-updates/ns",
+                              "cores": cores, "kind": "port", "wall_s": wl,
+                              "sample": f"{cores} threads x 3e7 attempts of oracle bc_oracle_reference_metropolis (literal "
+                                        "main.cpp:89-112, L=64): Metropolis attempts only, no Wolff, no RNG refill"}
+    except Exception as ex:
+        extra["loop_only"] = {"error": str(ex)}
     line = {
         "impl": "reference", "metric": "spin-updates/ns", "value": value, "unit": "spin-updates/ns",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "spin-updates/ns", "cores": cores, "kind": kind, "sample": sample,
-                         "cpu_model": cpu_model()},
+                         "cpu_model": cpu_model(), **extra},
         "e2e": {"value": value, "unit": "spin-updates/ns", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference cannot be built for L >= 512 (main.cpp:57-59); its per-attempt rate is size independent",
+        "note": "reference cannot be built for L >= 512 (main.cpp:57-59); its per-attempt rate is size independent; "
+                "value = whole-program rate at L=32 (i), cpu_baseline.l64_nominal = the same at L=64, "
+                "cpu_baseline.loop_only = attempt loop alone (ii)",
     }
     emit(line)
 
@@ -216,6 +251,115 @@ def other_configs(bc, device):
     out["cluster_move"] = {"workload": f"bc_cluster_update on one L={L} lattice (Swendsen-Wang on the +-1 spins)",
                            "ms_per_update": dt * 1e3, "sites_per_ns": L * L / (dt * 1e9)}
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 4: one L = 65536 lattice (4 GiB int8) split into row slabs over the ranks
+# ---------------------------------------------------------------------------------------------
+SLAB_L = 65536
+SLAB_SEED = 0x5EED0004
+SLAB_WARMUP = 5
+SLAB_SWEEPS = 100
+
+
+def slab_golden():
+    p = os.path.join(ROOT, "tests", "golden", f"slab_L{SLAB_L}.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+def slab_record(bc, torch, dist, rank, world, local_rank, L=SLAB_L, sweeps=SLAB_SWEEPS):
+    """Config 4 through bc_create_slab: halo exchange per half-sweep by NCCL send/recv and by peer stores fused into
+    the sweep kernel, next to the same lattice on ONE GPU (rank 0, same invocation).  (M, Q, B) after 2 sweeps is
+    compared with the CPU oracle's golden triple (tests/golden/make_slab_golden.py), after all sweeps with the
+    one-GPU run and with the committed one-GPU golden.  A failure fails this record, never the bench line."""
+    peak, _ = measured_peak()
+    gold = slab_golden()
+    total_sweeps = 2 + SLAB_WARMUP + sweeps
+    rec = {"workload": f"L={L} periodic int8 (one lattice, {L * L / 2**30:.0f} GiB), {world} row slabs of {L // world} rows, "
+                       f"2 + {SLAB_WARMUP} warm-up + {sweeps} timed sweeps, halo exchange per half-sweep",
+           "L": L, "sweeps": sweeps, "seed": SLAB_SEED, "golden_file": f"tests/golden/slab_L{L}.json"}
+
+    def run(n_ranks, r, nid, transport):
+        e = bc.Engine(L, bc.PERIODIC, 1, local_rank, SLAB_SEED, slab=(n_ranks, r, nid))
+        try:
+            if transport == "peer_store" and n_ranks > 1:
+                mine = torch.frombuffer(bytearray(e.ipc_export()), dtype=torch.uint8).cuda()
+                allb = [torch.empty_like(mine) for _ in range(n_ranks)]
+                dist.all_gather(allb, mine)
+                blobs = [bytes(t.cpu().numpy().tobytes()) for t in allb]
+                e.ipc_connect(blobs[(r - 1) % n_ranks], blobs[(r + 1) % n_ranks])
+                dist.barrier()
+            elif transport == "peer_store":
+                e.ipc_connect(None, None)  # one slab is its own ring neighbour: same kernels, no NVLink
+            e.set_params(T, D, J)
+            e.init_random()
+            e.sweep(2)
+            early = e.measure()[0]
+            e.sweep(SLAB_WARMUP)
+            e.sync()
+            if n_ranks > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            l0 = e.launch_count
+            e.timer_start()
+            e.sweep(sweeps)
+            ms = e.timer_stop()
+            launches = e.launch_count - l0
+            final = e.measure()[0]
+            e.sync()
+            plan = e.plan()
+        finally:
+            e.close()
+        if n_ranks > 1:
+            t_ms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            ms = t_ms.item()
+        ups = float(L) * L * sweeps / (ms * 1e6)
+        return {"ms": ms, "updates_per_ns": ups, "updates_per_ns_per_gpu": ups / n_ranks,
+                "hbm_frac_per_gpu": ups / n_ranks * ALGO_BYTES_PER_UPDATE / peak, "gpu_launches_per_rank": int(launches),
+                "plan": plan, "obs_after_2": [int(early[f]) for f in ("M", "Q", "B")],
+                "obs_final": [int(final[f]) for f in ("M", "Q", "B")]}
+
+    # the same lattice on one GPU (rank 0 only; the other ranks wait at the barrier)
+    single = None
+    if rank == 0:
+        try:
+            single = run(1, 0, None, "peer_store")
+        except Exception as ex:
+            single = {"error": str(ex)}
+    dist.barrier()
+    rec["single_gpu"] = single
+    nid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    for transport in ("nccl", "peer_store"):
+        try:
+            if rank == 0:
+                nid.copy_(torch.frombuffer(bytearray(bc.slab_unique_id()), dtype=torch.uint8))
+            dist.broadcast(nid, 0)
+            out = run(world, rank, bytes(nid.cpu().numpy().tobytes()), transport)
+        except Exception as ex:
+            out = {"error": str(ex)}
+        if rank == 0 and "error" not in out:
+            if single and "error" not in single:
+                out["efficiency_vs_1gpu"] = out["updates_per_ns"] / (world * single["updates_per_ns"])
+                out["equals_single_gpu"] = out["obs_final"] == single["obs_final"] and out["obs_after_2"] == single["obs_after_2"]
+            g2 = gold.get("after", {}).get("2")
+            out["equals_oracle_after_2"] = (out["obs_after_2"] == g2) if g2 else None
+            gf = gold.get("gpu_n1", {}).get(str(total_sweeps))
+            out["equals_committed_golden"] = (out["obs_final"] == gf) if gf else None
+            checks = [out.get("equals_single_gpu"), out["equals_oracle_after_2"], out["equals_committed_golden"]]
+            out["ok"] = all(c is not False for c in checks) and any(c for c in checks)
+        rec[transport] = out
+    if rank == 0 and single and "error" not in single:
+        g2 = gold.get("after", {}).get("2")
+        single["equals_oracle_after_2"] = (single["obs_after_2"] == g2) if g2 else None
+        gf = gold.get("gpu_n1", {}).get(str(total_sweeps))
+        single["equals_committed_golden"] = (single["obs_final"] == gf) if gf else None
+    rec["golden"] = {"oracle_after_2": gold.get("after", {}).get("2"),
+                     "gpu_n1_final": gold.get("gpu_n1", {}).get(str(total_sweeps)), "total_sweeps": total_sweeps}
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------
@@ -343,6 +487,17 @@ def run_ours(args, rank, world, local_rank):
     h2d_bytes = sum(h.nbytes for h in hosts[0])
     d2h_bytes = h2d_bytes + obs_buf.nbytes * split
 
+    for row in engs:  # free the end-to-end handles before the 4 GiB slab lattice is created
+        for e_k in row:
+            e_k.close()
+    engs = []
+    slab = None
+    if dist is not None and not args.no_slab:
+        try:
+            slab = slab_record(bc, torch, dist, rank, world, local_rank)
+        except Exception as ex:  # the record fails, the line does not
+            slab = {"error": str(ex)}
+
     ms_t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -359,11 +514,16 @@ def run_ours(args, rank, world, local_rank):
         bytes_per_launch = 1.5 * L * L * N_REPLICAS
         avg_launch_ms = ms / max(launches, 1)
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM bytes per launch from the tracked ncu --set full capture of this workload: a STORED number (a profiler
+        # cannot run inside the timed region), labelled as such in traffic_source
+        traffic = traffic_src = None
         prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                pj = json.load(open(prof))
+                traffic = pj.get("dram_bytes_per_launch")
+                traffic_src = (f"stored: profiles/ncu_summary.json ({pj.get('source', 'ncu --set full')}, "
+                               f"kernel {pj.get('kernel', '?')}), not measured in this run")
             except Exception:
                 traffic = None
         # bounded CPU sample of the reference on this box's host cores
@@ -372,6 +532,12 @@ def run_ours(args, rank, world, local_rank):
             a, w, kind, sample = reference_sample(1, 32, 2)
             cpu = {"value": a / w / 1e9, "unit": "spin-updates/ns", "cores": 1, "kind": kind, "sample": sample,
                    "cpu_model": cpu_model(), "host_cores": os.cpu_count()}
+            try:  # (ii) of BASELINE.md 4.3: the attempt loop alone, one thread
+                al, wl = loop_only_sample(1)
+                cpu["loop_only"] = {"value": al / wl / 1e9, "unit": "spin-updates/ns", "cores": 1, "kind": "port",
+                                    "sample": "3e7 attempts of the oracle's literal main.cpp:89-112 loop, L=64"}
+            except Exception as ex:
+                cpu["loop_only"] = {"error": str(ex)}
         N = L * L
         line = {
             "metric": "spin-updates/ns", "value": value, "unit": "spin-updates/ns", "n_gpus": world,
@@ -384,7 +550,7 @@ def run_ours(args, rank, world, local_rank):
                     "handles": n_handles, "sub_batches_per_step": split},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "bc::sweep_fast_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "bc::sweep_fast_kernel",
                          "algorithmic_bytes_per_launch": bytes_per_launch,
                          "avg_launch_ms": avg_launch_ms, "sweep_launches": sweep_launches},
             "cpu_baseline": cpu,
@@ -392,6 +558,7 @@ def run_ours(args, rank, world, local_rank):
             "single_lattice": {"workload": f"one L={L} lattice (16 MiB, L2-resident; CUDA-graph replay + PDL)",
                                "updates_per_ns": single},
             "other_configs": others,
+            "slab": slab,
             "check": {"abs_m_last": float(np.abs(last_obs[-1]["M"]).mean() / N),
                       "q_last": float(last_obs[-1]["Q"].mean() / N), "ties": ties_resident},
         }
@@ -429,6 +596,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l64", action="store_true", help="reference arm: skip the two-minute nominal L=64 run")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the config-4 slab record (L=65536 over the ranks)")
     ap.add_argument("--e2e-handles", type=int, default=3, help="steps in flight in the end-to-end loop")
     ap.add_argument("--e2e-split", type=int, default=4, help="sub-batches (handles) a step's replicas travel as")
     args = ap.parse_args()

@@ -84,6 +84,18 @@ struct SweepParams {
     int Ly;                  // owned rows (== rows_arr unless ghost rows are present)
     uint8_t* peer_prev;      // HALO kernels: the rank above's array of the colour being updated (peer memory);
     uint8_t* peer_next;      //   the rank below's.  nullptr at an open edge.
+    // HALO kernels (peer-memory slabs): the whole half-sweep of a slab is ONE launch whose first CTAs hold the two
+    // boundary strips.  Those CTAs wait for the neighbours' ghost rows (epoch flags), store their fresh first / last
+    // rows into the neighbours' ghost rows, and the last of them to finish publishes the next epoch.
+    const long long* halo_flags;  // this rank's flags: [0] top ghost rows valid through epoch, [1] bottom
+    long long* halo_clock;        // epochs this rank has published so far (== what the neighbours must have published)
+    unsigned* halo_done;          // boundary CTAs of this launch that have finished (reset by the last one)
+    int* halo_err;                // raised when a neighbour did not deliver in time
+    long long* peer_prev_flags;   // the rank above's flags (its [1] is ours to write), nullptr at an open edge
+    long long* peer_next_flags;   // the rank below's flags (its [0] is ours to write)
+    long long halo_timeout_ns;
+    int halo_ctas_per_rep;        // CTAs per replica that hold boundary-strip items (the first ones of the replica)
+    int halo_need;                // bit 0: wait for the top ghost rows, bit 1: for the bottom ghost rows
 };
 
 }  // namespace bc

@@ -85,8 +85,9 @@ struct bc_engine {
     long long* peer_prev_flags = nullptr;
     long long* peer_next_flags = nullptr;
     void* ipc_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    long long halo_epoch = 0;          // exchanges issued so far (identical on every rank)
-    long long halo_waited = 0;         // last epoch a wait was enqueued for
+    long long* d_halo_clock = nullptr; // epochs published so far (device resident: graph-replayed kernels advance it)
+    unsigned* d_halo_done = nullptr;   // boundary CTAs of the running HALO launch that have finished
+    int opt_halo_timeout_ms = 60000;   // bounded wait for a neighbour's halo rows
     cudaStream_t halo_stream = nullptr;  // high-priority side stream for the slab halo exchange
     cudaEvent_t ev_boundary = nullptr, ev_halo = nullptr;
     int opt_overlap = 1;
@@ -114,11 +115,12 @@ struct bc_engine {
     // CUDA-graph replay of blocks of unmeasured sweeps (cuts per-launch CPU cost and launch gaps)
     int64_t* d_clock = nullptr;      // device-resident sweep counter read by graph-captured kernels
     cudaGraphExec_t graph_exec = nullptr;
-    int graph_rows = -1, graph_block = 0;  // plan signature the graph was captured for
+    int graph_rows = -1, graph_block = 0, graph_halo = 0;  // plan signature the graph was captured for
     // bc_sweep_group with this handle as member 0: graph of a block of unmeasured group sweeps + what it was built for
     cudaGraphExec_t group_graph = nullptr;
     std::vector<uint64_t> group_sig;
     cudaEvent_t ev_group = nullptr;  // joins / forks the members' streams around a group sweep
+    bool group_carveout_set = false; // shared-memory carve-out of the group kernels requested on this handle's device
     // persistent kernel (all half-sweeps of an unmeasured run in one cooperative launch)
     int opt_persist = 0;             // 0 never (default: measured slower than graph replay + PDL), 1 whenever possible
     unsigned* d_bar = nullptr;       // [0] arrivals, [1] generation, [2] abort
@@ -159,7 +161,7 @@ struct bc_engine {
     } while (0)
 
 typedef void (*fast_fn)(const SweepParams);
-static void pair_kernels(fast_fn (&out)[10]);
+static void pair_kernels(fast_fn (&out)[20]);
 
 static Geom geom_of(const bc_engine* e) {
     Geom g;
@@ -225,7 +227,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->halo_stream) cudaStreamSynchronize(e->halo_stream);
     for (void* p : e->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
-    cudaFree(e->d_flags); cudaFree(e->d_halo_err);
+    cudaFree(e->d_flags); cudaFree(e->d_halo_err); cudaFree(e->d_halo_clock); cudaFree(e->d_halo_done);
     if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
     if (e->ev_boundary) cudaEventDestroy(e->ev_boundary);
     if (e->ev_halo) cudaEventDestroy(e->ev_halo);
@@ -311,7 +313,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if (L % 32 == 0 && L >= 128 &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
     if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
-        fast_fn pf[10];
+        fast_fn pf[20];
         pair_kernels(pf);
         for (fast_fn f : pf) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -330,6 +332,10 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
         if ((st = cudaMemset(e->d_flags, 0, 2 * sizeof(long long))) != cudaSuccess) return bail("memset", st);
         if ((st = cudaMalloc(&e->d_halo_err, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", st);
         if ((st = cudaMemset(e->d_halo_err, 0, sizeof(int))) != cudaSuccess) return bail("memset", st);
+        if ((st = cudaMalloc(&e->d_halo_clock, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc", st);
+        if ((st = cudaMemset(e->d_halo_clock, 0, sizeof(long long))) != cudaSuccess) return bail("memset", st);
+        if ((st = cudaMalloc(&e->d_halo_done, sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc", st);
+        if ((st = cudaMemset(e->d_halo_done, 0, sizeof(unsigned))) != cudaSuccess) return bail("memset", st);
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if ((st = cudaStreamCreateWithPriority(&e->halo_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("halo stream", st);
@@ -405,17 +411,20 @@ extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, doub
         e->params_set[r] = 1;
         e->h_TJ[(size_t)r * 2] = T; e->h_TJ[(size_t)r * 2 + 1] = J;
     }
-    // synchronous copies: the tables are tiny and the host vectors are temporaries
-    BC_CUDA(e, cudaStreamSynchronize(e->stream));
-    BC_CUDA(e, cudaMemcpy(e->d_tab31 + (size_t)r0 * TABLE_ENTRIES, &e->h_tab31[(size_t)r0 * TABLE_ENTRIES],
-                          (size_t)(r1 - r0) * TABLE_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    BC_CUDA(e, cudaMemcpy(e->d_tab16 + (size_t)r0 * TABLE_ENTRIES, h16.data(),
-                          h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    // Everything on the engine's stream, in order: the two table copies, the pair-table kernel that reads the coarse
+    // table, and (after the final synchronize) whatever sweep comes next.  h16 is a temporary, and a sweep launched
+    // with programmatic stream serialization stages the pair table BEFORE griddepcontrol.wait: that is only safe if
+    // pair_table_kernel has completed and flushed, hence the wait here (not a hot call).
+    BC_CUDA(e, cudaMemcpyAsync(e->d_tab31 + (size_t)r0 * TABLE_ENTRIES, &e->h_tab31[(size_t)r0 * TABLE_ENTRIES],
+                               (size_t)(r1 - r0) * TABLE_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    BC_CUDA(e, cudaMemcpyAsync(e->d_tab16 + (size_t)r0 * TABLE_ENTRIES, h16.data(),
+                               h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
     if (e->d_tab2) {
         const long long words = (long long)(r1 - r0) * TAB2_WORDS;
         pair_table_kernel<<<(unsigned)((words + 255) / 256), 256, 0, e->stream>>>(e->d_tab16, e->d_tab2, r0, r1 - r0);
         BC_CUDA(e, cudaGetLastError());
     }
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
     return BC_OK;
 }
 

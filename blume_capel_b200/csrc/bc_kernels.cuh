@@ -21,7 +21,9 @@
 #include "bc_common.cuh"
 #include "bc_update.cuh"
 #include "bc_sweep_stream.cuh"
-#include "bc_sweep_wave.cuh"
+#ifdef BC_EXPERIMENTAL
+#include "bc_sweep_wave.cuh"  // measured negative result, kept as a record
+#endif
 #include "bc_sweep_resident.cuh"
 #include "bc_sweep_generic.cuh"
 #include "bc_util_kernels.cuh"

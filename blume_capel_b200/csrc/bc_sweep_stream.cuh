@@ -35,9 +35,14 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #define BC_FAST_MIN_BLOCKS 6
 #endif
 
-//   HALO  = true : slab boundary-strip launch in peer-memory mode: the thread that produces a chunk of the
-//                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank
-//                  above / below (peer pointers over NVLink): compute and halo transfer are one kernel.
+//   HALO  = true : half-sweep of a slab in peer-memory mode, ONE launch for the whole slab: the first CTAs of every
+//                  replica hold the two boundary strips (first and last strip of the slab); they wait for the
+//                  neighbours' ghost rows (epoch flags, ld.acquire.sys), the thread that produces a chunk of the
+//                  slab's first / last owned row also stores it into the bottom / top ghost row of the rank above /
+//                  below (peer pointers over NVLink), and the last boundary CTA to finish publishes the next epoch
+//                  in the neighbours' flags (st.release.sys).  The interior strips follow in the same grid and
+//                  overlap the transfer.  Compute, halo transfer and synchronisation are one kernel, so a slab
+//                  half-sweep is graph-replayed and programmatically chained exactly like a plain one.
 //   PAIR >= 1    : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
 //                  thresholds of two sites up with one IDP.4A + one LDS.32; pays when a CTA marches over enough
 //                  rows to amortise the staging (host: LaunchPlan::pair).
@@ -47,17 +52,76 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 // (72 registers) or drops the measuring / open variants to 5 CTAs/SM.
 template <bool MEASURE, bool OPEN, int PAIR>
 struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; };
-template <bool SMALL, bool MEASURE, bool OPEN, int PAIR>
+template <bool SMALL, bool MEASURE, bool OPEN, int PAIR, bool HALO = false>
 struct FastMinBlocks {
     static constexpr int value =
-        (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+        (MEASURE || SMALL || HALO || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
 };
+
+// HALO launches: CTA order inside a replica.  A replica has C = items / 128 CTAs in item order (strip-major); the
+// nb = max(1, cpr / 128) CTAs that hold its first strip and the nb CTAs that hold its last strip are moved to the
+// front of the replica's CTA range (they are scheduled first, so their halo rows travel while the interior is
+// computed).  Returns the item-order CTA index for launch-order index `bid`; *boundary = CTA holds a boundary strip.
+// All uniform-datapath arithmetic on the block index (permuting the strip index per thread instead cost the row loop
+// of the periodic kernels 64 bytes of spills).
+__device__ __forceinline__ unsigned halo_cta_order(const SweepParams& P, const unsigned bid, bool* boundary) {
+    const unsigned cpr = (unsigned)P.cpr, C = (unsigned)P.strips * cpr / FAST_THREADS;
+    const unsigned nb = cpr >= FAST_THREADS ? cpr / FAST_THREADS : 1u;
+    const unsigned nh = 2u * nb < C ? 2u * nb : C;
+    const unsigned rep = bid / C, b = bid - rep * C;
+    *boundary = b < nh;
+    const unsigned item = b < nb ? b : (b < nh ? C - (nh - nb) + (b - nb) : b - (nh - nb));
+    return rep * C + item;
+}
+
+// Epilogue of a HALO launch (see sweep_fast_body): halo transfer and epoch signal of the boundary CTAs.  Everything
+// is recomputed from laundered thread / block ids so that nothing has to stay live across the row loop.
+__device__ __forceinline__ void halo_epilogue(const SweepParams& P) {
+    uint32_t tid, bid0;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(bid0));
+    bool boundary;
+    const unsigned bid = halo_cta_order(P, bid0, &boundary);
+    if (!boundary) return;  // CTA-uniform
+    const uint32_t cpr = (uint32_t)P.cpr, ipr = (uint32_t)P.strips * cpr;
+    const unsigned long long gid0 = (unsigned long long)bid * FAST_THREADS;
+    const uint32_t rep = (uint32_t)(gid0 / ipr);
+    const uint32_t rem = (uint32_t)(gid0 - (unsigned long long)rep * ipr) + tid;
+    const uint32_t s = rem / cpr, j = rem - s * cpr;
+    const uint32_t Wc = (uint32_t)P.Wc;
+    const size_t rep_base = (size_t)rep * (size_t)P.rows_arr * Wc;
+    // Fused halo transfer: the thread that produced a chunk of the slab's first owned row copies it into the bottom
+    // ghost row of the rank above, the one that produced a chunk of the last owned row into the top ghost row of
+    // the rank below (same array geometry on every rank; a thread reads back its own stores).
+    if (P.peer_prev && s == 0u)
+        *reinterpret_cast<uint4*>(P.peer_prev + rep_base + (size_t)(P.Ly + 1) * Wc + (size_t)j * 16) =
+            *reinterpret_cast<const uint4*>(P.own + rep_base + (size_t)P.row_first * Wc + (size_t)j * 16);
+    if (P.peer_next && s == (uint32_t)P.strips - 1u)
+        *reinterpret_cast<uint4*>(P.peer_next + rep_base + (size_t)j * 16) =
+            *reinterpret_cast<const uint4*>(P.own + rep_base + (size_t)(P.row_first + P.Ly - 1) * Wc + (size_t)j * 16);
+    // every boundary CTA: its halo stores are issued; the last one to get here publishes the next epoch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        const unsigned total = (unsigned)P.halo_ctas_per_rep * (unsigned)P.n_replicas;
+        if (atomicAdd(P.halo_done, 1u) + 1u == total) {
+            __threadfence_system();
+            *P.halo_done = 0u;
+            const long long epoch = *reinterpret_cast<volatile long long*>(P.halo_clock) + 1;
+            *reinterpret_cast<volatile long long*>(P.halo_clock) = epoch;
+            if (P.peer_prev_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(P.peer_prev_flags + 1), "l"(epoch) : "memory");
+            if (P.peer_next_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(P.peer_next_flags + 0), "l"(epoch) : "memory");
+        }
+    }
+}
 
 // The kernel body; `bid` is the CTA's index among the CTAs that work on P's lattices (blockIdx.x for an ordinary
 // launch, blockIdx.x minus the group's first CTA for a group launch, see sweep_group_kernel).
 template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO, int PAIR>
-__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid, const int64_t t_add = 0) {
-    static_assert(!(PAIR && SMALL) && !(PAIR && HALO), "the pair table is one replica per CTA; HALO kernels use the per-site table");
+__device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsigned bid_launch, const int64_t t_add = 0) {
+    bool halo_cta = false;  // HALO: this CTA holds (part of) a boundary strip
+    const unsigned bid = HALO ? halo_cta_order(P, bid_launch, &halo_cta) : bid_launch;
+    static_assert(!(PAIR && SMALL) && !(HALO && SMALL), "the pair table and the slab halo logic are one replica per CTA");
     __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
@@ -165,18 +229,9 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
         if (SWP) {
             *reinterpret_cast<uint4*>(own_col + off) = update_chunk16_sp<COL, MEASURE, (PAIR > 0)>(
                 ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, n_ties);
-        } else if (!HALO) {
+        } else {
             *reinterpret_cast<uint4*>(own_col + off) =
                 update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
-        } else {
-            const uint4 nv = update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
-            *reinterpret_cast<uint4*>(own_col + off) = nv;
-            // fused halo transfer: first owned row -> bottom ghost row of the rank above, last owned row -> top
-            // ghost row of the rank below (same array geometry on every rank)
-            if (P.peer_prev && off == (uint32_t)P.row_first * Wc)
-                *reinterpret_cast<uint4*>(P.peer_prev + rep_base + (size_t)(P.Ly + 1) * Wc + (size_t)j * 16) = nv;
-            if (P.peer_next && off == (uint32_t)(P.row_first + P.Ly - 1) * Wc)
-                *reinterpret_cast<uint4*>(P.peer_next + rep_base + (size_t)j * 16) = nv;
         }
     };
 
@@ -201,6 +256,26 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     };
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // the previous half-sweep (other colour) is complete
+    if (HALO && halo_cta) {
+        // boundary strips read ghost rows: wait until both neighbours have published the epoch this rank is at
+        // (bounded: raises *halo_err instead of hanging the GPU; the run is then reported as failed by the host)
+        if (threadIdx.x == 0) {
+            const long long epoch = *reinterpret_cast<volatile long long*>(P.halo_clock);
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (int k = 0; k < 2; ++k) {
+                if (!((P.halo_need >> k) & 1)) continue;
+                long long v;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(P.halo_flags + k) : "memory");
+                    if (v >= epoch) break;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if ((long long)(t1 - t0) > P.halo_timeout_ns) { *P.halo_err = 1; break; }
+                }
+            }
+        }
+        __syncthreads();
+    }
     uint32_t off = y0 * Wc;  // byte offset of row y inside the replica's colour array
 #if BC_PAIR_TMA
     auto wait_pair_table = [&]() {  // phase 0 of the mbarrier: the body runs once per CTA in the PAIR kernels
@@ -318,10 +393,11 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
         }
     }
     if (n_ties && P.ties) atomicAdd(P.ties, (unsigned long long)n_ties);
+    if (HALO) halo_epilogue(P);
 }
 
 template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO = false, int PAIR = 0>
-__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR>::value)
+__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<SMALL, MEASURE, OPEN, PAIR, HALO>::value)
 sweep_fast_kernel(const __grid_constant__ SweepParams P) {
     sweep_fast_body<COL, SMALL, MEASURE, OPEN, HALO, PAIR>(P, blockIdx.x);
 }
@@ -352,6 +428,7 @@ sweep_group_kernel(const __grid_constant__ GroupParams G) {
     sweep_fast_body<COL, false, MEASURE, OPEN, false, PAIR>(G.p[g], blockIdx.x - first);
 }
 
+#ifdef BC_EXPERIMENTAL
 // ------------------------------------------------------------------------------------------
 // Persistent kernel -- experimental, off by default (a measured negative result): ALL half-sweeps of a
 // run of unmeasured sweeps in ONE cooperative launch, with a grid-wide barrier between half-sweeps instead of a
@@ -423,5 +500,6 @@ sweep_persist_kernel(const __grid_constant__ PersistParams P) {
         if (h + 1 < P.n_half && !persist_barrier(P.bar, (unsigned)(h + 1))) return;
     }
 }
+#endif  // BC_EXPERIMENTAL
 
 }  // namespace bc

@@ -182,26 +182,37 @@ __global__ void halo_push_kernel(const uint8_t* __restrict__ c, uint8_t* __restr
     }
 }
 
-// After the pushes of an exchange have completed (stream order): publish the epoch in the neighbours' flags.
+// After the pushes of an exchange have completed (stream order): advance this rank's epoch counter and publish the
+// new epoch in the neighbours' flags.  (The HALO sweep kernel does the same from its last boundary CTA.)
 // flags[0] of a rank = "top ghost rows valid through epoch" (written by the rank above),
 // flags[1]           = "bottom ghost rows valid through epoch" (written by the rank below).
-__global__ void halo_signal_kernel(long long* peer_prev_flags, long long* peer_next_flags, long long epoch) {
+// The epoch lives in device memory so that graph-replayed launches need no per-launch argument; every rank issues
+// the same sequence of exchanges, so "the epoch I am at" is also what both neighbours must have published.
+__global__ void halo_signal_kernel(long long* clock, long long* peer_prev_flags, long long* peer_next_flags) {
     __threadfence_system();
+    const long long epoch = *clock + 1;
+    *clock = epoch;
     if (peer_prev_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_prev_flags + 1), "l"(epoch) : "memory");
     if (peer_next_flags) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_next_flags + 0), "l"(epoch) : "memory");
 }
 
-// Before ghost rows are read: wait until both neighbours have published `epoch`.  One thread, one GPU per
-// rank (never two ranks on one GPU), bounded: gives up after ~4 s and raises *err instead of hanging the GPU.
-__global__ void halo_wait_kernel(const long long* my_flags, int need_top, int need_bottom, long long epoch, int* err) {
-    const long long t0 = clock64();
+// Before ghost rows are read: wait until both neighbours have published this rank's current epoch.  One thread, one
+// GPU per rank (never two ranks on one GPU), bounded: gives up after timeout_ns and raises *err (sticky; every
+// synchronising entry point of the library reports it) instead of hanging the GPU.
+__global__ void halo_wait_kernel(const long long* my_flags, const long long* clock, int need_top, int need_bottom,
+                                 long long timeout_ns, int* err) {
+    const long long epoch = *clock;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (int k = 0; k < 2; ++k) {
         if (!(k == 0 ? need_top : need_bottom)) continue;
         long long v;
-        do {
+        for (;;) {
             asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(my_flags + k) : "memory");
-            if (v < epoch && clock64() - t0 > 8000000000LL) { *err = 1; return; }
-        } while (v < epoch);
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if ((long long)(t1 - t0) > timeout_ns) { *err = 1; break; }
+        }
     }
 }
 

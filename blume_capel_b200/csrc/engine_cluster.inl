@@ -141,20 +141,6 @@ extern "C" int bc_sync(bc_engine* e) {
     if (!e) return BC_ERR_ARG;
     BC_CUDA(e, cudaSetDevice(e->device));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
-    if (e->d_wave) {
-        int flags[2] = {0, 0};
-        BC_CUDA(e, cudaMemcpy(flags, e->d_wave, sizeof(flags), cudaMemcpyDeviceToHost));
-        if (flags[1]) return fail(e, BC_ERR_STATE, "bc_sync: the wavefront kernel timed out waiting for a dependency");
-    }
-    if (e->d_bar) {
-        unsigned bar[3] = {0, 0, 0};
-        BC_CUDA(e, cudaMemcpy(bar, e->d_bar, sizeof(bar), cudaMemcpyDeviceToHost));
-        if (bar[2]) return fail(e, BC_ERR_STATE, "bc_sync: the persistent kernel timed out at a grid barrier");
-    }
-    if (e->d_halo_err) {
-        int err = 0;
-        BC_CUDA(e, cudaMemcpy(&err, e->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost));
-        if (err) return fail(e, BC_ERR_STATE, "bc_sync: a slab neighbour did not deliver its halo rows in time");
-    }
+    { int rcf = check_device_flags(e, "bc_sync"); if (rcf != BC_OK) return rcf; }
     return BC_OK;
 }

@@ -54,6 +54,7 @@ static int ensure_group_graph(bc_engine* const* es, const GroupPlan& gp, int blo
         sig.push_back((uint64_t)(uintptr_t)es[g]->d_c[0]); sig.push_back((uint64_t)(uintptr_t)es[g]->d_tab16);
         sig.push_back((uint64_t)es[g]->seed); sig.push_back((uint64_t)gp.plan[g].rows);
         sig.push_back((uint64_t)(es[g]->t - e0->t)); sig.push_back((uint64_t)es[g]->n_rep);
+        sig.push_back((uint64_t)es[g]->L); sig.push_back((uint64_t)es[g]->boundary); sig.push_back((uint64_t)gp.cta_end[g]);
     }
     if (e0->group_graph && sig == e0->group_sig) return BC_OK;
     if (e0->group_graph) { cudaGraphExecDestroy(e0->group_graph); e0->group_graph = nullptr; }
@@ -140,8 +141,8 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
     // (a member with shorter strips only stages the 11.4 KB table more often; the results do not depend on it)
     gp.pair = have_tab2 && e0->opt_pair_min_rows > 0 && 2 * sites_long >= sites_all;
 
-    if (gp.pair) {  // 6 CTAs x 30 KB per SM need the large shared-memory carve-out
-        static bool carveout_set = false;
+    if (gp.pair) {  // 6 CTAs x 30 KB per SM need the large shared-memory carve-out (a per-device function attribute)
+        bool& carveout_set = e0->group_carveout_set;
         if (!carveout_set) {
             for (int m = 0; m < 2; ++m)
                 for (int o = 0; o < 2; ++o) {
@@ -170,12 +171,14 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
     const int block = e0->opt_graph_block;
     for (int64_t slot = 0; slot <= n_meas; ++slot) {
         const int64_t until = slot < n_meas ? e0->pending_sweeps[(size_t)slot] - e0->t : n_sweeps;
+#ifdef BC_EXPERIMENTAL
         GroupPlan pp;
         if (until > done && persist_plan(engines, n_engines, until - done, &pp)) {
             int rc = run_persist(engines, pp, done, until - done);
             if (rc != BC_OK) return rc;
             done = until;
         }
+#endif
         if (e0->opt_use_graph && block > 0 && until - done >= block) {
             int rc = ensure_group_graph(engines, gp, block);
             if (rc != BC_OK) return rc;
@@ -245,6 +248,7 @@ extern "C" int bc_measure(bc_engine* e, bc_obs* out) {
     if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
     cudaFree(d_raw);
     if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_measure: ") + cudaGetErrorString(st));
+    { int rcf = check_device_flags(e, "bc_measure"); if (rcf != BC_OK) return rcf; }
     for (int r = 0; r < e->n_rep; ++r) raw_to_obs(e, &raw[(size_t)r * OBS_RAW], e->t - 1, &out[r]);
     return BC_OK;
 }

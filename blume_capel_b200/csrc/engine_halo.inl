@@ -32,9 +32,8 @@ static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr, b
                 geom_of(e), e->n_rep);
             ++e->launches;
         }
-        ++e->halo_epoch;
-        halo_signal_kernel<<<1, 1, 0, stream>>>(prev >= 0 ? e->peer_prev_flags : nullptr,
-                                                next >= 0 ? e->peer_next_flags : nullptr, e->halo_epoch);
+        halo_signal_kernel<<<1, 1, 0, stream>>>(e->d_halo_clock, prev >= 0 ? e->peer_prev_flags : nullptr,
+                                                next >= 0 ? e->peer_next_flags : nullptr);
         ++e->launches;
         BC_CUDA(e, cudaGetLastError());
         return BC_OK;
@@ -58,13 +57,37 @@ static int exchange_halo(bc_engine* e, int col, cudaStream_t stream = nullptr, b
 
 // P2P mode: before a kernel reads ghost rows, wait (on the GPU) for the neighbours' latest epoch
 static int halo_wait(bc_engine* e, cudaStream_t stream) {
-    if (!e->p2p || e->halo_waited == e->halo_epoch) return BC_OK;
+    if (!e->p2p) return BC_OK;
     const bool periodic = e->boundary == BC_PERIODIC;
     const int need_top = (e->rank > 0 || periodic) ? 1 : 0, need_bottom = (e->rank + 1 < e->nranks || periodic) ? 1 : 0;
-    halo_wait_kernel<<<1, 1, 0, stream>>>(e->d_flags, need_top, need_bottom, e->halo_epoch, e->d_halo_err);
+    halo_wait_kernel<<<1, 1, 0, stream>>>(e->d_flags, e->d_halo_clock, need_top, need_bottom,
+                                          (long long)e->opt_halo_timeout_ms * 1000000LL, e->d_halo_err);
     ++e->launches;
-    e->halo_waited = e->halo_epoch;
     BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+// Sticky device-side failure flags (a slab neighbour that did not deliver its halo rows in time; the experimental
+// kernels' bounded waits): read after the stream has been synchronised, by every synchronising entry point.
+static int check_device_flags(bc_engine* e, const char* who) {
+    if (e->d_halo_err) {
+        int err = 0;
+        BC_CUDA(e, cudaMemcpy(&err, e->d_halo_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(e, BC_ERR_STATE, std::string(who) + ": a slab neighbour did not deliver its halo rows in time "
+                                              "(results since then are invalid; option \"halo_timeout_ms\")");
+    }
+#ifdef BC_EXPERIMENTAL
+    if (e->d_wave) {
+        int flags[2] = {0, 0};
+        BC_CUDA(e, cudaMemcpy(flags, e->d_wave, sizeof(flags), cudaMemcpyDeviceToHost));
+        if (flags[1]) return fail(e, BC_ERR_STATE, std::string(who) + ": the wavefront kernel timed out waiting for a dependency");
+    }
+    if (e->d_bar) {
+        unsigned bar[3] = {0, 0, 0};
+        BC_CUDA(e, cudaMemcpy(bar, e->d_bar, sizeof(bar), cudaMemcpyDeviceToHost));
+        if (bar[2]) return fail(e, BC_ERR_STATE, std::string(who) + ": the persistent kernel timed out at a grid barrier");
+    }
+#endif
     return BC_OK;
 }
 

@@ -37,12 +37,20 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
     if (n == "swp_min_rows") { e->opt_swp_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "pair_min_rows") { e->opt_pair_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
+#ifdef BC_EXPERIMENTAL
     if (n == "wave") { e->opt_wave = (int)value; return BC_OK; }
+    if (n == "persist") { e->opt_persist = (int)value; return BC_OK; }
+#else
+    if (n == "wave" || n == "persist") {
+        if (value == 0) return BC_OK;
+        return fail(e, BC_ERR_UNSUPPORTED, "bc_set_option: " + n + " is an experimental kernel (a measured negative result); build with -DBC_EXPERIMENTAL");
+    }
+#endif
+    if (n == "halo_timeout_ms") { if (value < 1 || value > 3600000) return fail(e, BC_ERR_ARG, "halo_timeout_ms out of range"); e->opt_halo_timeout_ms = (int)value; return BC_OK; }
     if (n == "pdl") { e->opt_pdl = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
-    if (n == "fused_halo") { e->opt_fused_halo = value != 0; return BC_OK; }
+    if (n == "fused_halo") { e->opt_fused_halo = value != 0; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "overlap") { e->opt_overlap = value != 0; return BC_OK; }
     if (n == "resident") { e->opt_resident = (int)value; return BC_OK; }
-    if (n == "persist") { e->opt_persist = (int)value; return BC_OK; }
     if (n == "use_graph") { e->opt_use_graph = value != 0; return BC_OK; }
     if (n == "graph_block") { if (value < 1 || value > 1024) return fail(e, BC_ERR_ARG, "graph_block out of range"); e->opt_graph_block = (int)value; return BC_OK; }
     if (n == "force_generic") { e->opt_force_generic = value != 0; return BC_OK; }

@@ -22,9 +22,19 @@ extern "C" int bc_slab_ipc_export(bc_engine* e, void* blob192) {
 
 extern "C" int bc_slab_ipc_connect(bc_engine* e, const void* prev_blob192, const void* next_blob192) {
     if (!e) return BC_ERR_ARG;
-    if (!e->ghost || e->nranks < 2) return fail(e, BC_ERR_STATE, "bc_slab_ipc_connect: needs a slab handle with n_ranks >= 2");
+    if (!e->ghost) return fail(e, BC_ERR_STATE, "bc_slab_ipc_connect: needs a slab handle");
     BC_CUDA(e, cudaSetDevice(e->device));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (e->nranks == 1) {
+        // A single slab is its own ring neighbour: with two NULL blobs the peer pointers are the handle's own arrays
+        // and flags, and the HALO kernels (boundary CTAs first, in-kernel wait / halo stores / epoch signal) run on
+        // one GPU exactly as they do across GPUs.  This is how the single-GPU tests cover them.
+        if (prev_blob192 || next_blob192) return fail(e, BC_ERR_ARG, "bc_slab_ipc_connect: a one-rank slab connects to itself (pass NULL, NULL)");
+        for (int c = 0; c < 2; ++c) { e->peer_prev_c[c] = e->d_c[c]; e->peer_next_c[c] = e->d_c[c]; }
+        e->peer_prev_flags = e->d_flags; e->peer_next_flags = e->d_flags;
+        e->p2p = true;
+        return BC_OK;
+    }
     const bool same = prev_blob192 && next_blob192 && std::memcmp(prev_blob192, next_blob192, sizeof(IpcBlob)) == 0;
     auto open3 = [&](const void* blob, uint8_t* (&c)[2], long long*& flags, int slot) -> int {
         IpcBlob b;

@@ -84,7 +84,10 @@ static int download_range(bc_engine* e, int r0, int n, int8_t* spins, bool wait 
     rc = stage_from_device(e, r0, n);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaMemcpyAsync(spins, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
-    if (wait) BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (wait) {
+        BC_CUDA(e, cudaStreamSynchronize(e->stream));
+        return check_device_flags(e, "bc_download");
+    }
     return BC_OK;
 }
 

@@ -11,7 +11,9 @@ static fast_fn fast_open(bool open) {
 }
 
 template <int COL, bool MEAS>
-static fast_fn fast_halo(bool open) {
+static fast_fn fast_halo(bool open, int pair) {
+    if (pair == 2 && !open && !MEAS) return (fast_fn)sweep_fast_kernel<COL, false, false, false, true, 2>;
+    if (pair) return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true, 1> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true, 1>;
     return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true>;
 }
 
@@ -22,23 +24,26 @@ static fast_fn fast_pair(bool open, bool swp = false) {
                 : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, false, 1>;
 }
 
-static void pair_kernels(fast_fn (&out)[10]) {
+static void pair_kernels(fast_fn (&out)[20]) {
     int n = 0;
     for (int open = 0; open < 2; ++open) {
         out[n++] = fast_pair<0, false>(open); out[n++] = fast_pair<0, true>(open);
         out[n++] = fast_pair<1, false>(open); out[n++] = fast_pair<1, true>(open);
+        out[n++] = fast_halo<0, false>(open, 1); out[n++] = fast_halo<0, true>(open, 1);
+        out[n++] = fast_halo<1, false>(open, 1); out[n++] = fast_halo<1, true>(open, 1);
     }
     out[n++] = fast_pair<0, false>(false, true); out[n++] = fast_pair<1, false>(false, true);
+    out[n++] = fast_halo<0, false>(false, 2); out[n++] = fast_halo<1, false>(false, 2);
 }
 
 static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false, int pair = 0) {
-    if (pair && !small && !halo) {
+    if (halo && !small) {
+        if (col == 0) return meas ? fast_halo<0, true>(open, pair) : fast_halo<0, false>(open, pair);
+        return meas ? fast_halo<1, true>(open, pair) : fast_halo<1, false>(open, pair);
+    }
+    if (pair && !small) {
         if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open, pair == 2);
         return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open, pair == 2);
-    }
-    if (halo && !small) {
-        if (col == 0) return meas ? fast_halo<0, true>(open) : fast_halo<0, false>(open);
-        return meas ? fast_halo<1, true>(open) : fast_halo<1, false>(open);
     }
     if (col == 0) {
         if (!small) return meas ? fast_open<0, false, true>(open) : fast_open<0, false, false>(open);
@@ -118,6 +123,9 @@ static SweepParams sweep_params(const bc_engine* e, const LaunchPlan& plan, int 
     P.Ly = e->Ly;
     P.peer_prev = nullptr;
     P.peer_next = nullptr;
+    P.halo_flags = nullptr; P.halo_clock = nullptr; P.halo_done = nullptr; P.halo_err = nullptr;
+    P.peer_prev_flags = nullptr; P.peer_next_flags = nullptr;
+    P.halo_timeout_ns = 0; P.halo_ctas_per_rep = 0; P.halo_need = 0;
     P.Wc = e->Wc;
     P.cpr = plan.cpr;
     P.strips = plan.strips;
@@ -130,17 +138,30 @@ static SweepParams sweep_params(const bc_engine* e, const LaunchPlan& plan, int 
     return P;
 }
 
+// Peer-memory slab whose whole half-sweep is ONE launch of the HALO instantiation (boundary strips first, waits,
+// halo stores and epoch signal inside the kernel): graph replay and programmatic dependent launch apply to it.
+static bool slab_fused(const bc_engine* e, const LaunchPlan& plan) {
+    return e->ghost && e->p2p && e->opt_fused_halo && plan.fast && !plan.small;
+}
+
 // part: 0 = all strips, 1 = the two boundary strips of the slab, 2 = the interior strips
 static int launch_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot,
                        const int64_t* t_ptr = nullptr, int part = 0, cudaStream_t stream = nullptr) {
     if (!stream) stream = e->stream;
     SweepParams P = sweep_params(e, plan, col, t, slot, t_ptr);
-    // boundary-strip launch of a peer-memory slab: the kernel itself stores the halo rows into the neighbours
-    const bool fused_halo = part == 1 && e->p2p && e->opt_fused_halo && plan.fast && !plan.small;
+    const bool fused_halo = part == 0 && slab_fused(e, plan);
     if (fused_halo) {
         const bool periodic = e->boundary == BC_PERIODIC;
-        if (e->rank > 0 || periodic) P.peer_prev = e->peer_prev_c[col];
-        if (e->rank + 1 < e->nranks || periodic) P.peer_next = e->peer_next_c[col];
+        const bool has_prev = e->rank > 0 || periodic, has_next = e->rank + 1 < e->nranks || periodic;
+        if (has_prev) { P.peer_prev = e->peer_prev_c[col]; P.peer_prev_flags = e->peer_prev_flags; }
+        if (has_next) { P.peer_next = e->peer_next_c[col]; P.peer_next_flags = e->peer_next_flags; }
+        P.halo_flags = e->d_flags; P.halo_clock = e->d_halo_clock; P.halo_done = e->d_halo_done; P.halo_err = e->d_halo_err;
+        P.halo_timeout_ns = (long long)e->opt_halo_timeout_ms * 1000000LL;
+        // CTAs per replica that hold (part of) the first or the last strip: see halo_cta_order
+        const long long C = (long long)plan.strips * plan.cpr / FAST_THREADS;
+        const long long nb = plan.cpr >= FAST_THREADS ? plan.cpr / FAST_THREADS : 1;
+        P.halo_ctas_per_rep = (int)std::min<long long>(2 * nb, C);
+        P.halo_need = (has_prev ? 1 : 0) | (has_next ? 2 : 0);
     }
     unsigned grid = plan.grid;
     if (part == 1) { P.strips = 2; P.strip_stride = plan.strips - 1; }
@@ -186,6 +207,7 @@ static int fetch_pending(bc_engine* e, bc_obs* out) {
         BC_NCCL(e, g_nccl.AllReduce(e->d_obs, e->d_obs, raw.size(), ncclUint64, ncclSum, e->comm, e->stream));
     BC_CUDA(e, cudaMemcpyAsync(raw.data(), e->d_obs, raw.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    { int rcf = check_device_flags(e, "observables"); if (rcf != BC_OK) return rcf; }
     for (int64_t m = 0; m < n; ++m)
         for (int r = 0; r < e->n_rep; ++r)
             raw_to_obs(e, &raw[((size_t)m * e->n_rep + r) * OBS_RAW], e->pending_sweeps[m], &out[(size_t)m * e->n_rep + r]);
@@ -197,6 +219,7 @@ static int fetch_pending(bc_engine* e, bc_obs* out) {
 // half-sweep waits for both.  (The boundary strips are whole strips of the ordinary decomposition, so the
 // result is identical to the single-launch order: sites of one colour never read each other.)
 static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure, int64_t t, int64_t slot) {
+    if (slab_fused(e, plan)) return launch_half(e, plan, col, measure, t, slot);
     const long long ipr_part = (long long)2 * plan.cpr, ipr_int = (long long)(plan.strips - 2) * plan.cpr;
     const bool can_split = plan.fast && !plan.small && plan.strips >= 4 && (ipr_part % FAST_THREADS) == 0 &&
                            (ipr_int % FAST_THREADS) == 0 && e->opt_overlap;
@@ -215,7 +238,7 @@ static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure
     int rc = halo_wait(e, e->halo_stream);
     if (rc != BC_OK) return rc;
     launch_half(e, plan, col, measure, t, slot, nullptr, 1, e->halo_stream);
-    rc = exchange_halo(e, col, e->halo_stream, e->p2p && e->opt_fused_halo);
+    rc = exchange_halo(e, col, e->halo_stream);
     if (rc != BC_OK) return rc;
     BC_CUDA(e, cudaEventRecord(e->ev_halo, e->halo_stream));
     launch_half(e, plan, col, measure, t, slot, nullptr, 2, e->stream);
@@ -226,7 +249,9 @@ static int slab_half(bc_engine* e, const LaunchPlan& plan, int col, bool measure
 // (Re)capture the graph of `block` unmeasured sweeps for the current plan: 2*block kernels reading the
 // device clock plus one node that advances it.
 static int ensure_graph(bc_engine* e, const LaunchPlan& plan, int block) {
-    if (e->graph_exec && e->graph_rows == plan.rows && e->graph_grid == plan.grid && e->graph_block == block) return BC_OK;
+    const int halo_sig = slab_fused(e, plan) ? 1 : 0;
+    if (e->graph_exec && e->graph_rows == plan.rows && e->graph_grid == plan.grid && e->graph_block == block &&
+        e->graph_halo == halo_sig) return BC_OK;
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     BC_CUDA(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -242,10 +267,11 @@ static int ensure_graph(bc_engine* e, const LaunchPlan& plan, int block) {
     st = cudaGraphInstantiate(&e->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (st != cudaSuccess) { e->graph_exec = nullptr; return fail(e, BC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(st)); }
-    e->graph_rows = plan.rows; e->graph_grid = plan.grid; e->graph_block = block;
+    e->graph_rows = plan.rows; e->graph_grid = plan.grid; e->graph_block = block; e->graph_halo = halo_sig;
     return BC_OK;
 }
 
+#ifdef BC_EXPERIMENTAL
 // ---- wavefront kernel: all half-sweeps of a run of unmeasured sweeps in one launch (L2-resident lattices) ----
 static bool wave_eligible(const bc_engine* e, const LaunchPlan& plan, int64_t n) {
     if (e->opt_wave == 0 || e->ghost || !plan.fast || plan.small || (plan.rows & 3) || n < 2) return false;
@@ -295,7 +321,8 @@ static int run_wave(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n)
     return BC_OK;
 }
 
-// ---- persistent kernel: a whole run of unmeasured sweeps in one cooperative launch -------------------------
+#endif  // BC_EXPERIMENTAL
+
 // rows per thread R for a member of a multi-handle launch: even, whole strips, whole CTAs per replica (!SMALL body)
 static bool group_rows_valid(const bc_engine* e, int R) {
     const int cpr = e->L / 32;
@@ -334,6 +361,8 @@ static void fill_group_plan(bc_engine* const* es, int n, int target, GroupPlan* 
     }
 }
 
+#ifdef BC_EXPERIMENTAL
+// ---- persistent kernel: a whole run of unmeasured sweeps in one cooperative launch -------------------------
 static int persist_capacity(bc_engine* e0) {
     const int open = e0->boundary == BC_OPEN;
     if (!e0->persist_cap[open]) {
@@ -405,17 +434,21 @@ static int run_persist(bc_engine* const* es, const GroupPlan& gp, int64_t s0, in
     return BC_OK;
 }
 
+#endif  // BC_EXPERIMENTAL
+
 // n unmeasured sweeps starting at sweep index t0
 static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, int64_t n) {
+#ifdef BC_EXPERIMENTAL
     if (wave_eligible(e, plan, n)) return run_wave(e, plan, t0, n);
     if (plan.fast) {
         GroupPlan gp;
         bc_engine* one[1] = {e};
         if (persist_plan(one, 1, n, &gp)) return run_persist(one, gp, t0 - e->t, n);
     }
+#endif
     int64_t done = 0;
     const int block = e->opt_graph_block;
-    if (e->opt_use_graph && !e->ghost && block > 0 && n >= block) {
+    if (e->opt_use_graph && (!e->ghost || slab_fused(e, plan)) && block > 0 && n >= block) {
         int rc = ensure_graph(e, plan, block);
         if (rc != BC_OK) return rc;
         clock_set_kernel<<<1, 1, 0, e->stream>>>(e->d_clock, t0);

@@ -74,13 +74,13 @@ def connect_p2p(bc, e, rank, world, periodic):
     dist.barrier()
 
 
-def gpu_slab(boundary, p2p=False):
+def gpu_slab(boundary, p2p=False, L=None, rows=0, fused=1):
     """bc_create_slab over NCCL (or peer stores) == single-GPU engine, lattice and fused observables."""
     import blume_capel_b200 as bc
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L, n, seed = (2048 if p2p else 256), 8, 4321
+    L, n, seed = (L or (2048 if p2p else 256)), 8, 4321
     b = bc.PERIODIC if boundary == "periodic" else bc.OPEN
     nid = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -89,6 +89,9 @@ def gpu_slab(boundary, p2p=False):
     e = bc.Engine(L, b, 1, local, seed, slab=(world, rank, bytes(nid.cpu().numpy().tobytes())))
     if p2p:
         connect_p2p(bc, e, rank, world, boundary == "periodic")
+        e.set_option("fused_halo", fused)
+    e.set_option("rows_per_thread", rows)
+    e.set_option("graph_block", 2)
     e.set_params(*TC)
     e.init_random()
     obs = e.sweep(n, 2)
@@ -128,4 +131,9 @@ def gpu_slab(boundary, p2p=False):
 
 if __name__ == "__main__":
     mode, boundary = sys.argv[1], sys.argv[2]
-    sys.exit(cpu_slab(boundary) if mode == "cpu" else gpu_slab(boundary, p2p=(mode == "gpu_p2p")))
+    if mode == "cpu":
+        sys.exit(cpu_slab(boundary))
+    L = int(sys.argv[3]) if len(sys.argv) > 3 else None
+    rows = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    fused = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+    sys.exit(gpu_slab(boundary, p2p=(mode == "gpu_p2p"), L=L, rows=rows, fused=fused))

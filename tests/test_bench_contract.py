@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_line(tmp_path):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--no-l64"],  # the nominal L=64 run takes two minutes per process: not in the CPU suite
                        cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [x for x in r.stdout.splitlines() if x.strip()]
@@ -21,6 +22,8 @@ def test_reference_arm_line(tmp_path):
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    lo = cb["loop_only"]  # the attempt loop alone
+    assert lo["kind"] == "port" and lo["value"] > d["value"] and lo["cores"] == cb["cores"]
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly(tmp_path):

@@ -53,7 +53,14 @@ def test_group_persistent_equals_individual_sweeps(bc, boundary):
     sizes, reps = (128, 512, 256), (2, 1, 3)
     a = make(bc, sizes, boundary, 300, reps)
     b = make(bc, sizes, boundary, 300, reps)
-    a[0].set_option("persist", 1)
+    try:
+        a[0].set_option("persist", 1)
+    except Exception as ex:
+        if getattr(ex, "code", 0) != -5:
+            raise
+        for e in a + b:
+            e.close()
+        pytest.skip("persist: experimental kernel not compiled in (build with -DBC_EXPERIMENTAL)")
     a[2].sweep(2)
     b[2].sweep(2)
     l0 = a[0].launch_count

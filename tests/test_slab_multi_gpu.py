@@ -45,13 +45,17 @@ def test_slab_nccl_two_gpus(boundary):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("boundary", ["periodic", "open"])
-def test_slab_peer_store_halo_two_gpus(boundary):
+@pytest.mark.parametrize("boundary,L,rows,fused", [("periodic", 2048, 0, 1), ("open", 2048, 0, 1), ("periodic", 2048, 64, 1),
+                                                   ("periodic", 8192, 64, 1), ("open", 8192, 16, 1), ("periodic", 2048, 0, 0),
+                                                   ("periodic", 256, 0, 1)])
+def test_slab_peer_store_halo_two_gpus(boundary, L, rows, fused):
     """Halo rows stored directly into the neighbour's ghost rows over NVLink (CUDA IPC peer pointers +
-    epoch flags) instead of NCCL send/recv; L = 2048 so the boundary-strips-first split is active."""
+    epoch flags) instead of NCCL send/recv.  fused = 1: the whole half-sweep of a slab is one launch of the HALO
+    kernels (plain, pair-table and pipelined variants depending on the strip height; L = 8192 has two CTAs per
+    boundary strip); fused = 0: boundary strips, push kernel, signal kernel, interior as separate launches."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["gpu_p2p", boundary])
+    r = _torchrun(2, ["gpu_p2p", boundary, str(L), str(rows), str(fused)])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SLAB_OK" in r.stdout
