@@ -1,0 +1,507 @@
+// bc_cluster_tile.cuh -- bit-parallel cluster labelling of one 64 x 64 tile by one warp.
+// Part of the sm_100a Blume-Capel engine; included through bc_cluster_kernels.cuh.
+//
+// What the reference does one cluster at a time with a BFS queue (wolff(), /root/reference/main.cpp:113-154, bond
+// probability 1 - exp(-2J/T) at :115, zeros never join :123-130,144) and, for the dumps, with a DFS over the whole
+// lattice (form_clusters, main.cpp:179-230), is done here for all clusters at once on 64-bit ROW MASKS:
+//   * a tile row is four 64-bit words: plus sites, minus sites, open bonds to the right, open bonds downwards;
+//   * lane l of the warp owns tile rows 2l and 2l+1: it converts its 2 x 64 spin bytes (two 32-byte pieces of the
+//     two compact colour arrays per row) to masks, draws the random bonds of its rows 32 at a time (bit-plane
+//     uniforms, most significant plane first, until every candidate bond is decided: about two Philox calls per 32
+//     bonds, see cl_draw_bonds), and finds the horizontal runs of its rows with one AND-NOT;
+//   * only RUN STARTS are union-find nodes (16-bit labels in shared memory): a vertical bond costs a union only when
+//     the bond to its left does not already join the same two runs; the larger root is always linked under the
+//     smaller one, so a cluster's root is its smallest site, independent of the order of the unions;
+//   * clusters that touch the tile's perimeter are flagged and merged across tiles by cl_border_kernel in a global
+//     union-find over their roots' site indices; everything else never leaves shared memory.
+// Between kernels a tile is 8 KB of labels (raw copy of the shared-memory array, 2 B / site), 512 B of bond masks
+// and 512 B of perimeter roots -- against 1 B + 4 B + 1 B per site written and 4 B chains re-read by round 1's
+// one-thread-per-two-sites kernels (0.24 ms per L = 4096 update; profiles/r01_ncu_launches_cluster_v2.csv).
+//
+// Every function here is host + device: the phases of the kernels are plain functions of (lane, tile state), the
+// kernels call them with __syncwarp() in between, and tests/cpu/cluster_emulation.cpp runs the same phases lane by
+// lane on the CPU against the oracle (there is no GPU in the development container).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BC_HD __host__ __device__ __forceinline__
+#define BC_UNROLL _Pragma("unroll")
+#else
+#define BC_UNROLL
+#define BC_HD inline
+struct uint4 { uint32_t x, y, z, w; };  // CPU emulation build (tests/cpu/cluster_emulation.cpp)
+#endif
+
+namespace bc {
+
+constexpr int CL_T = 64;                 // tile edge (sites)
+constexpr int CL_SITES = CL_T * CL_T;
+constexpr uint16_t CL_FLAG = 0x8000u;    // label entry: the root's cluster touches the tile perimeter
+constexpr uint16_t CL_IDX = 0x0FFFu;     // label entry: tile-local site index ly * 64 + lx of the root
+constexpr uint16_t CL_NONE = 0xFFFFu;    // perimeter entry: empty site
+constexpr uint32_t CL_STREAM_BOND = 3u, CL_STREAM_FLIP = 4u;
+
+// ---- small portable helpers -------------------------------------------------------------------------------------
+BC_HD int cl_ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+BC_HD int cl_clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+// position of the run start at or before x: the highest set bit of rs among bits 0..x (there always is one for an
+// occupied x, because an occupied site without a bond from its left neighbour starts a run)
+BC_HD int cl_run_start(uint64_t rs, int x) { return 63 - cl_clz64(rs & (~0ull >> (63 - x))); }
+
+BC_HD uint16_t cl_cas16(uint16_t* p, uint16_t cmp, uint16_t val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(reinterpret_cast<unsigned short*>(p), (unsigned short)cmp, (unsigned short)val);
+#else
+    const uint16_t old = *p;
+    if (old == cmp) *p = val;
+    return old;
+#endif
+}
+BC_HD void cl_or32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+BC_HD uint32_t cl_cas32(uint32_t* p, uint32_t cmp, uint32_t val) {
+#if defined(__CUDA_ARCH__)
+    return atomicCAS(p, cmp, val);
+#else
+    const uint32_t old = *p;
+    if (old == cmp) *p = val;
+    return old;
+#endif
+}
+
+BC_HD void cl_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+    BC_UNROLL
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ (k0 + (uint32_t)r * 0x9E3779B9u);
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ (k1 + (uint32_t)r * 0xBB67AE85u);
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// bits 0..31 of v to the even bit positions of a 64-bit word, and back
+BC_HD uint64_t cl_spread(uint32_t v) {
+    uint64_t s = v;
+    s = (s | (s << 16)) & 0x0000FFFF0000FFFFull;
+    s = (s | (s << 8)) & 0x00FF00FF00FF00FFull;
+    s = (s | (s << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    s = (s | (s << 2)) & 0x3333333333333333ull;
+    s = (s | (s << 1)) & 0x5555555555555555ull;
+    return s;
+}
+BC_HD uint32_t cl_squeeze(uint64_t s) {
+    s &= 0x5555555555555555ull;
+    s = (s | (s >> 1)) & 0x3333333333333333ull;
+    s = (s | (s >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    s = (s | (s >> 4)) & 0x00FF00FF00FF00FFull;
+    s = (s | (s >> 8)) & 0x0000FFFF0000FFFFull;
+    s = (s | (s >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)s;
+}
+// bit 0 of each of the four bytes of w as a nibble (no carries: the four products land on distinct bits)
+BC_HD uint32_t cl_nibble(uint32_t w) { return ((w & 0x01010101u) * 0x00204081u >> 21) & 0xFu; }
+// and back: bits 0..3 of n to bit 0 of the four bytes
+BC_HD uint32_t cl_bytes(uint32_t n) { return ((n & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+// ---- geometry ---------------------------------------------------------------------------------------------------
+// Colour arrays as the sweep kernels keep them: code = spin + 1, [replica][array row][Wc], site (x, y) lives in array
+// (x + y) & 1 at byte x >> 1 of array row row_first + y.  A one-rank slab handle has ghost rows (row_first = 1);
+// the labelling wraps by index and never reads them.
+struct ClGeom {
+    int L, Wc, rows_arr, row_first, open;
+    int tiles_x, tiles_y;
+};
+struct ClTileId {
+    uint32_t rep;
+    int tx, ty, x0, y0, w, h;  // w, h: sites of the tile that exist (the last tiles of a lattice may be clipped)
+    uint32_t tile;             // index of the tile among all tiles of all replicas
+};
+BC_HD ClTileId cl_tile_id(const ClGeom& g, uint32_t tile) {
+    ClTileId t;
+    const uint32_t per = (uint32_t)g.tiles_x * (uint32_t)g.tiles_y;
+    t.tile = tile;
+    t.rep = tile / per;
+    const uint32_t in = tile - t.rep * per;
+    t.ty = (int)(in / (uint32_t)g.tiles_x);
+    t.tx = (int)(in - (uint32_t)t.ty * (uint32_t)g.tiles_x);
+    t.x0 = t.tx * CL_T; t.y0 = t.ty * CL_T;
+    t.w = g.L - t.x0 < CL_T ? g.L - t.x0 : CL_T;
+    t.h = g.L - t.y0 < CL_T ? g.L - t.y0 : CL_T;
+    return t;
+}
+BC_HD uint32_t cl_global_site(const ClGeom& g, const ClTileId& t, uint32_t local) {
+    return (uint32_t)(t.y0 + (int)(local >> 6)) * (uint32_t)g.L + (uint32_t)(t.x0 + (int)(local & 63u));
+}
+BC_HD size_t cl_row_offset(const ClGeom& g, uint32_t rep, int gy) {
+    return ((size_t)rep * (size_t)g.rows_arr + (size_t)(g.row_first + gy)) * (size_t)g.Wc;
+}
+BC_HD uint32_t cl_site_code(const ClGeom& g, const uint8_t* c0, const uint8_t* c1, uint32_t rep, int gx, int gy) {
+    return (((gx + gy) & 1) ? c1 : c0)[cl_row_offset(g, rep, gy) + (size_t)(gx >> 1)];
+}
+
+// Masks of the plus (code 2) and minus (code 0) sites of the 64 sites x0 .. x0+63 of lattice row gy.  Even x come
+// from array gy & 1, odd x from the other one, 32 bytes each; bytes behind the lattice edge are pad bytes of code 1.
+BC_HD void cl_load_row(const ClGeom& g, const uint8_t* c0, const uint8_t* c1, uint32_t rep, int x0, int gy, uint64_t* P,
+                       uint64_t* M) {
+    const size_t off = cl_row_offset(g, rep, gy) + (size_t)(x0 >> 1);
+    const uint8_t* ev = ((gy & 1) ? c1 : c0) + off;
+    const uint8_t* od = ((gy & 1) ? c0 : c1) + off;
+    const int vecs = (g.Wc - (x0 >> 1)) >= 32 ? 2 : ((g.Wc - (x0 >> 1)) >= 16 ? 1 : 0);  // Wc is a multiple of 16
+    uint32_t pe = 0, po = 0, me = 0, mo = 0;
+    BC_UNROLL
+    for (int v = 0; v < 2; ++v) {
+        if (v >= vecs) break;
+        const uint4 a = *reinterpret_cast<const uint4*>(ev + 16 * v), b = *reinterpret_cast<const uint4*>(od + 16 * v);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    BC_UNROLL
+        for (int k = 0; k < 4; ++k) {
+            const int sh = 16 * v + 4 * k;
+            pe |= cl_nibble(aw[k] >> 1) << sh;
+            po |= cl_nibble(bw[k] >> 1) << sh;
+            me |= cl_nibble(~(aw[k] | (aw[k] >> 1))) << sh;
+            mo |= cl_nibble(~(bw[k] | (bw[k] >> 1))) << sh;
+        }
+    }
+    *P = cl_spread(pe) | (cl_spread(po) << 1);
+    *M = cl_spread(me) | (cl_spread(mo) << 1);
+}
+
+// ---- random bonds -----------------------------------------------------------------------------------------------
+// Spec (restated one bond at a time by the CPU checker): the 32 sites x = 32 grp .. 32 grp + 31 of lattice row gy share 32
+// bit-plane words per direction; plane b (b = 0 most significant) is word b & 3 of
+// Philox(gy << 15 | grp << 4 | dir << 3 | b >> 2, c_lo, c_hi, BOND << 1), the uniform of a site is the column of
+// its bit through the planes, and the bond is open iff uniform < thr.  Evaluated for all candidates of a 32-site
+// group at once: while some candidate is undecided, draw the next plane; where the plane's bit differs from the
+// threshold's bit the comparison is decided.  Expected planes for 32 candidates: about seven (two Philox calls).
+BC_HD uint64_t cl_draw_bonds(uint64_t cand, uint32_t gy, uint32_t grp0, uint32_t dir, uint32_t thr, uint32_t c_lo,
+                             uint32_t c_hi, uint32_t k0, uint32_t k1) {
+    uint64_t open = 0;
+    for (uint32_t half = 0; half < 2; ++half) {
+        uint32_t U = (uint32_t)(cand >> (32 * half)), R = 0;
+        for (uint32_t c4 = 0; c4 < 8 && U; ++c4) {
+            uint32_t w[4];
+            cl_philox((gy << 15) | ((grp0 + half) << 4) | (dir << 3) | c4, c_lo, c_hi, CL_STREAM_BOND << 1, k0, k1, w);
+    BC_UNROLL
+            for (uint32_t j = 0; j < 4; ++j) {
+                if ((thr >> (31u - (4u * c4 + j))) & 1u) { R |= U & ~w[j]; U &= w[j]; }
+                else U &= ~w[j];
+            }
+        }
+        open |= (uint64_t)R << (32 * half);
+    }
+    return open;
+}
+
+// flip decision of the cluster whose smallest site is `root` (oracle: cluster_flips); `blk` / `w` cache the last call
+BC_HD uint32_t cl_flip_bit(uint32_t root, uint32_t c_lo, uint32_t c_hi, uint32_t k0, uint32_t k1, uint32_t* blk,
+                           uint32_t (&w)[4]) {
+    if ((root >> 7) != *blk) {
+        *blk = root >> 7;
+        cl_philox(*blk, c_lo, c_hi, CL_STREAM_FLIP << 1, k0, k1, w);
+    }
+    return (w[(root >> 5) & 3u] >> (root & 31u)) & 1u;
+}
+
+// ---- union-find over run starts (shared memory, 16-bit tile-local labels) ---------------------------------------
+// find with path halving: every value ever stored in par[a] is an ancestor of a, so concurrent finds and unions only
+// ever see valid (possibly longer) paths; roots are never written by the halving store.
+BC_HD uint16_t cl_find(volatile uint16_t* par, uint16_t a) {
+    uint16_t p = par[a];
+    while (p != a) {
+        const uint16_t gp = par[p];
+        if (gp != p) par[a] = gp;
+        a = p;
+        p = gp;
+    }
+    return a;
+}
+// link the larger root under the smaller one; retry from the current roots if the larger one stopped being a root
+BC_HD void cl_union(uint16_t* par, uint16_t a, uint16_t b) {
+    uint16_t ra = cl_find(par, a), rb = cl_find(par, b);
+    while (ra != rb) {
+        if (ra < rb) { const uint16_t t = ra; ra = rb; rb = t; }
+        const uint16_t old = cl_cas16(par + ra, ra, rb);
+        if (old == ra) break;
+        ra = cl_find(par, old);
+        rb = cl_find(par, rb);
+    }
+}
+// the same over global site indices (clusters that cross tile borders)
+BC_HD uint32_t cl_gfind(volatile uint32_t* par, uint32_t a) {
+    uint32_t p = par[a];
+    while (p != a) {
+        const uint32_t gp = par[p];
+        if (gp != p) par[a] = gp;
+        a = p;
+        p = gp;
+    }
+    return a;
+}
+BC_HD void cl_gunion(uint32_t* par, uint32_t a, uint32_t b) {
+    uint32_t ra = cl_gfind(par, a), rb = cl_gfind(par, b);
+    while (ra != rb) {
+        if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
+        const uint32_t old = cl_cas32(par + ra, ra, rb);
+        if (old == ra) break;
+        ra = cl_gfind(par, old);
+        rb = cl_gfind(par, rb);
+    }
+}
+
+// ---- tile state -------------------------------------------------------------------------------------------------
+struct ClTileSmem {
+    uint16_t par[CL_SITES];       // union-find over run starts; non-run-start entries are never read
+    uint64_t plus[CL_T], minus[CL_T];
+    uint64_t rs[CL_T];            // run starts per tile row
+    uint64_t hb[CL_T];            // open bonds to the right (bit x: x -- x+1; bit w-1: into the next tile)
+    uint32_t flag[CL_SITES / 32]; // labelling: roots that touch the perimeter; flip: roots that flip
+};
+struct ClLane {                   // registers of one lane: its two tile rows 2*lane, 2*lane + 1
+    uint64_t P[2], M[2], HB[2], VB[2], RS[2];
+};
+// What a tile leaves in global memory for the kernels that follow (all tile-major)
+struct ClTileOut {
+    uint16_t* par;        // [tile][4096]  raw copy of ClTileSmem::par (run-start entries: root | CL_FLAG)
+    uint64_t* hb;         // [tile][64]
+    uint64_t* vbb;        // [tile]        open bonds from the tile's last row into the tile below
+    uint16_t* proot;      // [tile][256]   root of the perimeter sites: top row, bottom row, left column, right column
+    uint32_t* gparent;    // [replica][L*L] global union-find, touched only at the site indices of flagged roots
+};
+struct ClRng {
+    const uint32_t* thr;  // [replica] bond threshold p * 2^32 (nullptr: every candidate bond is open)
+    uint32_t k0, k1, c_lo, c_hi;
+};
+
+// ---- labelling phases (cl_label_kernel) -------------------------------------------------------------------------
+// Phase 1: masks of the lane's two rows.
+BC_HD void cl_phase_load(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1, ClTileSmem& sm,
+                         ClLane& ln) {
+    for (int i = 0; i < CL_SITES / 32 / 32; ++i) sm.flag[(CL_SITES / 32 / 32) * lane + i] = 0u;
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int r = 2 * lane + k;
+        ln.P[k] = ln.M[k] = 0;
+        if (r < t.h) cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + r, &ln.P[k], &ln.M[k]);
+        if (t.w < CL_T) { ln.P[k] &= (1ull << t.w) - 1; ln.M[k] &= (1ull << t.w) - 1; }
+        sm.plus[r] = ln.P[k];
+        sm.minus[r] = ln.M[k];
+    }
+}
+
+// Phase 2: candidate bonds (equal non-zero neighbours), random bonds, runs.
+BC_HD void cl_phase_bonds(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1, const ClRng& rng,
+                          ClTileSmem& sm, ClLane& ln) {
+    const uint32_t thr = rng.thr ? rng.thr[t.rep] : 0xFFFFFFFFu;
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int r = 2 * lane + k, gy = t.y0 + r;
+        ln.HB[k] = ln.VB[k] = ln.RS[k] = 0;
+        if (r < t.h) {
+            const uint64_t P = ln.P[k], M = ln.M[k];
+            // right neighbour of the tile's last column: the next tile's first column, or the wrap, or nothing
+            uint64_t pr = 0, mr = 0;
+            int nx = t.x0 + t.w;
+            if (nx == g.L) nx = g.open ? -1 : 0;
+            if (nx >= 0) {
+                const uint32_t c = cl_site_code(g, c0, c1, t.rep, nx, gy);
+                pr = c == 2u; mr = c == 0u;
+            }
+            uint64_t hc = (P & ((P >> 1) | (pr << (t.w - 1)))) | (M & ((M >> 1) | (mr << (t.w - 1))));
+            // row below: inside the tile from shared memory, for the tile's last row from the lattice (or the wrap)
+            uint64_t Pd = 0, Md = 0;
+            if (r + 1 < t.h) { Pd = sm.plus[r + 1]; Md = sm.minus[r + 1]; }
+            else {
+                int ny = gy + 1;
+                if (ny == g.L) ny = g.open ? -1 : 0;
+                if (ny >= 0 && ny != gy) {
+                    cl_load_row(g, c0, c1, t.rep, t.x0, ny, &Pd, &Md);
+                    if (t.w < CL_T) { Pd &= (1ull << t.w) - 1; Md &= (1ull << t.w) - 1; }
+                }
+            }
+            uint64_t vc = (P & Pd) | (M & Md);
+            if (rng.thr) {
+                hc = cl_draw_bonds(hc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 0u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+                vc = cl_draw_bonds(vc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 1u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+            }
+            ln.HB[k] = hc; ln.VB[k] = vc;
+            ln.RS[k] = (P | M) & ~(hc << 1);
+            for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
+                const uint16_t i = (uint16_t)(r * CL_T + cl_ctz64(m));
+                sm.par[i] = i;
+            }
+        }
+        sm.rs[r] = ln.RS[k];
+        sm.hb[r] = ln.HB[k];
+    }
+}
+
+// Phase 3: one union per pair of runs joined by a vertical bond (skipped when the bond to the left joins the same pair)
+BC_HD void cl_phase_unions(int lane, const ClTileId& t, ClTileSmem& sm, const ClLane& ln) {
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int r = 2 * lane + k;
+        if (r + 1 >= t.h) continue;  // the last row's bonds leave the tile
+        const uint64_t vb = ln.VB[k], rs_t = ln.RS[k], rs_d = sm.rs[r + 1];
+        for (uint64_t m = vb & ~((vb & ln.HB[k] & sm.hb[r + 1]) << 1); m; m &= m - 1) {
+            const int x = cl_ctz64(m);
+            cl_union(sm.par, (uint16_t)(r * CL_T + cl_run_start(rs_t, x)), (uint16_t)((r + 1) * CL_T + cl_run_start(rs_d, x)));
+        }
+    }
+}
+
+// Phase 4: every run start points at its root
+BC_HD void cl_phase_compress(int lane, ClTileSmem& sm, const ClLane& ln) {
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k)
+        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
+            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
+            const uint16_t root = cl_find(sm.par, i);
+            if (root != i) sm.par[i] = root;
+        }
+}
+
+// Phase 5: roots of the perimeter sites (lane l: columns 2l, 2l+1 of the top and bottom row, its own two rows of the
+// left and right column), flagged as "touches the perimeter"
+BC_HD void cl_phase_perimeter(int lane, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint16_t* proot) {
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int r = 2 * lane + k;
+        BC_UNROLL
+        for (int e = 0; e < 4; ++e) {
+            // e = 0, 1: column x = r of the top / bottom row; e = 2, 3: row y = r of the left / right column
+            const int row = e == 0 ? 0 : (e == 1 ? t.h - 1 : r), col = e < 2 ? r : (e == 2 ? 0 : t.w - 1);
+            const uint64_t occ = e < 2 ? (sm.plus[row] | sm.minus[row]) : (ln.P[k] | ln.M[k]);
+            const uint64_t rs = e < 2 ? sm.rs[row] : ln.RS[k];
+            uint16_t root = CL_NONE;
+            if (row < t.h && col < t.w && ((occ >> col) & 1ull)) {
+                root = sm.par[row * CL_T + cl_run_start(rs, col)];
+                cl_or32(&sm.flag[root >> 5], 1u << (root & 31u));
+            }
+            proot[64 * e + r] = root;
+        }
+    }
+}
+
+// Phase 6: flags into the labels; flagged roots become nodes of the global union-find
+BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint32_t* gparent_rep) {
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k)
+        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
+            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
+            const uint16_t root = sm.par[i];
+            if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
+                sm.par[i] = root | CL_FLAG;
+                if (root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
+            }
+        }
+}
+
+// ---- consumers of a labelled tile -------------------------------------------------------------------------------
+// Reload what cl_label_kernel left: labels into shared memory (done by the caller), masks and runs of the lane's rows.
+BC_HD void cl_phase_reload(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1,
+                           const uint64_t* hb_tile, ClLane& ln) {
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int r = 2 * lane + k;
+        ln.P[k] = ln.M[k] = ln.HB[k] = ln.RS[k] = 0;
+        if (r >= t.h) continue;
+        cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + r, &ln.P[k], &ln.M[k]);
+        if (t.w < CL_T) { ln.P[k] &= (1ull << t.w) - 1; ln.M[k] &= (1ull << t.w) - 1; }
+        ln.HB[k] = hb_tile[r];
+        ln.RS[k] = (ln.P[k] | ln.M[k]) & ~(ln.HB[k] << 1);
+    }
+}
+
+// smallest site of the cluster of tile-local root entry `e` (root | flag)
+BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, uint32_t* gparent_rep) {
+    const uint32_t s = cl_global_site(g, t, e & CL_IDX);
+    if (!(e & CL_FLAG)) return s;
+    const uint32_t root = cl_gfind(gparent_rep, s);
+    if (gparent_rep[s] != root) gparent_rep[s] = root;  // later lookups of this tile root take one hop
+    return root;
+}
+
+// Flip phase 1: the lane's roots decide (one Philox call serves the 128 sites around a root)
+BC_HD void cl_phase_decide(int lane, const ClGeom& g, const ClTileId& t, const ClRng& rng, ClTileSmem& sm, const ClLane& ln,
+                           uint32_t* gparent_rep) {
+    uint32_t blk = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    BC_UNROLL
+    for (int k = 0; k < 2; ++k)
+        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
+            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
+            const uint16_t e = sm.par[i];
+            if ((e & CL_IDX) != i) continue;
+            const uint32_t root = cl_cluster_site(g, t, e, gparent_rep);
+            if (cl_flip_bit(root, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep, &blk, w)) cl_or32(&sm.flag[i >> 5], 1u << (i & 31u));
+        }
+}
+
+// Flip phase 2: mask of the sites of row k of the lane whose cluster flips
+BC_HD uint64_t cl_flip_mask(int lane, int k, const ClTileSmem& sm, const ClLane& ln) {
+    uint64_t F = 0;
+    for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
+        const int x = cl_ctz64(m);
+        const uint16_t root = sm.par[(2 * lane + k) * CL_T + x] & CL_IDX;
+        if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
+            const uint64_t rest = m & (m - 1);                      // run starts behind this one
+            const uint64_t upto = rest ? ((rest & (~rest + 1)) - 1) : ~0ull;  // bits below the next run start
+            F |= upto & ~((1ull << x) - 1);
+        }
+    }
+    return F & (ln.P[k] | ln.M[k]);
+}
+
+// Flip phase 3: apply a flip mask to the 64 spin bytes of a row (code 0 <-> code 2: xor 2)
+BC_HD void cl_apply_flips(const ClGeom& g, uint8_t* c0, uint8_t* c1, uint32_t rep, int x0, int gy, uint64_t F) {
+    if (!F) return;
+    const size_t off = cl_row_offset(g, rep, gy) + (size_t)(x0 >> 1);
+    uint8_t* ev = ((gy & 1) ? c1 : c0) + off;
+    uint8_t* od = ((gy & 1) ? c0 : c1) + off;
+    const uint32_t fe = cl_squeeze(F), fo = cl_squeeze(F >> 1);
+    for (int v = 0; v < 2; ++v) {
+        const uint32_t he = (fe >> (16 * v)) & 0xFFFFu, ho = (fo >> (16 * v)) & 0xFFFFu;
+        if (he) {
+            uint4 a = *reinterpret_cast<uint4*>(ev + 16 * v);
+            a.x ^= cl_bytes(he) << 1; a.y ^= cl_bytes(he >> 4) << 1; a.z ^= cl_bytes(he >> 8) << 1; a.w ^= cl_bytes(he >> 12) << 1;
+            *reinterpret_cast<uint4*>(ev + 16 * v) = a;
+        }
+        if (ho) {
+            uint4 b = *reinterpret_cast<uint4*>(od + 16 * v);
+            b.x ^= cl_bytes(ho) << 1; b.y ^= cl_bytes(ho >> 4) << 1; b.z ^= cl_bytes(ho >> 8) << 1; b.w ^= cl_bytes(ho >> 12) << 1;
+            *reinterpret_cast<uint4*>(od + 16 * v) = b;
+        }
+    }
+}
+
+// Label phase for the measurements: the smallest site of the cluster of every site of row k of the lane
+// (0xFFFFFFFF for a zero spin) into `out` (the row's 64 entries of a row-major label array; clipped tiles: w entries)
+BC_HD void cl_row_labels(int lane, int k, const ClGeom& g, const ClTileId& t, const ClTileSmem& sm, const ClLane& ln,
+                         uint32_t* gparent_rep, uint32_t* out) {
+    uint32_t cur = 0xFFFFFFFFu;
+    const uint64_t S = ln.P[k] | ln.M[k];
+    for (int x = 0; x < t.w; ++x) {
+        if ((ln.RS[k] >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[(2 * lane + k) * CL_T + x], gparent_rep);
+        out[x] = ((S >> x) & 1ull) ? cur : 0xFFFFFFFFu;
+    }
+}
+
+}  // namespace bc

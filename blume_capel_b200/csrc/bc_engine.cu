@@ -126,14 +126,33 @@ struct bc_engine {
     unsigned* d_bar = nullptr;       // [0] arrivals, [1] generation, [2] abort
     int persist_cap[2] = {0, 0};     // resident CTAs of sweep_persist_kernel<OPEN> on this device
     unsigned graph_grid = 0;
-    // cluster move scratch
-    int32_t* d_parent = nullptr;
-    uint8_t* d_bonds = nullptr;
-    int32_t* d_csize = nullptr;             // cluster sizes per root (bc_cluster_moments), allocated on first use
+    // cluster labelling (allocated on first use): what a labelled tile leaves between kernels (bc_cluster_tile.cuh)
+    uint16_t* cl_par = nullptr;             // [tile][4096] labels
+    uint64_t* cl_hb = nullptr;              // [tile][64] open bonds to the right
+    uint64_t* cl_vbb = nullptr;             // [tile] open bonds into the tile below
+    uint16_t* cl_proot = nullptr;           // [tile][256] roots of the perimeter sites
+    uint32_t* cl_gparent = nullptr;         // [replica][L*L] global union-find over flagged tile roots (sparse)
+    uint32_t* cl_labels = nullptr;          // [replica][L*L] smallest site of every site's cluster (measurements)
+    uint32_t* d_bond_thr = nullptr;         // [replica] bond threshold p * 2^32, p = 1 - exp(-2 J / T)
+    // cluster member lists (bc_cluster_sort.cuh): sort buffers, the sorted list, per-replica counts, dump-writer arrays
+    uint2* cl_sort[2] = {nullptr, nullptr};
+    uint2* cl_list = nullptr;               // == cl_sort[k] holding the final pass
+    uint32_t* cl_sort_hist = nullptr;
+    uint32_t* cl_count = nullptr;
+    uint32_t* cl_sites = nullptr;
+    uint32_t* cl_starts = nullptr;
+    uint32_t* cl_ordinal = nullptr;
+    int8_t* cl_signs = nullptr;
+    uint32_t* cl_nclusters = nullptr;
+    unsigned long long* d_gap_hist = nullptr;
+    size_t gap_hist_cap = 0;
+    int64_t state_version = 0;              // bumped by everything that changes a lattice; keys the list cache
+    int64_t list_version = -1, list_mstep = -1, heads_version = -1, heads_mstep = -1;
+    int list_kind = -1, heads_kind = -1;
+    uint32_t* d_csize = nullptr;            // cluster sizes per root (bc_cluster_moments)
     unsigned long long* d_cmom = nullptr;   // [replica][3] moments
-    size_t cluster_cap = 0;
     int64_t cluster_step = 0;  // counter of the cluster-move RNG streams
-    std::vector<double> h_TJ;  // (T, J) per replica, for the bond probability
+    std::vector<uint32_t> h_bond_thr;
     // options
     int opt_use_graph = 1;
     int opt_graph_block = 16;  // sweeps per graph launch
@@ -237,7 +256,11 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaFree(e->d_bar);
     if (e->ev_group) cudaEventDestroy(e->ev_group);
     cudaFree(e->d_clock);
-    cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_csize); cudaFree(e->d_cmom);
+    cudaFree(e->cl_par); cudaFree(e->cl_hb); cudaFree(e->cl_vbb); cudaFree(e->cl_proot); cudaFree(e->cl_gparent);
+    cudaFree(e->cl_labels); cudaFree(e->d_bond_thr); cudaFree(e->d_csize); cudaFree(e->d_cmom);
+    cudaFree(e->cl_sort[0]); cudaFree(e->cl_sort[1]); cudaFree(e->cl_sort_hist); cudaFree(e->cl_count);
+    cudaFree(e->cl_sites); cudaFree(e->cl_starts); cudaFree(e->cl_ordinal); cudaFree(e->cl_signs); cudaFree(e->cl_nclusters);
+    cudaFree(e->d_gap_hist);
     cudaFree(e->d_wave);
     cudaFree(e->d_c[0]); cudaFree(e->d_c[1]);
     cudaFree(e->d_tab16); cudaFree(e->d_tab31); cudaFree(e->d_tab2);
@@ -294,7 +317,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     e->colour_bytes = (size_t)n_replicas * (size_t)e->rows_arr * (size_t)e->Wc;
     e->h_tab31.assign((size_t)n_replicas * TABLE_ENTRIES, 0u);
     e->params_set.assign((size_t)n_replicas, 0);
-    e->h_TJ.assign((size_t)n_replicas * 2, 0.0);
+    e->h_bond_thr.assign((size_t)n_replicas, 0u);
     auto bail = [&](const char* what, cudaError_t s) {
         g_create_error = std::string("bc_create: ") + what + ": " + cudaGetErrorString(s);
         bc_destroy(e);
@@ -310,6 +333,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_c[1], e->colour_bytes)) != cudaSuccess) return bail("cudaMalloc lattice", st);
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
+    if ((st = cudaMalloc(&e->d_bond_thr, (size_t)n_replicas * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if (L % 32 == 0 && L >= 128 &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
     if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
@@ -404,12 +428,18 @@ extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, doub
     uint16_t t16[TABLE_ENTRIES];
     build_table(T, D, J, thr, t16);
     const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? e->n_rep : replica + 1;
+    // bond probability of the cluster move, p = 1 - exp(-2 J / T) (main.cpp:115), as a 32-bit threshold
+    uint32_t bond_thr = 0;
+    {
+        const double p = 1 - std::exp(-2 * (1 / T) * J);
+        if (p > 0) { const double q = std::floor(p * 4294967296.0 + 0.5); bond_thr = q > 4294967295.0 ? 4294967295u : (uint32_t)q; }
+    }
     std::vector<uint16_t> h16((size_t)(r1 - r0) * TABLE_ENTRIES);
     for (int r = r0; r < r1; ++r) {
         std::memcpy(&e->h_tab31[(size_t)r * TABLE_ENTRIES], thr, sizeof(thr));
         std::memcpy(&h16[(size_t)(r - r0) * TABLE_ENTRIES], t16, sizeof(t16));
         e->params_set[r] = 1;
-        e->h_TJ[(size_t)r * 2] = T; e->h_TJ[(size_t)r * 2 + 1] = J;
+        e->h_bond_thr[r] = bond_thr;
     }
     // Everything on the engine's stream, in order: the two table copies, the pair-table kernel that reads the coarse
     // table, and (after the final synchronize) whatever sweep comes next.  h16 is a temporary, and a sweep launched
@@ -419,6 +449,8 @@ extern "C" int bc_set_params(bc_engine* e, int replica, double T, double D, doub
                                (size_t)(r1 - r0) * TABLE_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     BC_CUDA(e, cudaMemcpyAsync(e->d_tab16 + (size_t)r0 * TABLE_ENTRIES, h16.data(),
                                h16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+    BC_CUDA(e, cudaMemcpyAsync(e->d_bond_thr + r0, &e->h_bond_thr[(size_t)r0], (size_t)(r1 - r0) * sizeof(uint32_t),
+                               cudaMemcpyHostToDevice, e->stream));
     if (e->d_tab2) {
         const long long words = (long long)(r1 - r0) * TAB2_WORDS;
         pair_table_kernel<<<(unsigned)((words + 255) / 256), 256, 0, e->stream>>>(e->d_tab16, e->d_tab2, r0, r1 - r0);

@@ -16,7 +16,9 @@
 //   bc_sweep_resident.cuh  shared-memory-resident kernel for small lattices
 //   bc_sweep_generic.cuh   one thread per site, any L
 //   bc_util_kernels.cuh    layout conversion, init, pair tables, slab halos, stand-alone measurement
-//   bc_cluster_kernels.cuh Swendsen-Wang cluster move and cluster-size moments
+//   bc_cluster_tile.cuh    bit-parallel labelling of one 64 x 64 tile by one warp (host + device phases)
+//   bc_cluster_kernels.cuh Swendsen-Wang cluster move, cluster labels and cluster-size moments
+//   bc_cluster_sort.cuh    cluster member lists (radix sort by label), gap-size histogram, dump-writer lists
 #pragma once
 #include "bc_common.cuh"
 #include "bc_update.cuh"
@@ -28,3 +30,4 @@
 #include "bc_sweep_generic.cuh"
 #include "bc_util_kernels.cuh"
 #include "bc_cluster_kernels.cuh"
+#include "bc_cluster_sort.cuh"

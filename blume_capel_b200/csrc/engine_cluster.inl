@@ -1,128 +1,227 @@
-// engine_cluster.inl -- cluster move and cluster-size moments, bc_sync.
+// engine_cluster.inl -- cluster move, cluster labels and cluster-size moments, bc_sync.
 // Part of bc_engine.cu (included there once; not a stand-alone translation unit).
 
 // ---------------------------------------------------------------------------------------------
-// cluster move: Swendsen-Wang on the +-1 spins, all replicas
+// cluster move: Swendsen-Wang on the +-1 spins, all replicas, straight on the compact colour arrays
 // ---------------------------------------------------------------------------------------------
-// shared by the cluster move and the cluster-size measurement: stage the lattices row-major, draw the bonds
-// (threshold thr on Philox stream 3 at counter `cstep`), label connected components (root = smallest site)
-// grid of the per-site cluster kernels: x = 256-site blocks of one replica, y = replicas (stride loop beyond 65535)
-static dim3 site_grid(const bc_engine* e) {
-    const long long N = (long long)e->L * e->L;
-    return dim3((unsigned)((N + 255) / 256), (unsigned)std::min(e->n_rep, 65535));
+static int cluster_alloc(bc_engine* e) {
+    if (e->cl_par) return BC_OK;
+    const size_t tiles_1d = (size_t)(e->L + CL_T - 1) / CL_T, n_tiles = tiles_1d * tiles_1d * (size_t)e->n_rep;
+    if (n_tiles > 0x7FFFFFFFull) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: too many tiles for one launch");
+    const size_t N = (size_t)e->L * (size_t)e->L;
+    BC_CUDA(e, cudaMalloc(&e->cl_par, n_tiles * CL_SITES * sizeof(uint16_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_hb, n_tiles * CL_T * sizeof(uint64_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_vbb, n_tiles * sizeof(uint64_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_proot, n_tiles * 256 * sizeof(uint16_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_gparent, (size_t)e->n_rep * N * sizeof(uint32_t)));
+    return BC_OK;
 }
 
-static int label_clusters(bc_engine* e, uint32_t thr, int64_t cstep, bool always = false) {
-    const long long N = (long long)e->L * e->L, total = N * e->n_rep;
-    if (N > 0x7FFFFFFFLL) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: site indices are 32-bit (L <= 46340)");
-    int rc = ensure_stage(e, (size_t)total);
+static int cluster_args(bc_engine* e, const char* who, bool random_bonds, int64_t cstep, ClArgs* A) {
+    if (e->ghost && e->nranks > 1)
+        return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": not available on a slab of a multi-rank decomposition");
+    for (int r = 0; r < e->n_rep; ++r)
+        if (random_bonds && !e->params_set[r]) return fail(e, BC_ERR_STATE, std::string(who) + ": bc_set_params not called for every replica");
+    BC_CUDA(e, cudaSetDevice(e->device));
+    int rc = cluster_alloc(e);
     if (rc != BC_OK) return rc;
-    if (e->cluster_cap < (size_t)total) {
-        BC_CUDA(e, cudaStreamSynchronize(e->stream));
-        cudaFree(e->d_parent); cudaFree(e->d_bonds); cudaFree(e->d_csize);
-        e->d_parent = nullptr; e->d_bonds = nullptr; e->d_csize = nullptr; e->cluster_cap = 0;
-        BC_CUDA(e, cudaMalloc(&e->d_parent, (size_t)total * sizeof(int32_t)));
-        BC_CUDA(e, cudaMalloc(&e->d_bonds, (size_t)total));
-        e->cluster_cap = (size_t)total;
-    }
-    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
-    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
-    rc = stage_from_device(e, 0, e->n_rep);
-    if (rc != BC_OK) return rc;
-    const int tiles_x = (e->L + SW_TX - 1) / SW_TX, tiles_y = (e->L + SW_TY - 1) / SW_TY;
-    const long long ctas = (long long)tiles_x * tiles_y * e->n_rep;
-    if (ctas > 0x7FFFFFFFLL) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: too many tiles for one launch");
-    sw_local_kernel<<<(unsigned)ctas, SW_THREADS, 0, e->stream>>>(e->d_stage, e->d_bonds, e->d_parent, e->L, tiles_x, tiles_y,
-                                                                  e->boundary == BC_OPEN, always ? 1 : 0, thr, k0, k1, c_lo, c_hi);
-    sw_border_kernel<<<(unsigned)ctas, SW_TX + SW_TY, 0, e->stream>>>(e->d_bonds, e->d_parent, e->L, tiles_x, tiles_y);
+    memset(A, 0, sizeof(*A));
+    A->g.L = e->L; A->g.Wc = e->Wc; A->g.rows_arr = e->rows_arr; A->g.row_first = e->row_first;
+    A->g.open = e->boundary == BC_OPEN;
+    A->g.tiles_x = A->g.tiles_y = (e->L + CL_T - 1) / CL_T;
+    A->c0 = e->d_c[0]; A->c1 = e->d_c[1];
+    A->out.par = e->cl_par; A->out.hb = e->cl_hb; A->out.vbb = e->cl_vbb; A->out.proot = e->cl_proot; A->out.gparent = e->cl_gparent;
+    A->rng.thr = random_bonds ? e->d_bond_thr : nullptr;  // per replica: p = 1 - exp(-2 J / T) (main.cpp:115)
+    A->rng.k0 = (uint32_t)e->seed; A->rng.k1 = (uint32_t)(e->seed >> 32);
+    A->rng.c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu); A->rng.c_hi = (uint32_t)((uint64_t)cstep >> 32);
+    A->n_tiles = (uint32_t)((size_t)A->g.tiles_x * A->g.tiles_y * e->n_rep);
+    return BC_OK;
+}
+
+// labels every tile and merges the clusters across tile borders (two launches)
+static int label_clusters(bc_engine* e, const ClArgs& A) {
+    const unsigned grid = (A.n_tiles + CL_WARPS - 1) / CL_WARPS;
+    cl_label_kernel<<<grid, 32 * CL_WARPS, 0, e->stream>>>(A);
+    cl_border_kernel<<<A.n_tiles, 128, 0, e->stream>>>(A);
     e->launches += 2;
     BC_CUDA(e, cudaGetLastError());
     return BC_OK;
 }
 
-static int bond_threshold_of(bc_engine* e, const char* who, uint32_t* thr) {
-    for (int r = 0; r < e->n_rep; ++r) {
-        if (!e->params_set[r]) return fail(e, BC_ERR_STATE, std::string(who) + ": bc_set_params not called for every replica");
-        if (e->h_TJ[(size_t)r * 2] != e->h_TJ[0] || e->h_TJ[(size_t)r * 2 + 1] != e->h_TJ[1])
-            return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": all replicas of the handle must share (T, J)");
-    }
-    // bond probability p = 1 - exp(-2 J / T) (main.cpp:115) as a 32-bit threshold
-    const double p = 1 - std::exp(-2 * (1 / e->h_TJ[0]) * e->h_TJ[1]);
-    *thr = 0;
-    if (p > 0) { double q = std::floor(p * 4294967296.0 + 0.5); *thr = q > 4294967295.0 ? 4294967295u : (uint32_t)q; }
-    return BC_OK;
-}
-
 extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
     if (!e || n_updates < 0) return BC_ERR_ARG;
-    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_update: not available on a slab handle");
-    uint32_t thr = 0;
-    int rc = bond_threshold_of(e, "bc_cluster_update", &thr);
-    if (rc != BC_OK) return rc;
-    BC_CUDA(e, cudaSetDevice(e->device));
-    const long long N = (long long)e->L * e->L;
-    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     for (int64_t u = 0; u < n_updates; ++u) {
-        rc = label_clusters(e, thr, e->cluster_step);
+        ClArgs A;
+        int rc = cluster_args(e, "bc_cluster_update", true, e->cluster_step, &A);
+        if (rc == BC_OK) rc = label_clusters(e, A);
         if (rc != BC_OK) return rc;
-        const uint32_t c_lo = (uint32_t)((uint64_t)e->cluster_step & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)e->cluster_step >> 32);
-        // the bond bytes have served their purpose (border merge): the array now takes one flip bit per cluster root
-        const dim3 rgrid((unsigned)((N + 8LL * SW_ROOT_SPAN - 1) / (8LL * SW_ROOT_SPAN)), (unsigned)std::min(e->n_rep, 65535));
-        sw_rootbit_kernel<<<rgrid, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->d_bonds, e->L, e->n_rep, k0, k1, c_lo, c_hi);
-        dim3 fgrid = site_grid(e);
-        if ((N & 3) == 0) fgrid.x = (unsigned)((N / 4 + 255) / 256);  // four sites per thread
-        sw_flip_kernel<<<fgrid, 256, 0, e->stream>>>(e->d_stage, e->d_parent, e->d_bonds, e->L, e->n_rep);
-        e->launches += 2;
+        cl_flip_kernel<<<(A.n_tiles + CL_WARPS - 1) / CL_WARPS, 32 * CL_WARPS, 0, e->stream>>>(A);
+        ++e->launches;
         BC_CUDA(e, cudaGetLastError());
-        rc = stage_to_device(e, 0, e->n_rep);
-        if (rc != BC_OK) return rc;
+        if (e->ghost) { rc = exchange_both(e); if (rc != BC_OK) return rc; }  // one-rank slab: refresh its ghost rows
         ++e->cluster_step;
+        ++e->state_version;
     }
     return BC_OK;
 }
 
-// Cluster-size moments of the current configurations (consumer gamma_nu.cpp:35-60):
-// kind 0 = geometric "spin" clusters (every bond between equal non-zero neighbours, what export_clusters
-// writes to spin/ with bond probability 1, main.cpp:369-370), kind 1 = FK clusters (bond probability
-// 1 - exp(-2J/T), main.cpp:371-372; random bonds from the measurement counter `mstep`).
+// Cluster labels of the current configurations into e->cl_labels ([replica][L*L], smallest site of the cluster,
+// 0xFFFFFFFF for a zero spin): kind 0 = geometric "spin" clusters (every bond between equal non-zero neighbours, what
+// export_clusters writes to spin/ with bond probability 1, main.cpp:369-370), kind 1 = FK clusters (bond probability
+// 1 - exp(-2J/T), main.cpp:371-372; random bonds from the measurement counter 2^62 + mstep, which never collides
+// with the cluster move's counters).
+static int cluster_labels(bc_engine* e, const char* who, int kind, int64_t mstep) {
+    const size_t N = (size_t)e->L * (size_t)e->L;
+    if (N > 0xFFFFFFFFull) return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": site labels are 32-bit (L <= 32768)");
+    ClArgs A;
+    int rc = cluster_args(e, who, kind == 1, ((int64_t)1 << 62) + mstep, &A);
+    if (rc != BC_OK) return rc;
+    if (!e->cl_labels) BC_CUDA(e, cudaMalloc(&e->cl_labels, (size_t)e->n_rep * N * sizeof(uint32_t)));
+    A.labels = e->cl_labels;
+    rc = label_clusters(e, A);
+    if (rc != BC_OK) return rc;
+    cl_labels_kernel<<<(A.n_tiles + CL_WARPS - 1) / CL_WARPS, 32 * CL_WARPS, 0, e->stream>>>(A);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    return BC_OK;
+}
+
+// Cluster-size moments of the current configurations (consumer gamma_nu.cpp:35-60)
 extern "C" int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_cluster_stats* out) {
     if (!e || !out || (kind != 0 && kind != 1) || mstep < 0) return BC_ERR_ARG;
-    if (e->ghost) return fail(e, BC_ERR_UNSUPPORTED, "bc_cluster_moments: not available on a slab handle");
-    uint32_t thr = 0xFFFFFFFFu;
-    bool always = true;
-    if (kind == 1) {
-        int rc0 = bond_threshold_of(e, "bc_cluster_moments", &thr);
-        if (rc0 != BC_OK) return rc0;
-        always = false;
-    }
-    BC_CUDA(e, cudaSetDevice(e->device));
-    // measurement bonds use counters above 2^62 so that they never collide with the cluster move's stream
-    int rc = label_clusters(e, thr, ((int64_t)1 << 62) + mstep, always);
+    int rc = cluster_labels(e, "bc_cluster_moments", kind, mstep);
     if (rc != BC_OK) return rc;
     const long long N = (long long)e->L * e->L, total = N * e->n_rep;
-    if (!e->d_csize) BC_CUDA(e, cudaMalloc(&e->d_csize, e->cluster_cap * sizeof(int32_t)));
+    if (!e->d_csize) BC_CUDA(e, cudaMalloc(&e->d_csize, (size_t)total * sizeof(uint32_t)));
     if (!e->d_cmom) BC_CUDA(e, cudaMalloc(&e->d_cmom, (size_t)e->n_rep * 3 * sizeof(unsigned long long)));
-    int32_t* d_size = e->d_csize;
-    unsigned long long* d_out = e->d_cmom;
-    cudaError_t st = cudaMemsetAsync(d_size, 0, (size_t)total * sizeof(int32_t), e->stream);
-    if (st == cudaSuccess) st = cudaMemsetAsync(d_out, 0, (size_t)e->n_rep * 3 * sizeof(unsigned long long), e->stream);
+    BC_CUDA(e, cudaMemsetAsync(e->d_csize, 0, (size_t)total * sizeof(uint32_t), e->stream));
+    BC_CUDA(e, cudaMemsetAsync(e->d_cmom, 0, (size_t)e->n_rep * 3 * sizeof(unsigned long long), e->stream));
+    const dim3 cgrid((unsigned)((N + 255) / 256), (unsigned)std::min(e->n_rep, 65535));
+    cl_count_kernel<<<cgrid, 256, 0, e->stream>>>(e->cl_labels, e->d_csize, (uint32_t)N, e->n_rep);
+    cl_moments_kernel<<<(unsigned)((total + CL_MOM_PER_CTA - 1) / CL_MOM_PER_CTA), 256, 0, e->stream>>>(e->d_csize, N, e->n_rep, e->d_cmom);
+    e->launches += 2;
+    BC_CUDA(e, cudaGetLastError());
     std::vector<unsigned long long> h((size_t)e->n_rep * 3);
-    if (st == cudaSuccess) {
-        dim3 cgrid = site_grid(e);
-        if ((N & 3) == 0) cgrid.x = (unsigned)((N / 4 + 255) / 256);  // four sites per thread
-        sw_compress_kernel<<<cgrid, 256, 0, e->stream>>>(e->d_parent, e->L, e->n_rep);
-        sw_count_kernel<<<site_grid(e), 256, 0, e->stream>>>(e->d_stage, e->d_parent, d_size, e->L, e->n_rep);
-        sw_moments_kernel<<<(unsigned)((total + SW_MOM_PER_CTA - 1) / SW_MOM_PER_CTA), 256, 0, e->stream>>>(d_size, e->L, e->n_rep, d_out);
-        e->launches += 3;
-        st = cudaGetLastError();
-    }
-    if (st == cudaSuccess) st = cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
-    if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
-    if (st != cudaSuccess) return fail(e, BC_ERR_CUDA, std::string("bc_cluster_moments: ") + cudaGetErrorString(st));
+    BC_CUDA(e, cudaMemcpyAsync(h.data(), e->d_cmom, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
     for (int r = 0; r < e->n_rep; ++r) {
         out[r].sum_size_sq = (int64_t)h[(size_t)r * 3]; out[r].max_size = (int64_t)h[(size_t)r * 3 + 1];
         out[r].n_clusters = (int64_t)h[(size_t)r * 3 + 2];
     }
+    return BC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cluster member lists: the occupied sites of every replica sorted by (cluster, site)
+// ---------------------------------------------------------------------------------------------
+// Labels -> stable LSD radix sort by label (bc_cluster_sort.cuh).  Leaves e->cl_list (pairs (label, site), [replica][N])
+// and e->cl_count ([replica] occupied sites).  Cached per (lattice state, kind, mstep): bc_gap_histogram and
+// bc_cluster_lists of the same sample share one labelling and one sort.
+static int cluster_sorted_lists(bc_engine* e, const char* who, int kind, int64_t mstep) {
+    if (e->cl_list && e->list_version == e->state_version && e->list_kind == kind && e->list_mstep == mstep) return BC_OK;
+    int rc = cluster_labels(e, who, kind, mstep);
+    if (rc != BC_OK) return rc;
+    const size_t N = (size_t)e->L * (size_t)e->L;
+    const uint32_t n_chunks = (uint32_t)((N + SORT_CHUNK - 1) / SORT_CHUNK);
+    if (!e->cl_sort[0]) {
+        BC_CUDA(e, cudaMalloc(&e->cl_sort[0], (size_t)e->n_rep * N * sizeof(uint2)));
+        BC_CUDA(e, cudaMalloc(&e->cl_sort[1], (size_t)e->n_rep * N * sizeof(uint2)));
+        BC_CUDA(e, cudaMalloc(&e->cl_sort_hist, (size_t)e->n_rep * 256 * n_chunks * sizeof(uint32_t)));
+        BC_CUDA(e, cudaMalloc(&e->cl_count, (size_t)e->n_rep * sizeof(uint32_t)));
+    }
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < N) ++bits;  // labels are site indices < N
+    const int passes = (bits + 7) / 8;
+    const dim3 grid((n_chunks + SORT_WARPS - 1) / SORT_WARPS, (unsigned)e->n_rep);
+    for (int p = 0; p < passes; ++p) {
+        SortArgs A;
+        memset(&A, 0, sizeof(A));
+        A.labels = p == 0 ? e->cl_labels : nullptr;
+        A.in = p == 0 ? nullptr : e->cl_sort[(p - 1) & 1];
+        A.out = e->cl_sort[p & 1];
+        A.hist = e->cl_sort_hist; A.count_in = e->cl_count;
+        A.n = (uint32_t)N; A.cap = (uint32_t)N; A.n_chunks = n_chunks; A.shift = 8 * p;
+        sort_hist_kernel<<<grid, 32 * SORT_WARPS, 0, e->stream>>>(A);
+        scan_kernel<<<(unsigned)e->n_rep, 1024, 0, e->stream>>>(e->cl_sort_hist, 256u * n_chunks, (size_t)256 * n_chunks, e->cl_count);
+        sort_scatter_kernel<<<grid, 32 * SORT_WARPS, 0, e->stream>>>(A);
+        e->launches += 3;
+    }
+    BC_CUDA(e, cudaGetLastError());
+    e->cl_list = e->cl_sort[(passes - 1) & 1];
+    e->list_version = e->state_version; e->list_kind = kind; e->list_mstep = mstep;
+    return BC_OK;
+}
+
+// Gap-size histogram of the current configurations (gap_size_statistics.cpp:58-81,100-144 on the cluster
+// file of every sample): ADDS one sample per replica to hist[replica][bins] (variant 0: L/2 bins; 1: L-1 bins).
+extern "C" int bc_gap_histogram(bc_engine* e, int kind, int64_t mstep, int variant, int64_t* hist) {
+    if (!e || !hist || (kind != 0 && kind != 1) || (variant != 0 && variant != 1) || mstep < 0) return BC_ERR_ARG;
+    int rc = cluster_sorted_lists(e, "bc_gap_histogram", kind, mstep);
+    if (rc != BC_OK) return rc;
+    const size_t bins = variant == 0 ? (size_t)e->L / 2 : (size_t)e->L - 1, total = bins * (size_t)e->n_rep;
+    if (total == 0) return BC_OK;
+    if (e->gap_hist_cap < total) {
+        BC_CUDA(e, cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_gap_hist); e->d_gap_hist = nullptr; e->gap_hist_cap = 0;
+        BC_CUDA(e, cudaMalloc(&e->d_gap_hist, total * sizeof(unsigned long long)));
+        e->gap_hist_cap = total;
+    }
+    BC_CUDA(e, cudaMemsetAsync(e->d_gap_hist, 0, total * sizeof(unsigned long long), e->stream));
+    const size_t N = (size_t)e->L * (size_t)e->L;
+    const dim3 grid((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), (unsigned)e->n_rep);
+    gap_hist_kernel<<<grid, 256, 0, e->stream>>>(e->cl_list, e->cl_count, (uint32_t)N, e->L, variant, e->d_gap_hist);
+    ++e->launches;
+    BC_CUDA(e, cudaGetLastError());
+    std::vector<unsigned long long> h(total);
+    BC_CUDA(e, cudaMemcpyAsync(h.data(), e->d_gap_hist, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < total; ++i) hist[i] += (int64_t)h[i];
+    return BC_OK;
+}
+
+// Cluster lists of one replica for the dump writer (export_clusters, main.cpp:232-257): clusters in the order of
+// their smallest site, members ascending.  sites: the members of all clusters back to back (capacity L*L);
+// starts[c]: where cluster c begins in sites (capacity L*L + 1, starts[n_clusters] = n_sites); signs[c] = +-1.
+extern "C" int bc_cluster_lists(bc_engine* e, int replica, int kind, int64_t mstep, uint32_t* sites, uint32_t* starts,
+                                int8_t* signs, int64_t* n_sites, int64_t* n_clusters) {
+    if (!e || !sites || !starts || !signs || !n_sites || !n_clusters || (kind != 0 && kind != 1) || mstep < 0) return BC_ERR_ARG;
+    if (replica < 0 || replica >= e->n_rep) return fail(e, BC_ERR_ARG, "bc_cluster_lists: replica out of range");
+    const bool cached = e->cl_list && e->list_version == e->state_version && e->list_kind == kind && e->list_mstep == mstep &&
+                        e->heads_version == e->state_version && e->heads_kind == kind && e->heads_mstep == mstep;
+    const size_t N = (size_t)e->L * (size_t)e->L;
+    if (!cached) {
+        int rc = cluster_sorted_lists(e, "bc_cluster_lists", kind, mstep);
+        if (rc != BC_OK) return rc;
+        if (!e->cl_sites) {
+            BC_CUDA(e, cudaMalloc(&e->cl_sites, (size_t)e->n_rep * N * sizeof(uint32_t)));
+            BC_CUDA(e, cudaMalloc(&e->cl_starts, (size_t)e->n_rep * N * sizeof(uint32_t)));
+            BC_CUDA(e, cudaMalloc(&e->cl_ordinal, (size_t)e->n_rep * N * sizeof(uint32_t)));
+            BC_CUDA(e, cudaMalloc(&e->cl_signs, (size_t)e->n_rep * N));
+            BC_CUDA(e, cudaMalloc(&e->cl_nclusters, (size_t)e->n_rep * sizeof(uint32_t)));
+        }
+        const dim3 grid((unsigned)std::min<size_t>((N + 255) / 256, 148 * 8), (unsigned)e->n_rep);
+        // the ordinals of elements beyond a replica's count are never read: zero them so that the scan totals the heads
+        BC_CUDA(e, cudaMemsetAsync(e->cl_ordinal, 0, (size_t)e->n_rep * N * sizeof(uint32_t), e->stream));
+        cluster_heads_kernel<<<grid, 256, 0, e->stream>>>(e->cl_list, e->cl_count, (uint32_t)N, e->cl_ordinal);
+        scan_kernel<<<(unsigned)e->n_rep, 1024, 0, e->stream>>>(e->cl_ordinal, (uint32_t)N, N, e->cl_nclusters);
+        cluster_lists_kernel<<<grid, 256, 0, e->stream>>>(e->cl_list, e->cl_count, (uint32_t)N, e->cl_ordinal, e->d_c[0], e->d_c[1],
+                                                         e->L, e->Wc, e->rows_arr, e->row_first, e->cl_sites, e->cl_starts, e->cl_signs);
+        e->launches += 3;
+        BC_CUDA(e, cudaGetLastError());
+        e->heads_version = e->state_version; e->heads_kind = kind; e->heads_mstep = mstep;
+    }
+    uint32_t cnt = 0, ncl = 0;
+    BC_CUDA(e, cudaMemcpyAsync(&cnt, e->cl_count + replica, sizeof(cnt), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaMemcpyAsync(&ncl, e->cl_nclusters + replica, sizeof(ncl), cudaMemcpyDeviceToHost, e->stream));
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (cnt) BC_CUDA(e, cudaMemcpyAsync(sites, e->cl_sites + (size_t)replica * N, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (ncl) {
+        BC_CUDA(e, cudaMemcpyAsync(starts, e->cl_starts + (size_t)replica * N, (size_t)ncl * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        BC_CUDA(e, cudaMemcpyAsync(signs, e->cl_signs + (size_t)replica * N, (size_t)ncl, cudaMemcpyDeviceToHost, e->stream));
+    }
+    BC_CUDA(e, cudaStreamSynchronize(e->stream));
+    starts[ncl] = cnt;
+    *n_sites = cnt; *n_clusters = ncl;
     return BC_OK;
 }
 

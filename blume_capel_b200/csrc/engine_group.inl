@@ -208,6 +208,7 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
         bc_engine* e = engines[g];
         if (g > 0) BC_CUDA(e0, cudaStreamWaitEvent(e->stream, e0->ev_group, 0));
         e->t += n_sweeps;
+        if (n_sweeps > 0) ++e->state_version;
         e->pending_meas = (int64_t)e->pending_sweeps.size();
     }
     return 0;

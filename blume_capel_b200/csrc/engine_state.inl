@@ -24,6 +24,7 @@ extern "C" int bc_init_random(bc_engine* e, int replica) {
     init_kernel<<<blocks, 256, 0, e->stream>>>(e->d_c[0], e->d_c[1], geom_of(e), r0, n, (uint32_t)e->seed,
                                                (uint32_t)(e->seed >> 32));
     ++e->launches;
+    ++e->state_version;
     BC_CUDA(e, cudaGetLastError());
     return exchange_both(e);
 }
@@ -67,6 +68,7 @@ static int upload_range(bc_engine* e, int r0, int n, const int8_t* spins, bool w
     const size_t bytes = (size_t)n * e->Ly * e->L;
     int rc = ensure_stage(e, bytes);
     if (rc != BC_OK) return rc;
+    ++e->state_version;
     BC_CUDA(e, cudaMemcpyAsync(e->d_stage, spins, bytes, cudaMemcpyHostToDevice, e->stream));
     rc = stage_to_device(e, r0, n);
     if (rc != BC_OK) return rc;

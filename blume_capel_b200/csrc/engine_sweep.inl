@@ -586,6 +586,7 @@ extern "C" int64_t bc_sweep(bc_engine* e, int64_t n_sweeps, int64_t measure_ever
     e->have_timing = true;
     BC_CUDA(e, cudaGetLastError());
     e->t += n_sweeps;
+    if (n_sweeps > 0) ++e->state_version;
     e->pending_meas = n_meas;
     if (out && n_meas > 0) {
         int rc = fetch_pending(e, out);

@@ -61,6 +61,8 @@ SYMBOLS = {
     "bc_get_cluster_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_cluster_counter": (C.c_int, [_P, C.c_int64]),
     "bc_cluster_moments": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
+    "bc_gap_histogram": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, _P]),
+    "bc_cluster_lists": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bc_read_obs": (C.c_int64, [_P, _P, C.c_int64]),
     "bc_measure": (C.c_int, [_P, _P]),
     "bc_sync": (C.c_int, [_P]),
@@ -257,6 +259,24 @@ class Engine:
         buf = np.zeros(self.n_replicas, np.dtype([("sum_size_sq", "<i8"), ("max_size", "<i8"), ("n_clusters", "<i8")]))
         self._check(self._lib.bc_cluster_moments(self._h, kind, mstep, buf.ctypes.data))
         return buf
+
+    def gap_histogram(self, kind: int = 0, mstep: int = 0, variant: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Gap-size histogram of the current configurations (one sample per replica added to `out`):
+        (n_replicas, L/2) for variant 0 (the reference's), (n_replicas, L-1) for the open variant 1."""
+        bins = self.L // 2 if variant == 0 else self.L - 1
+        h = out if out is not None else np.zeros((self.n_replicas, bins), np.int64)
+        assert h.dtype == np.int64 and h.flags.c_contiguous and h.shape == (self.n_replicas, bins)
+        self._check(self._lib.bc_gap_histogram(self._h, kind, mstep, variant, h.ctypes.data))
+        return h
+
+    def cluster_lists(self, replica: int = 0, kind: int = 0, mstep: int = 0):
+        """(sites, starts, signs) of one replica's clusters, ordered like the reference's cluster files."""
+        N = self.L * self.L
+        sites, starts, signs = np.empty(N, np.uint32), np.empty(N + 1, np.uint32), np.empty(N, np.int8)
+        ns, nc = C.c_int64(), C.c_int64()
+        self._check(self._lib.bc_cluster_lists(self._h, replica, kind, mstep, sites.ctypes.data, starts.ctypes.data,
+                                               signs.ctypes.data, C.byref(ns), C.byref(nc)))
+        return sites[:ns.value].copy(), starts[:nc.value + 1].copy(), signs[:nc.value].copy()
 
     def read_obs(self, n_meas: int) -> np.ndarray:
         buf = np.zeros((n_meas, self.n_replicas), OBS_DTYPE)

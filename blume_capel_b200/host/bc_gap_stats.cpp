@@ -2,9 +2,12 @@
 //   bc_gap_stats hist out.txt L file1 [file2 ...]       CPU only: cluster files of one run -> histogram file
 //   bc_gap_stats run out_root T D J [--kind spin|fk] [--L 48,64] [--runs 100] [--samples n] [--burn-sweeps n]
 //                [--sweeps-per-sample n] [--cluster-every k] [--seed s] [--device d] [--boundary periodic|open]
-//       GPU: every run is one replica; per sample the lattice is downloaded, its clusters are formed on the host
-//       exactly as bc_run writes them, and the histogram is accumulated in memory; writes
-//       {out_root}/{L}/{run}.txt like the reference tool.
+//                [--corner out.csv]
+//       GPU: every run is one replica; per sample the clusters are labelled, sorted and walked ON THE GPU
+//       (bc_gap_histogram: no lattice download, no cluster text) and one histogram per run comes back; writes
+//       {out_root}/{L}/{run}.txt like the reference tool.  --boundary open selects the open-boundary variant of the
+//       histogram (unfolded gaps, no wrap-around gap, L-1 bins).  --corner also writes the table of
+//       gap_size_analysis.py:24-48 (Batch,L,Corner_Contribution,Error; batches of 10 runs) from the histograms.
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -16,14 +19,12 @@
 #include "gap_format.hpp"
 #include "gap_stats.hpp"
 
-static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-    for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+// gap_size_analysis.py:5-11: corner contribution of one run from its gap histogram,
+//   sum_{i < L/2} sum_{j >= i} hist[j]  /  (L^2 * nsamples)
+static double corner_contribution(const std::vector<long long>& hist, int L, long long nsamples) {
+    double tail = 0, total = 0;
+    for (size_t i = hist.size(); i-- > 0;) { tail += (double)hist[i]; total += tail; }
+    return total / ((double)L * L * (double)nsamples);
 }
 
 int main(int argc, const char* argv[]) {
@@ -50,6 +51,7 @@ int main(int argc, const char* argv[]) {
     int runs = 100, samples = 20, device = 0, kind = 0, boundary = BC_PERIODIC;
     int64_t burn = -1, sps = 30, cluster_every = 3;
     uint64_t seed = 1;
+    std::string corner_path;
     for (int i = 6; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -63,13 +65,15 @@ int main(int argc, const char* argv[]) {
         else if (a == "--seed") seed = std::strtoull(next(), nullptr, 0);
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--boundary") boundary = std::string(next()) == "open" ? BC_OPEN : BC_PERIODIC;
+        else if (a == "--corner") corner_path = next();
         else { std::cerr << "bc_gap_stats: unknown flag " << a << std::endl; return 2; }
     }
-    const double p_fk = 1 - std::exp(-2 * (1 / T) * J);
-    const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
     mkdir(out_root.c_str(), 0777);
+    const int variant = boundary == BC_OPEN ? 1 : 0;
+    std::string corner = "Batch,L,Corner_Contribution,Error\n";
     for (int L : Ls) {
         const int64_t N = (int64_t)L * L, b = burn >= 0 ? burn : 20 * N;
+        const size_t bins = variant == 0 ? (size_t)L / 2 : (size_t)L - 1;
         mkdir((out_root + "/" + std::to_string(L)).c_str(), 0777);
         bc_engine* e = nullptr;
         if (bc_create(&e, L, boundary, runs, BC_STORAGE_INT8, device, seed + (uint64_t)L) != BC_OK) {
@@ -85,30 +89,25 @@ int main(int argc, const char* argv[]) {
             }
             return true;
         };
-        std::vector<std::vector<long long>> hist((size_t)runs, std::vector<long long>((size_t)L / 2, 0));
-        std::vector<int8_t> spins((size_t)runs * N);
+        std::vector<int64_t> hist((size_t)runs * bins, 0);
         bool ok = bc_set_params(e, -1, T, D, J) == BC_OK && bc_init_random(e, -1) == BC_OK && evolve(b);
-        for (int k = 0; ok && k < samples; ++k) {
-            ok = evolve(sps) && bc_download_all(e, spins.data()) == BC_OK;
-            for (int r = 0; ok && r < runs; ++r) {
-                const int8_t* s = spins.data() + (size_t)r * N;
-                std::string text;
-                if (kind == 0) text = bcgap::spin_clusters_to_gap(s, L, boundary == BC_PERIODIC);
-                else {
-                    const uint32_t k0 = (uint32_t)(seed + (uint64_t)L), k1 = (uint32_t)((seed + (uint64_t)L) >> 32) ^ (uint32_t)r;
-                    text = bcgap::clusters_to_gap(s, L, boundary == BC_PERIODIC, [&](int64_t site, int dir) {
-                        uint32_t w[4];
-                        philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)k, (3u << 1) | (uint32_t)dir, k0, k1, w);
-                        return w[0] < thr;
-                    });
-                }
-                bcgapstats::accumulate(hist[(size_t)r], text, L);
-            }
-        }
+        for (int k = 0; ok && k < samples; ++k)  // FK bonds: measurement counter = the sample index, like bc_run's fk/ dumps
+            ok = evolve(sps) && bc_gap_histogram(e, kind, k, variant, hist.data()) == BC_OK;
         if (!ok) { std::cerr << "bc_gap_stats: " << bc_last_error(e) << std::endl; bc_destroy(e); return 1; }
         bc_destroy(e);
-        for (int r = 0; r < runs; ++r)
-            bcgap::write_file(out_root + "/" + std::to_string(L) + "/" + std::to_string(r) + ".txt", bcgapstats::run_file(hist[(size_t)r], samples));
+        std::vector<double> cc;
+        for (int r = 0; r < runs; ++r) {
+            const std::vector<long long> h(hist.begin() + (size_t)r * bins, hist.begin() + (size_t)(r + 1) * bins);
+            bcgap::write_file(out_root + "/" + std::to_string(L) + "/" + std::to_string(r) + ".txt", bcgapstats::run_file(h, samples));
+            cc.push_back(corner_contribution(h, L, samples));
+        }
+        for (size_t b0 = 0; b0 + 10 <= cc.size(); b0 += 10) {  // gap_size_analysis.py:24-48: batches of 10 runs
+            double mean = 0, var = 0;
+            for (size_t i = b0; i < b0 + 10; ++i) mean += cc[i] / 10;
+            for (size_t i = b0; i < b0 + 10; ++i) var += (cc[i] - mean) * (cc[i] - mean) / 9;
+            corner += std::to_string(b0 / 10) + "," + std::to_string(L) + "," + std::to_string(mean) + "," + std::to_string(std::sqrt(var / 10)) + "\n";
+        }
     }
+    if (!corner_path.empty()) bcgap::write_file(corner_path, corner);
     return 0;
 }

@@ -160,6 +160,9 @@ int main(int argc, const char* argv[]) {
         // burn = 0: continue the sweep counter after the nominal burn-in so that a collection run started
         // with the same --seed does not replay the random numbers the burn-in consumed
         if (burn < 1 && bc_set_sweep_counter(eng, burn_sweeps) != BC_OK) return die(eng, "bc_set_sweep_counter");
+        // ... nor the bond and flip streams of the burn-in's cluster moves
+        if (burn < 1 && cluster_every > 0 && bc_set_cluster_counter(eng, burn_sweeps / cluster_every) != BC_OK)
+            return die(eng, "bc_set_cluster_counter");
     }
 
     FILE* obs_file = nullptr;
@@ -168,30 +171,29 @@ int main(int argc, const char* argv[]) {
         if (obs_file) std::fprintf(obs_file, "sample,sweep,M,Q,B,E_per_site,m,q\n");
     }
     double sE = 0, sAm = 0, sQ = 0, sM2 = 0, sM4 = 0;
-    const double p_fk = 1 - std::exp(-2 * (1 / T) * J);  // main.cpp:371
+    std::vector<uint32_t> l_sites((size_t)N), l_starts((size_t)N + 1);
+    std::vector<int8_t> l_signs((size_t)N);
     for (int i = first_sample; i < nsteps; ++i) {
         bc_obs o;
         // measure_every = sweeps_per_sample: one fused measurement at the end of the block when aligned
         if (!evolve(sweeps_per_sample)) return die(eng, "bc_sweep");
         if (bc_measure(eng, &o) != BC_OK) return die(eng, "bc_measure");
-        if (bc_download(eng, 0, spins.data()) != BC_OK) return die(eng, "bc_download");
         const double E = (-J * (double)o.B + D * (double)o.Q) / (double)N, m = (double)o.M / (double)N,
                      q = (double)o.Q / (double)N;
         sE += E; sAm += std::fabs(m); sQ += q; sM2 += m * m; sM4 += m * m * m * m;
         if (obs_file)
             std::fprintf(obs_file, "%d,%lld,%lld,%lld,%lld,%.12g,%.12g,%.12g\n", i, (long long)o.sweep, (long long)o.M,
                          (long long)o.Q, (long long)o.B, E, m, q);
+        // the clusters are formed on the GPU (labelling + sort by cluster); the host only prints decimals
         const std::string name = std::to_string(i) + ".txt";
-        bcgap::write_file(spin_dir + name, bcgap::spin_clusters_to_gap(spins.data(), L, periodic));  // main.cpp:369-370
-        if (write_fk) {                                                                               // main.cpp:371-372
-            const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-            const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
-            auto bond = [&](int64_t site, int dir) {
-                uint32_t w[4];
-                philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)i, (3u << 1) | (uint32_t)dir, k0, k1, w);
-                return w[0] < thr;
-            };
-            bcgap::write_file(fk_dir + name, bcgap::clusters_to_gap(spins.data(), L, periodic, bond));
+        int64_t n_sites = 0, n_clusters = 0;
+        if (bc_cluster_lists(eng, 0, 0, 0, l_sites.data(), l_starts.data(), l_signs.data(), &n_sites, &n_clusters) != BC_OK)
+            return die(eng, "bc_cluster_lists");
+        bcgap::write_file(spin_dir + name, bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters));  // main.cpp:369-370
+        if (write_fk) {  // main.cpp:371-372: bonds open with probability 1 - exp(-2J/T), bond counter = the sample index
+            if (bc_cluster_lists(eng, 0, 1, i, l_sites.data(), l_starts.data(), l_signs.data(), &n_sites, &n_clusters) != BC_OK)
+                return die(eng, "bc_cluster_lists");
+            bcgap::write_file(fk_dir + name, bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters));
         }
     }
     if (obs_file) std::fclose(obs_file);

@@ -159,6 +159,8 @@ bool setup(const Options& o, Size& s) {
         }
         if (bc_upload_all(s.eng, s.spins.data()) != BC_OK) return fail(s, "bc_upload_all");
         if (bc_set_sweep_counter(s.eng, s.burn_sweeps) != BC_OK) return fail(s, "bc_set_sweep_counter");
+        if (o.cluster_every > 0 && bc_set_cluster_counter(s.eng, s.burn_sweeps / o.cluster_every) != BC_OK)
+            return fail(s, "bc_set_cluster_counter");
     }
     if (o.obs)
         for (int p = 0; p < n_points; ++p) {
@@ -171,14 +173,13 @@ bool setup(const Options& o, Size& s) {
 // after the sweeps of sample i: observables, lattices, dumps of every run
 bool record(const Options& o, Size& s, int i) {
     const long long N = (long long)s.L * s.L;
-    const bool periodic = o.boundary == BC_PERIODIC;
     if (bc_measure(s.eng, s.obs.data()) != BC_OK) return fail(s, "bc_measure");
-    if (o.dumps && bc_download_all(s.eng, s.spins.data()) != BC_OK) return fail(s, "bc_download_all");
     const std::string name = std::to_string(i) + ".txt", sL = std::to_string(s.L);
+    std::vector<uint32_t> l_sites, l_starts;
+    std::vector<int8_t> l_signs;
+    if (o.dumps) { l_sites.resize((size_t)N); l_starts.resize((size_t)N + 1); l_signs.resize((size_t)N); }
     for (int p = 0; p < (int)o.points.size(); ++p) {
         const Point& pt = o.points[(size_t)p];
-        const double p_fk = 1 - std::exp(-2 * (1 / pt.T) * o.J);  // main.cpp:371
-        const uint32_t thr = (uint32_t)std::llround(std::fmin(std::fmax(p_fk, 0.0), 1.0) * 4294967295.0);
         for (int r = 0; r < s.n_runs; ++r) {
             const int replica = p * s.n_runs + r;
             const bc_obs& ob = s.obs[(size_t)replica];
@@ -188,23 +189,20 @@ bool record(const Options& o, Size& s, int i) {
             if (s.obs_file[(size_t)p])
                 std::fprintf(s.obs_file[(size_t)p], "%d,%d,%lld,%lld,%lld,%lld\n", r, i, (long long)ob.sweep, (long long)ob.M,
                              (long long)ob.Q, (long long)ob.B);
-            if (!o.dumps) continue;
-            const int8_t* lat = &s.spins[(size_t)replica * N];
-            const std::string sRun = std::to_string(r);
-            bcgap::write_file("./" + pt.root + "/spin/" + sL + "/" + sRun + "/" + name,
-                              bcgap::spin_clusters_to_gap(lat, s.L, periodic));  // main.cpp:369-370
-            if (o.write_fk) {                                                      // main.cpp:371-372
-                const uint32_t k0 = (uint32_t)o.seed, k1 = (uint32_t)(o.seed >> 32) ^ (uint32_t)replica;  // the run's key
-                auto bond = [&](int64_t site, int dir) {
-                    uint32_t w[4];
-                    philox((uint32_t)site, (uint32_t)((uint64_t)site >> 32), (uint32_t)i, (3u << 1) | (uint32_t)dir, k0, k1, w);
-                    return w[0] < thr;
-                };
-                bcgap::write_file("./" + pt.root + "/fk/" + sL + "/" + sRun + "/" + name,
-                                  bcgap::clusters_to_gap(lat, s.L, periodic, bond));
-            }
         }
     }
+    if (!o.dumps) return true;
+    // Dumps: the clusters of every run are formed on the GPU (one labelling + one sort for the whole handle, cached
+    // by the library across the per-run fetches); the host prints decimals.  spin/ first for all runs, then fk/.
+    for (int kind = 0; kind < (o.write_fk ? 2 : 1); ++kind)
+        for (int p = 0; p < (int)o.points.size(); ++p)
+            for (int r = 0; r < s.n_runs; ++r) {
+                int64_t n_sites = 0, n_clusters = 0;
+                if (bc_cluster_lists(s.eng, p * s.n_runs + r, kind, kind ? i : 0, l_sites.data(), l_starts.data(), l_signs.data(),
+                                     &n_sites, &n_clusters) != BC_OK) return fail(s, "bc_cluster_lists");
+                bcgap::write_file("./" + o.points[(size_t)p].root + (kind ? "/fk/" : "/spin/") + sL + "/" + std::to_string(r) + "/" + name,
+                                  bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters, 1));  // main.cpp:369-372
+            }
     return true;
 }
 

@@ -11,6 +11,7 @@
 // probability 1 ("spin" clusters), same distribution for FK clusters (each same-sign bond is
 // open independently with probability p, which is what the DFS of main.cpp:179-230 samples).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -18,9 +19,55 @@
 #include <numeric>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace bcgap {
+
+// Cluster lists formed on the GPU (bc_cluster_lists: clusters in the order of their smallest site, members
+// ascending) -> the file text of export_clusters (main.cpp:236-256).  Only decimals are printed here; clusters are
+// dealt out to host threads in contiguous ranges of about equal member counts and the pieces are concatenated.
+inline std::string lists_to_gap(const uint32_t* sites, const uint32_t* starts, const int8_t* signs, int64_t n_clusters,
+                                int n_threads = 0) {
+    const int64_t n_sites = n_clusters ? (int64_t)starts[n_clusters] : 0;
+    if (n_threads <= 0) n_threads = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 1 + n_sites / 200000);
+    std::vector<std::string> piece((size_t)n_threads);
+    auto work = [&](int t) {
+        // cluster range of thread t: member offsets [t, t+1) * n_sites / n_threads, rounded to cluster starts
+        const int64_t lo_off = n_sites * t / n_threads, hi_off = n_sites * (t + 1) / n_threads;
+        const int64_t c0 = std::lower_bound(starts, starts + n_clusters, (uint32_t)lo_off) - starts;
+        const int64_t c1 = t + 1 == n_threads ? n_clusters : std::lower_bound(starts, starts + n_clusters, (uint32_t)hi_off) - starts;
+        std::string& out = piece[(size_t)t];
+        if (c1 > c0) out.reserve((size_t)(starts[c1] - starts[c0]) * 3 + (size_t)(c1 - c0) * 4 + 16);
+        char buf[16];
+        for (int64_t c = c0; c < c1; ++c) {
+            out += signs[c] > 0 ? "+ " : "- ";
+            uint32_t prev = 0;
+            for (uint32_t k = starts[c]; k < starts[c + 1]; ++k) {
+                uint32_t v = sites[k] - prev;  // members ascend from 0
+                char* e = buf + sizeof buf;
+                *--e = ' ';
+                do { *--e = (char)('0' + v % 10); v /= 10; } while (v);
+                out.append(e, (size_t)(buf + sizeof buf - e));
+                prev = sites[k];
+            }
+            out += '\n';
+        }
+    };
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    size_t total = 1;
+    for (const auto& x : piece) total += x.size();
+    std::string out;
+    out.reserve(total);
+    for (const auto& x : piece) out += x;
+    out += '\n';  // `file << lines << endl` (main.cpp:255)
+    return out;
+}
 
 struct UnionFind {
     std::vector<int32_t> parent;

@@ -1,21 +1,9 @@
 // host_util.hpp -- small helpers shared by the host drivers (bc_run, bc_runner).
 #pragma once
-#include <cstdint>
 #include <string>
 #include <sys/stat.h>
 
 namespace {
-
-// Philox4x32-10 on the host, for the FK bond variables only (stream 3 of the engine's key space).
-void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-    for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
 
 // mkdir -p
 void mkdirs(const std::string& path) {

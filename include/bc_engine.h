@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BC_ABI_VERSION 1
+#define BC_ABI_VERSION 2
 
 typedef struct bc_engine bc_engine; /* opaque */
 
@@ -150,7 +150,8 @@ int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int64_t n_sweep
  * main.cpp:113-154,158-163): n_updates Swendsen-Wang updates of every replica -- bonds between equal non-zero
  * neighbours with probability 1 - exp(-2J/T) (main.cpp:115; zeros never join, main.cpp:123-130,144), every
  * cluster flipped with probability 1/2.  Same stationary distribution as the reference's Wolff move, all
- * clusters at once instead of one.  All replicas of the handle must share (T, J).  Has its own RNG counter. */
+ * clusters at once instead of one.  Every replica uses its own bond probability (a handle may hold a (T, D) grid);
+ * available on plain handles and on one-rank slab handles.  Has its own RNG counter. */
 int bc_cluster_update(bc_engine* e, int64_t n_updates);
 int bc_get_cluster_counter(const bc_engine* e, int64_t* c);
 int bc_set_cluster_counter(bc_engine* e, int64_t c);
@@ -165,6 +166,24 @@ typedef struct {
     int64_t n_clusters;
 } bc_cluster_stats;
 int bc_cluster_moments(bc_engine* e, int kind, int64_t mstep, bc_cluster_stats* out);
+
+/* Gap-size histogram of the current configurations on the GPU: what
+ * corner_contribution/gap_size_statistics.cpp:58-81,100-144 derives from the cluster file of one sample, quirks
+ * included (the walk starts at the ROW of a cluster's first site and never records that site, :104-106), for the
+ * spin (kind 0) or FK (kind 1, bonds at measurement counter mstep) clusters of every replica.  ADDS one sample per
+ * replica to hist[replica][bins]: variant 0 = the reference's (gaps folded to min(gap, L - gap), wrap-around gap,
+ * L/2 bins, bin g-1 counts gaps of size g); variant 1 = open-boundary variant, new relative to the reference
+ * (unfolded gaps, no wrap-around gap, L-1 bins).  Input of gap_size_analysis.py:5-11. */
+int bc_gap_histogram(bc_engine* e, int kind, int64_t mstep, int variant, int64_t* hist);
+
+/* Cluster lists of one replica, formed on the GPU, for the dump writer: replaces form_clusters + the per-cluster
+ * sort of export_clusters (main.cpp:179-230, 236-239).  Clusters come in the order of their smallest site and
+ * their members ascend, exactly the order of the reference's files.  sites: members of all clusters back to back
+ * (capacity L*L); starts[c]: offset of cluster c in sites (capacity L*L + 1; starts[n_clusters] = n_sites);
+ * signs[c] = +1 / -1 (capacity L*L).  kind / mstep as in bc_cluster_moments (spin/ files: kind 0; fk/ files: kind 1
+ * with mstep = the sample index).  The labelling and the sort are cached per (lattice state, kind, mstep). */
+int bc_cluster_lists(bc_engine* e, int replica, int kind, int64_t mstep, uint32_t* sites, uint32_t* starts,
+                     int8_t* signs, int64_t* n_sites, int64_t* n_clusters);
 
 /* Fetch the records of the last bc_sweep that was called with out == NULL (waits for it).
  * Returns the number of records written or a negative status. */

@@ -219,6 +219,36 @@ static int32_t uf_find(int32_t* parent, int32_t a) {
     return a;
 }
 
+/* Bond uniform of site (x, y) in direction dir (0 = +x, 1 = +y) at cluster counter cstep, spec v2: the 32 sites
+ * x = 32g .. 32g+31 of a row share 32 "bit-plane" words; plane b (b = 0 is the most significant bit) is word b&3 of
+ * Philox(counter = (y << 15 | g << 4 | dir << 3 | b >> 2, cstep_lo, cstep_hi, BC_STREAM_BOND << 1)), and
+ * u(x) = sum_b bit_(x&31)(plane b) << (31 - b).  The bond is open iff u < thr.  (A GPU thread evaluates 32 bonds at
+ * once, most significant plane first, and stops drawing planes when every bond is decided: about two Philox calls
+ * per 32 bonds instead of sixteen.)  Evaluated here exactly like that definition, one bond at a time. */
+static int bond_open(const uint32_t key[2], int x, int y, int dir, int64_t cstep, uint32_t thr) {
+    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 32; ++b) {
+        if ((b & 3) == 0) {
+            uint32_t ctr[4] = {((uint32_t)y << 15) | ((uint32_t)(x >> 5) << 4) | ((uint32_t)dir << 3) | (uint32_t)(b >> 2),
+                               c_lo, c_hi, BC_STREAM_BOND << 1};
+            bc_oracle_philox4x32_10(ctr, key, w);
+        }
+        const uint32_t ubit = (w[b & 3] >> (x & 31)) & 1u, tbit = (thr >> (31 - b)) & 1u;
+        if (ubit != tbit) return ubit < tbit;
+    }
+    return 0; /* u == thr */
+}
+
+/* flip decision of the cluster whose smallest site index is `root`: bit root&31 of word (root>>5)&3 of
+ * Philox(counter = (root >> 7, cstep_lo, cstep_hi, BC_STREAM_FLIP << 1)) */
+static int cluster_flips(const uint32_t key[2], uint32_t root, int64_t cstep) {
+    uint32_t ctr[4] = {root >> 7, (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), (uint32_t)((uint64_t)cstep >> 32),
+                       BC_STREAM_FLIP << 1}, w[4];
+    bc_oracle_philox4x32_10(ctr, key, w);
+    return (int)((w[(root >> 5) & 3u] >> (root & 31u)) & 1u);
+}
+
 /* union-find over the open bonds; parent[] ends up holding the smallest site index of each cluster */
 static int32_t* label_clusters(int L, int boundary, const int8_t* spins, int always, uint32_t bond_thr, uint64_t seed,
                                uint32_t replica, int64_t cstep) {
@@ -227,14 +257,11 @@ static int32_t* label_clusters(int L, int boundary, const int8_t* spins, int alw
     uint32_t key[2];
     site_key(seed, replica, key);
     for (int64_t i = 0; i < N; ++i) parent[i] = (int32_t)i;
-    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
     for (int y = 0; y < L; ++y)
         for (int x = 0; x < L; ++x) {
             const int64_t i = x + (int64_t)y * L;
             const int8_t s = spins[i];
-            if (s == 0) continue;
-            uint32_t ctr[4] = {(uint32_t)(i >> 1), c_lo, c_hi, BC_STREAM_BOND << 1}, w[4] = {0, 0, 0, 0};
-            if (!always) bc_oracle_philox4x32_10(ctr, key, w);
+            if (s == 0) continue; /* zeros never join a cluster (main.cpp:123-130,144) */
             for (int dir = 0; dir < 2; ++dir) {
                 int nx = x + (dir == 0), ny = y + (dir == 1);
                 if (nx == L || ny == L) {
@@ -243,7 +270,7 @@ static int32_t* label_clusters(int L, int boundary, const int8_t* spins, int alw
                 }
                 const int64_t j = nx + (int64_t)ny * L;
                 if (j == i || spins[j] != s) continue;
-                if (always || w[2 * (i & 1) + dir] < bond_thr) {
+                if (always || bond_open(key, x, y, dir, cstep, bond_thr)) {
                     int32_t a = uf_find(parent, (int32_t)i), b = uf_find(parent, (int32_t)j);
                     if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; } /* root = smallest site */
                 }
@@ -259,14 +286,81 @@ void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_
     int32_t* parent = label_clusters(L, boundary, spins, 0, bond_thr, seed, replica, cstep);
     uint32_t key[2];
     site_key(seed, replica, key);
-    const uint32_t c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), c_hi = (uint32_t)((uint64_t)cstep >> 32);
     for (int64_t i = 0; i < N; ++i) {
         if (spins[i] == 0) continue;
-        uint32_t ctr[4] = {(uint32_t)parent[i], c_lo, c_hi, BC_STREAM_FLIP << 1}, w[4];
-        bc_oracle_philox4x32_10(ctr, key, w);
-        if (w[0] & 1u) spins[i] = (int8_t)-spins[i];
+        if (cluster_flips(key, (uint32_t)parent[i], cstep)) spins[i] = (int8_t)-spins[i];
     }
     free(parent);
+}
+
+void bc_oracle_cluster_labels(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                              uint32_t replica, int64_t mstep, int32_t* labels) {
+    const int64_t N = (int64_t)L * L;
+    int32_t* parent = label_clusters(L, boundary, spins, kind == 0, bond_thr, seed, replica, ((int64_t)1 << 62) + mstep);
+    for (int64_t i = 0; i < N; ++i) labels[i] = spins[i] ? parent[i] : -1;
+    free(parent);
+}
+
+/* Gap-size histogram of the clusters of one configuration, what corner_contribution/gap_size_statistics.cpp derives
+ * from one cluster file (get_sample_gap_sizes, :128-144), restated on the labelled lattice.  A cluster file line is
+ * the cluster's sites ascending (main.cpp:236-256); the tool walks it as follows, quirks included:
+ *   - the walk starts at posn = first_site / L -- the ROW of the first site, not its column (:104) -- and the first
+ *     site itself is never recorded (:106 starts at i = 1);
+ *   - posn += delta; when posn >= L the collected "row" is closed (kept only if it holds more than one entry) and
+ *     posn %= L (:108-118).  Equivalently: the sites s of the cluster are shifted to s' = s - first + first / L and
+ *     grouped by s' / L, with in-row position s' % L;
+ *   - per kept row: the gaps between consecutive entries, each folded to min(gap, L - gap), plus the wrap-around gap
+ *     last - first; a row of exactly two entries contributes its one gap only (:58-81); bin gap - 1.
+ * variant 0 = the reference's (periodic: hist has L/2 bins); variant 1 = open-boundary variant, new relative to the
+ * reference (no folding and no wrap-around gap: hist has L - 1 bins). */
+static void close_row(int64_t* hist, const int64_t* row, int64_t n, int L, int variant) {
+    if (n < 2) return;
+    if (variant == 1) {
+        for (int64_t i = 0; i + 1 < n; ++i) ++hist[row[i + 1] - row[i] - 1];
+        return;
+    }
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        int64_t gap = row[i + 1] - row[i];
+        if (L - gap < gap) gap = L - gap;
+        ++hist[gap - 1];
+    }
+    if (n > 2) {
+        int64_t gap = row[n - 1] - row[0];
+        if (L - gap < gap) gap = L - gap;
+        ++hist[gap - 1];
+    }
+}
+
+void bc_oracle_gap_histogram(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                             uint32_t replica, int64_t mstep, int variant, int64_t* hist) {
+    const int64_t N = (int64_t)L * L;
+    int32_t* parent = label_clusters(L, boundary, spins, kind == 0, bond_thr, seed, replica, ((int64_t)1 << 62) + mstep);
+    /* members of every cluster in ascending order: counting sort by root (roots are smallest sites) */
+    int64_t* start = (int64_t*)calloc((size_t)N + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < N; ++i) if (spins[i]) ++start[parent[i] + 1];
+    for (int64_t i = 0; i < N; ++i) start[i + 1] += start[i];
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)N);
+    int32_t* member = (int32_t*)malloc(sizeof(int32_t) * (size_t)(start[N] > 0 ? start[N] : 1));
+    memcpy(fill, start, sizeof(int64_t) * (size_t)N);
+    for (int64_t i = 0; i < N; ++i) if (spins[i]) member[fill[parent[i]]++] = (int32_t)i;
+    int64_t* row = (int64_t*)malloc(sizeof(int64_t) * (size_t)L);
+    for (int64_t r = 0; r < N; ++r) {
+        const int64_t n = start[r + 1] - start[r];
+        if (n == 0) continue;
+        const int32_t* m = member + start[r];
+        int64_t posn = m[0] / L, in_row = 0; /* gap_size_statistics.cpp:104 */
+        for (int64_t i = 1; i < n; ++i) {
+            posn += m[i] - m[i - 1];
+            if (posn >= L) {
+                close_row(hist, row, in_row, L, variant);
+                in_row = 0;
+                posn %= L;
+            }
+            row[in_row++] = posn;
+        }
+        close_row(hist, row, in_row, L, variant);
+    }
+    free(row); free(member); free(fill); free(start); free(parent);
 }
 
 /* sum size^2, max size, number of clusters (what gamma_nu.cpp:35-60 derives from a cluster file);

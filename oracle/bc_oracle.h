@@ -79,17 +79,26 @@ void bc_oracle_half_sweep_rows(int L, int boundary, int8_t* spins, const uint32_
 
 /* Cluster move (Swendsen-Wang on the +-1 spins; zeros never join, like wolff() main.cpp:113-154):
  * bond between equal non-zero neighbours open with probability p = 1 - exp(-2J/T) (main.cpp:115), every
- * cluster (identified by its smallest site index) flipped with probability 1/2.  Philox streams 3 (bonds:
- * counter (i>>1, cstep_lo, cstep_hi, 3<<1), word 2*(i&1)+dir, dir 0 = +x, 1 = +y) and 4 (flips: counter
- * (cluster id, cstep_lo, cstep_hi, 4<<1), bit 0 of word 0).  NEW relative to the reference (which grows one
- * Wolff cluster at a time from a non-reproducible RNG); same stationary distribution. */
+ * cluster (identified by its smallest site index) flipped with probability 1/2.  Philox streams 3 (bonds) and 4
+ * (flips); spec v2, bit-plane bond uniforms: see bond_open() / cluster_flips() in bc_oracle.c and DESIGN.md.
+ * NEW relative to the reference (which grows one Wolff cluster at a time from a non-reproducible RNG); same
+ * stationary distribution. */
 #define BC_STREAM_FLIP 4u
 uint32_t bc_oracle_bond_threshold(double T, double J);
 void bc_oracle_cluster_update(int L, int boundary, int8_t* spins, uint32_t bond_thr, uint64_t seed, uint32_t replica,
                               int64_t cstep);
 
+/* kind 0 = geometric "spin" clusters (the content of spin/ files, main.cpp:369-370), kind 1 = FK clusters (bond
+ * probability p, main.cpp:371-372, bonds at counter 2^62 + mstep). */
 void bc_oracle_cluster_moments(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
                                uint32_t replica, int64_t mstep, int64_t out[3]);
+/* labels[i] = smallest site index of the cluster of site i, -1 for a zero spin */
+void bc_oracle_cluster_labels(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                              uint32_t replica, int64_t mstep, int32_t* labels);
+/* gap-size histogram of one configuration (corner_contribution/gap_size_statistics.cpp:58-81,100-144); ADDS to hist:
+ * variant 0: L/2 bins (the reference's, folded gaps + wrap-around gap), variant 1: L-1 bins (open variant) */
+void bc_oracle_gap_histogram(int L, int boundary, const int8_t* spins, int kind, uint32_t bond_thr, uint64_t seed,
+                             uint32_t replica, int64_t mstep, int variant, int64_t* hist);
 
 /* Counts ties (coarse 15-bit draw equal to coarse threshold) seen since last reset; diagnostics. */
 int64_t bc_oracle_tie_count(int reset);

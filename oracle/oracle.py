@@ -53,6 +53,10 @@ def lib():
         l.bc_oracle_cluster_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64]
         l.bc_oracle_cluster_moments.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32,
                                                 C.c_int64, C.c_void_p]
+        l.bc_oracle_cluster_labels.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32,
+                                               C.c_int64, C.c_void_p]
+        l.bc_oracle_gap_histogram.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32,
+                                              C.c_int64, C.c_int, C.c_void_p]
         _lib = l
     return _lib
 
@@ -147,3 +151,23 @@ def cluster_moments(spins, kind, T, J, seed, replica=0, mstep=0, boundary=PERIOD
     lib().bc_oracle_cluster_moments(s.shape[0], boundary, s.ctypes.data, kind, bond_threshold(T, J), seed, replica, mstep,
                                     out.ctypes.data)
     return tuple(int(x) for x in out)
+
+
+def cluster_labels(spins, kind, T, J, seed, replica=0, mstep=0, boundary=PERIODIC):
+    """Smallest site index of every site's cluster (-1 for zero spins); kind 0 = spin clusters, 1 = FK clusters."""
+    s = np.ascontiguousarray(spins, np.int8)
+    out = np.zeros(s.shape, np.int32)
+    lib().bc_oracle_cluster_labels(s.shape[0], boundary, s.ctypes.data, kind, bond_threshold(T, J), seed, replica, mstep,
+                                   out.ctypes.data)
+    return out
+
+
+def gap_histogram(spins, kind, T, J, seed, replica=0, mstep=0, boundary=PERIODIC, variant=0):
+    """Gap-size histogram of one configuration as gap_size_statistics.cpp derives it from a cluster file
+    (variant 0: L/2 bins; variant 1 = open variant: L-1 bins, no folding, no wrap-around gap)."""
+    s = np.ascontiguousarray(spins, np.int8)
+    L = s.shape[0]
+    hist = np.zeros(L // 2 if variant == 0 else L - 1, np.int64)
+    lib().bc_oracle_gap_histogram(L, boundary, s.ctypes.data, kind, bond_threshold(T, J), seed, replica, mstep, variant,
+                                  hist.ctypes.data)
+    return hist

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported_and_bound(bc):
 
 
 def test_abi_version(bc):
-    assert bc.load_library().bc_abi_version() == 1
+    assert bc.load_library().bc_abi_version() == 2
 
 
 def test_no_torch_types_or_cpp_in_header():
@@ -109,4 +109,4 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-o", str(exe), str(src), "-L", lib_dir, "-lbc_engine", f"-Wl,-rpath,{lib_dir}"], check=True,
                    capture_output=True, text=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.split()[0] == "1"
+    assert r.returncode == 0 and r.stdout.split()[0] == "2"

@@ -92,18 +92,68 @@ def test_metropolis_plus_cluster_statistics_L4(bc):
     assert np.all(np.abs(mean - exact) < 5 * err + 5e-4), (mean, err)
 
 
+def test_cluster_update_per_replica_temperatures(bc, oracle):
+    """BASELINE config 3 is an 8 x 8 (T, D) grid: every replica of a handle has its own bond probability
+    1 - exp(-2J/T) (main.cpp:115), so the cluster move works on a ladder handle with 8 distinct temperatures."""
+    L, n_rep, seed = 128, 8, 0x7E3
+    Ts = np.linspace(0.58, 0.64, n_rep)
+    e = bc.Engine(L, 0, n_rep, 0, seed)
+    for r, T in enumerate(Ts):
+        e.set_params(float(T), 1.94 + 0.005 * r, 1.0, replica=r)
+    e.init_random()
+    ref = np.stack([oracle.init_random(L, seed, r) for r in range(n_rep)])
+    for step in range(2):
+        e.sweep(3)
+        e.cluster_update(1)
+        for r, T in enumerate(Ts):
+            oracle.sweep(ref[r], oracle.build_table(float(T), 1.94 + 0.005 * r, 1.0), seed, r, 3 * step, 3, 0, 0)
+            oracle.cluster_update(ref[r], float(T), 1.0, seed, r, step, 0)
+    assert np.array_equal(e.download(), ref)
+    e.close()
+
+
+@pytest.mark.parametrize("boundary", [0, 1])
+def test_cluster_update_on_a_one_rank_slab(bc, oracle, boundary):
+    """Slab handles (ghost rows in the colour arrays) take the cluster move when they hold the whole lattice."""
+    L, seed, T = 192, 0x51AB, 0.608
+    e = bc.Engine(L, boundary, 1, 0, seed, slab=(1, 0, None))
+    e.set_params(T, 1.966, 1.0)
+    e.init_random()
+    ref = oracle.init_random(L, seed, 0)
+    tab = oracle.build_table(T, 1.966, 1.0)
+    for step in range(2):
+        e.cluster_update(1)
+        e.sweep(2)  # reads the ghost rows the cluster move has to refresh
+        oracle.cluster_update(ref, T, 1.0, seed, 0, step, boundary)
+        oracle.sweep(ref, tab, seed, 0, 2 * step, 2, 0, boundary)
+    assert np.array_equal(e.download(0), ref)
+    e.close()
+
+
+def test_cluster_update_full_size(bc, oracle):
+    """L = 4096 (4096 tiles, clusters across thousands of tile borders) against the oracle."""
+    L, seed, T = 4096, 0xF00D, 0.608
+    e = bc.Engine(L, 0, 1, 0, seed)
+    e.set_params(T, 1.966, 1.0)
+    e.init_random()
+    e.sweep(20)
+    s = e.download(0)
+    e.cluster_update(1)
+    ref = s.copy()
+    oracle.cluster_update(ref, T, 1.0, seed, 0, 0, 0)
+    assert np.array_equal(e.download(0), ref)
+    want = oracle.cluster_moments(ref, 1, T, 1.0, seed, 0, 2, 0)
+    got = e.cluster_moments(1, mstep=2)[0]
+    assert (got["sum_size_sq"], got["max_size"], got["n_clusters"]) == want
+    e.close()
+
+
 def test_cluster_update_errors(bc):
     e = bc.Engine(32, 0, 2, 0, 1)
     e.set_params(1.0, 0.0, 1.0, replica=0)
-    e.set_params(2.0, 0.0, 1.0, replica=1)
     with pytest.raises(bc.BCError):
-        e.cluster_update(1)  # replicas at different T
+        e.cluster_update(1)  # parameters of replica 1 not set
     e.close()
-    s = bc.Engine(64, 0, 1, 0, 1, slab=(1, 0, None))
-    s.set_params(1.0, 0.0, 1.0)
-    with pytest.raises(bc.BCError):
-        s.cluster_update(1)
-    s.close()
 
 
 def test_cluster_moves_match_the_committed_vectors(bc):

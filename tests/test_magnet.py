@@ -20,16 +20,44 @@ def test_table_is_byte_identical_to_the_reference_tool(tmp_path):
 
 
 @pytest.mark.gpu
-def test_bc_magnet_on_gpu(tmp_path):
+def test_bc_magnet_on_gpu_is_byte_identical_to_the_reference_tool(tmp_path):
+    """bc_magnet's table from the fused magnetisations of a GPU run == the table the UNMODIFIED magnet binary
+    (oracle/_ref/magnet, built from corner_contribution/magnet.cpp) prints from the cluster files of the very same
+    samples: the run is repeated through the Python binding with bc_magnet's seeds and sweep schedule
+    (bc_magnet.cpp: seed + L, burn, counter aligned to the sample spacing), every sample of every run is written
+    as a spin/ cluster file, and the reference tool reads them (its hard-wired 100 runs of L = 48 and 64)."""
+    import numpy as np
+    import blume_capel_b200 as bc
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "magnet")
+    gaptool = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gaptool")
+    if not os.access(ref_tool, os.X_OK):
+        pytest.skip("oracle/_ref/magnet not built")
+    runs, samples, burn, sps, seed = 100, 3, 60, 20, 5
     out = tmp_path / "chi.csv"
-    subprocess.run([TOOL, str(out), "0.608", "1.966", "1.0", "--L", "32,64", "--runs", "20", "--samples", "30",
-                    "--burn-sweeps", "2000", "--sweeps-per-sample", "200", "--seed", "5"], check=True)
+    subprocess.run([TOOL, str(out), "0.608", "1.966", "1.0", "--L", "48,64", "--runs", str(runs), "--samples", str(samples),
+                    "--burn-sweeps", str(burn), "--sweeps-per-sample", str(sps), "--seed", str(seed)], check=True)
+    inp = tmp_path / "in"
+    for L in (48, 64):
+        e = bc.Engine(L, 0, runs, 0, seed + L)
+        e.set_params(0.608, 1.966, 1.0)
+        e.init_random()
+        e.sweep(burn)
+        e.sweep_counter = (burn + sps - 1) // sps * sps
+        for k in range(samples):
+            e.sweep(sps)
+            s = e.download()
+            for r in range(runs):
+                d = inp / str(L) / str(r)
+                d.mkdir(parents=True, exist_ok=True)
+                raw = tmp_path / "l.bin"
+                raw.write_bytes(s[r].tobytes())
+                subprocess.run([gaptool, "write", str(L), "periodic", str(raw), str(d / f"{k}.txt")], check=True)
+        e.close()
+    want = tmp_path / "ref.csv"
+    subprocess.run([ref_tool, str(inp), str(want)], check=True)
     rows = out.read_text().strip().splitlines()
-    assert rows[0] == "batch,L,magnetic_susceptibility,standard_error"
-    assert len(rows) == 1 + 2 * 2
-    for r in rows[1:]:
-        b, L, chi, err = r.split(",")
-        assert int(L) in (32, 64) and float(chi) > 0 and float(err) >= 0
+    assert rows[0] == "batch,L,magnetic_susceptibility,standard_error" and len(rows) == 1 + 2 * 10
+    assert out.read_bytes() == want.read_bytes()
 
 
 GAMMA_TOOL = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gamma_nu")
@@ -100,13 +128,3 @@ def test_gap_histogram_is_byte_identical_to_the_reference_tool(tmp_path):
         out = tmp_path / f"{key}.out"
         subprocess.run([tool, "hist", str(out), str(L)] + files, check=True)
         assert out.read_text() == expected, key
-
-
-@pytest.mark.gpu
-def test_bc_gap_stats_on_gpu(tmp_path):
-    tool = os.path.join(ROOT, "blume_capel_b200", "host", "bc_gap_stats")
-    subprocess.run([tool, "run", str(tmp_path / "gap"), "0.608", "1.966", "1.0", "--L", "48", "--runs", "6", "--samples", "4",
-                    "--burn-sweeps", "200", "--kind", "spin", "--seed", "2"], check=True)
-    for r in range(6):
-        rows = (tmp_path / "gap" / "48" / f"{r}.txt").read_text().split("\n")
-        assert rows[0] == "4" and len(rows[1].split()) == 24 and sum(map(int, rows[1].split())) > 0
