@@ -6,4 +6,4 @@ tests, bench.py and the Python examples; the C++ command-line driver with the
 reference's argv (``run root burn nsteps T D J``, /root/reference/main.cpp:316-324)
 lives in host/.
 """
-from .engine import Engine, BCError, Obs, load_library, library_path, slab_unique_id, sweep_group, PERIODIC, OPEN  # noqa: F401
+from .engine import Engine, BCError, Obs, load_library, library_path, slab_unique_id, sweep_group, pack_spins, unpack_spins, PERIODIC, OPEN  # noqa: F401

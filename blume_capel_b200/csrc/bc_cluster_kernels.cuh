@@ -3,10 +3,10 @@
 //
 // Cluster move (all clusters of the +-1 spins at once; zeros never join, like wolff() of main.cpp:113-154; bond
 // probability 1 - exp(-2J/T), main.cpp:115) in three launches, straight on the compact colour arrays:
-//   cl_label_kernel   one warp per 64 x 64 tile: row masks, random bonds, runs, unions in shared memory
+//   cl_label_kernel   64 threads per 64 x 64 tile: row masks, random bonds, runs, unions in shared memory
 //                     (bc_cluster_tile.cuh); leaves 2 B / site of labels + 1 KB of masks and perimeter roots per tile
 //   cl_border_kernel  one thread per bond that leaves a tile: global union-find over the flagged tile roots
-//   cl_flip_kernel    one warp per tile: one flip bit per cluster (keyed by the cluster's smallest site), flip masks
+//   cl_flip_kernel    64 threads per tile: one flip bit per cluster (keyed by the cluster's smallest site), flip masks
 //                     per row, spin bytes rewritten in place
 // Algorithmic traffic per site: 1 B spins read + 2 B labels written; 2 B labels + 1 B spins read, < 1 B spins
 // written: about 7 B / site (round 1: about 22 B / site through a row-major staging copy and int32 labels).
@@ -15,8 +15,6 @@
 #include "bc_common.cuh"
 
 namespace bc {
-
-constexpr int CL_WARPS = 2;  // tiles per CTA (one warp each; the warps of a CTA never synchronise with each other)
 
 struct ClArgs {
     ClGeom g;
@@ -28,36 +26,30 @@ struct ClArgs {
     uint32_t* labels;      // cl_labels_kernel: [replica][L*L] smallest site of the cluster, 0xFFFFFFFF for a zero spin
 };
 
-__global__ void __launch_bounds__(32 * CL_WARPS) cl_label_kernel(const __grid_constant__ ClArgs A) {
-    __shared__ __align__(16) ClTileSmem s_tiles[CL_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * CL_WARPS + warp;
-    if (tile >= A.n_tiles) return;
-    ClTileSmem& sm = s_tiles[warp];
+// One CTA of 64 threads per tile, thread l = tile row l (10.75 KB of shared memory: 21 tiles per SM)
+__global__ void __launch_bounds__(CL_LANES) cl_label_kernel(const __grid_constant__ ClArgs A) {
+    __shared__ __align__(16) ClTileSmem sm;
+    const int lane = threadIdx.x;
+    const uint32_t tile = blockIdx.x;
     const ClTileId t = cl_tile_id(A.g, tile);
     ClLane ln;
     cl_phase_load(lane, A.g, t, A.c0, A.c1, sm, ln);
-    __syncwarp();
+    __syncthreads();
     cl_phase_bonds(lane, A.g, t, A.c0, A.c1, A.rng, sm, ln);
-    __syncwarp();
+    __syncthreads();
     cl_phase_unions(lane, t, sm, ln);
-    __syncwarp();
-    cl_phase_compress(lane, sm, ln);
-    __syncwarp();
+    __syncthreads();
     cl_phase_perimeter(lane, t, sm, ln, A.out.proot + (size_t)tile * 256);
-    __syncwarp();
+    __syncthreads();
     cl_phase_finish(lane, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);
-    __syncwarp();
+    __syncthreads();
     // what the following kernels need: labels (raw 8 KB copy), bond masks of the rows, bonds into the tile below
     const uint4* src = reinterpret_cast<const uint4*>(sm.par);
     uint4* dst = reinterpret_cast<uint4*>(A.out.par + (size_t)tile * CL_SITES);
-#pragma unroll 4
-    for (int i = lane; i < CL_SITES * 2 / 16; i += 32) dst[i] = src[i];
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        A.out.hb[(size_t)tile * CL_T + 2 * lane + k] = ln.HB[k];
-        if (2 * lane + k == t.h - 1) A.out.vbb[tile] = ln.VB[k];
-    }
+#pragma unroll
+    for (int i = lane; i < CL_SITES * 2 / 16; i += CL_LANES) dst[i] = src[i];
+    A.out.hb[(size_t)tile * CL_T + lane] = ln.HB;
+    if (lane == t.h - 1) A.out.vbb[tile] = ln.VB;
 }
 
 // One thread per bond that can leave a tile: thread j < 64 the bond of row j of the tile's last column to the right,
@@ -84,53 +76,41 @@ __global__ void __launch_bounds__(128) cl_border_kernel(const __grid_constant__ 
     cl_gunion(gp, cl_global_site(A.g, t, a), cl_global_site(A.g, n, b));
 }
 
-// reload a labelled tile: labels into shared memory, masks and runs of the lane's rows into registers
-__device__ __forceinline__ void cl_reload_tile(const ClArgs& A, const ClTileId& t, int lane, ClTileSmem& sm, ClLane& ln) {
+// reload a labelled tile: labels into shared memory, masks and runs of the thread's row into registers
+__device__ __forceinline__ void cl_reload_tile(const ClArgs& A, const ClTileId& t, int lane, ClLabelSmem& sm, ClLane& ln) {
     const uint4* src = reinterpret_cast<const uint4*>(A.out.par + (size_t)t.tile * CL_SITES);
     uint4* dst = reinterpret_cast<uint4*>(sm.par);
-#pragma unroll 4
-    for (int i = lane; i < CL_SITES * 2 / 16; i += 32) dst[i] = src[i];
-    for (int i = 0; i < CL_SITES / 32 / 32; ++i) sm.flag[(CL_SITES / 32 / 32) * lane + i] = 0u;
+#pragma unroll
+    for (int i = lane; i < CL_SITES * 2 / 16; i += CL_LANES) dst[i] = src[i];
+    for (int i = 0; i < CL_SITES / 32 / CL_LANES; ++i) sm.flag[(CL_SITES / 32 / CL_LANES) * lane + i] = 0u;
     cl_phase_reload(lane, A.g, t, A.c0, A.c1, A.out.hb + (size_t)t.tile * CL_T, ln);
-    __syncwarp();
+    __syncthreads();
 }
 
-__global__ void __launch_bounds__(32 * CL_WARPS) cl_flip_kernel(const __grid_constant__ ClArgs A) {
-    __shared__ __align__(16) ClTileSmem s_tiles[CL_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * CL_WARPS + warp;
-    if (tile >= A.n_tiles) return;
-    ClTileSmem& sm = s_tiles[warp];
-    const ClTileId t = cl_tile_id(A.g, tile);
+// (8.7 KB of shared memory per tile: 26 tiles = 52 warps per SM; the kernel is latency-bound)
+__global__ void __launch_bounds__(CL_LANES) cl_flip_kernel(const __grid_constant__ ClArgs A) {
+    __shared__ __align__(16) ClLabelSmem sm;
+    const int lane = threadIdx.x;
+    const ClTileId t = cl_tile_id(A.g, blockIdx.x);
     ClLane ln;
     cl_reload_tile(A, t, lane, sm, ln);
     cl_phase_decide(lane, A.g, t, A.rng, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);
-    __syncwarp();
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k)
-        if (2 * lane + k < t.h)
-            cl_apply_flips(A.g, A.c0, A.c1, t.rep, t.x0, t.y0 + 2 * lane + k, cl_flip_mask(lane, k, sm, ln));
+    __syncthreads();
+    if (lane < t.h) cl_apply_flips(A.g, A.c0, A.c1, t.rep, t.x0, t.y0 + lane, cl_flip_mask(lane, sm, ln));
 }
 
 // Cluster labels for the measurements (cluster-size moments, gap-size histogram, cluster lists of the dumps):
 // labels[site] = smallest site of the site's cluster, row-major like the reference's lattice (main.cpp:98-101).
-__global__ void __launch_bounds__(32 * CL_WARPS) cl_labels_kernel(const __grid_constant__ ClArgs A) {
-    __shared__ __align__(16) ClTileSmem s_tiles[CL_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * CL_WARPS + warp;
-    if (tile >= A.n_tiles) return;
-    ClTileSmem& sm = s_tiles[warp];
-    const ClTileId t = cl_tile_id(A.g, tile);
+__global__ void __launch_bounds__(CL_LANES) cl_labels_kernel(const __grid_constant__ ClArgs A) {
+    __shared__ __align__(16) ClLabelSmem sm;
+    const int lane = threadIdx.x;
+    const ClTileId t = cl_tile_id(A.g, blockIdx.x);
     ClLane ln;
     cl_reload_tile(A, t, lane, sm, ln);
     const size_t N = (size_t)A.g.L * (size_t)A.g.L;
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k;
-        if (r >= t.h) continue;
-        cl_row_labels(lane, k, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * N,
-                      A.labels + (size_t)t.rep * N + (size_t)(t.y0 + r) * (size_t)A.g.L + (size_t)t.x0);
-    }
+    if (lane < t.h)
+        cl_row_labels(lane, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * N,
+                      A.labels + (size_t)t.rep * N + (size_t)(t.y0 + lane) * (size_t)A.g.L + (size_t)t.x0);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -173,7 +173,7 @@ gap_hist_kernel(const uint2* __restrict__ list, const uint32_t* __restrict__ cou
     };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
         const uint2 me = ls[i];
-        if (me.y == me.x) continue;  // the cluster's first site is never recorded
+        if (me.y == me.x || i == 0) continue;  // the cluster's first site is never recorded (a list starts with one)
         const long long c = (long long)(me.x / (uint32_t)L) - (long long)me.x;
         const long long row = ((long long)me.y + c) / L;
         const uint2 prev = ls[i - 1];  // i > 0: the first element of a list is a cluster's first site

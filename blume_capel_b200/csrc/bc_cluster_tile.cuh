@@ -1,14 +1,14 @@
-// bc_cluster_tile.cuh -- bit-parallel cluster labelling of one 64 x 64 tile by one warp.
+// bc_cluster_tile.cuh -- bit-parallel cluster labelling of one 64 x 64 tile by 64 threads.
 // Part of the sm_100a Blume-Capel engine; included through bc_cluster_kernels.cuh.
 //
 // What the reference does one cluster at a time with a BFS queue (wolff(), /root/reference/main.cpp:113-154, bond
 // probability 1 - exp(-2J/T) at :115, zeros never join :123-130,144) and, for the dumps, with a DFS over the whole
 // lattice (form_clusters, main.cpp:179-230), is done here for all clusters at once on 64-bit ROW MASKS:
 //   * a tile row is four 64-bit words: plus sites, minus sites, open bonds to the right, open bonds downwards;
-//   * lane l of the warp owns tile rows 2l and 2l+1: it converts its 2 x 64 spin bytes (two 32-byte pieces of the
-//     two compact colour arrays per row) to masks, draws the random bonds of its rows 32 at a time (bit-plane
+//   * thread l of the tile's 64 owns tile row l: it converts its 64 spin bytes (one 32-byte piece of each of the
+//     two compact colour arrays) to masks, draws the random bonds of its row 32 at a time (bit-plane
 //     uniforms, most significant plane first, until every candidate bond is decided: about two Philox calls per 32
-//     bonds, see cl_draw_bonds), and finds the horizontal runs of its rows with one AND-NOT;
+//     bonds, see cl_draw_bonds), and finds the horizontal runs of its row with one AND-NOT;
 //   * only RUN STARTS are union-find nodes (16-bit labels in shared memory): a vertical bond costs a union only when
 //     the bond to its left does not already join the same two runs; the larger root is always linked under the
 //     smaller one, so a cluster's root is its smallest site, independent of the order of the unions;
@@ -19,7 +19,7 @@
 // one-thread-per-two-sites kernels (0.24 ms per L = 4096 update; profiles/r01_ncu_launches_cluster_v2.csv).
 //
 // Every function here is host + device: the phases of the kernels are plain functions of (lane, tile state), the
-// kernels call them with __syncwarp() in between, and tests/cpu/cluster_emulation.cpp runs the same phases lane by
+// kernels call them with __syncthreads() in between (one CTA of 64 threads per tile), and tests/cpu/cluster_emulation.cpp runs the same phases lane by
 // lane on the CPU against the oracle (there is no GPU in the development container).
 #pragma once
 #include <stdint.h>
@@ -234,8 +234,16 @@ BC_HD uint16_t cl_find(volatile uint16_t* par, uint16_t a) {
     }
     return a;
 }
-// link the larger root under the smaller one; retry from the current roots if the larger one stopped being a root
-BC_HD void cl_union(uint16_t* par, uint16_t a, uint16_t b) {
+// find without stores, entries read through CL_IDX (phases in which every entry has exactly one writer and may
+// already carry its flag)
+BC_HD uint16_t cl_find_ro(const volatile uint16_t* par, uint16_t a) {
+    uint16_t p = par[a] & CL_IDX;
+    while (p != a) { a = p; p = par[a] & CL_IDX; }
+    return a;
+}
+// link the larger root under the smaller one; retry from the current roots if the larger one stopped being a root.
+// Returns the root of the merged tree as far as this thread knows (a hint for its next union).
+BC_HD uint16_t cl_union(uint16_t* par, uint16_t a, uint16_t b) {
     uint16_t ra = cl_find(par, a), rb = cl_find(par, b);
     while (ra != rb) {
         if (ra < rb) { const uint16_t t = ra; ra = rb; rb = t; }
@@ -244,6 +252,7 @@ BC_HD void cl_union(uint16_t* par, uint16_t a, uint16_t b) {
         ra = cl_find(par, old);
         rb = cl_find(par, rb);
     }
+    return rb;
 }
 // the same over global site indices (clusters that cross tile borders)
 BC_HD uint32_t cl_gfind(volatile uint32_t* par, uint32_t a) {
@@ -267,16 +276,36 @@ BC_HD void cl_gunion(uint32_t* par, uint32_t a, uint32_t b) {
     }
 }
 
+// f(x) for every set bit x of m, ascending: the two 32-bit halves separately (a 64-bit find-first-set is four times
+// the instructions of a 32-bit one, and these loops are the kernels' inner loops)
+template <class F>
+BC_HD void cl_for_bits(uint64_t m, F f) {
+    BC_UNROLL
+    for (int half = 0; half < 2; ++half)
+        for (uint32_t w = (uint32_t)(m >> (32 * half)); w; w &= w - 1) {
+#if defined(__CUDA_ARCH__)
+            f(32 * half + __ffs((int)w) - 1);
+#else
+            f(32 * half + __builtin_ctz(w));
+#endif
+        }
+}
+
 // ---- tile state -------------------------------------------------------------------------------------------------
-struct ClTileSmem {
+constexpr int CL_LANES = CL_T;    // threads per tile: thread l owns tile row l
+struct ClTileSmem {               // cl_label_kernel
     uint16_t par[CL_SITES];       // union-find over run starts; non-run-start entries are never read
     uint64_t plus[CL_T], minus[CL_T];
     uint64_t rs[CL_T];            // run starts per tile row
     uint64_t hb[CL_T];            // open bonds to the right (bit x: x -- x+1; bit w-1: into the next tile)
-    uint32_t flag[CL_SITES / 32]; // labelling: roots that touch the perimeter; flip: roots that flip
+    uint32_t flag[CL_SITES / 32]; // roots that touch the perimeter
 };
-struct ClLane {                   // registers of one lane: its two tile rows 2*lane, 2*lane + 1
-    uint64_t P[2], M[2], HB[2], VB[2], RS[2];
+struct ClLabelSmem {              // consumers of a labelled tile (cl_flip_kernel, cl_labels_kernel)
+    uint16_t par[CL_SITES];       // the tile's labels as cl_label_kernel left them
+    uint32_t flag[CL_SITES / 32]; // roots that flip
+};
+struct ClLane {                   // registers of one thread: its tile row
+    uint64_t P, M, HB, VB, RS;
 };
 // What a tile leaves in global memory for the kernels that follow (all tile-major)
 struct ClTileOut {
@@ -291,144 +320,117 @@ struct ClRng {
     uint32_t k0, k1, c_lo, c_hi;
 };
 
-// ---- labelling phases (cl_label_kernel) -------------------------------------------------------------------------
-// Phase 1: masks of the lane's two rows.
+// ---- labelling phases (cl_label_kernel; `lane` = 0 .. 63 = the thread's tile row) -------------------------------
+// Phase 1: masks of the thread's row.
 BC_HD void cl_phase_load(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1, ClTileSmem& sm,
                          ClLane& ln) {
-    for (int i = 0; i < CL_SITES / 32 / 32; ++i) sm.flag[(CL_SITES / 32 / 32) * lane + i] = 0u;
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k;
-        ln.P[k] = ln.M[k] = 0;
-        if (r < t.h) cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + r, &ln.P[k], &ln.M[k]);
-        if (t.w < CL_T) { ln.P[k] &= (1ull << t.w) - 1; ln.M[k] &= (1ull << t.w) - 1; }
-        sm.plus[r] = ln.P[k];
-        sm.minus[r] = ln.M[k];
-    }
+    for (int i = 0; i < CL_SITES / 32 / CL_LANES; ++i) sm.flag[(CL_SITES / 32 / CL_LANES) * lane + i] = 0u;
+    ln.P = ln.M = 0;
+    if (lane < t.h) cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + lane, &ln.P, &ln.M);
+    if (t.w < CL_T) { ln.P &= (1ull << t.w) - 1; ln.M &= (1ull << t.w) - 1; }
+    sm.plus[lane] = ln.P;
+    sm.minus[lane] = ln.M;
 }
 
 // Phase 2: candidate bonds (equal non-zero neighbours), random bonds, runs.
 BC_HD void cl_phase_bonds(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1, const ClRng& rng,
                           ClTileSmem& sm, ClLane& ln) {
-    const uint32_t thr = rng.thr ? rng.thr[t.rep] : 0xFFFFFFFFu;
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k, gy = t.y0 + r;
-        ln.HB[k] = ln.VB[k] = ln.RS[k] = 0;
-        if (r < t.h) {
-            const uint64_t P = ln.P[k], M = ln.M[k];
-            // right neighbour of the tile's last column: the next tile's first column, or the wrap, or nothing
-            uint64_t pr = 0, mr = 0;
-            int nx = t.x0 + t.w;
-            if (nx == g.L) nx = g.open ? -1 : 0;
-            if (nx >= 0) {
-                const uint32_t c = cl_site_code(g, c0, c1, t.rep, nx, gy);
-                pr = c == 2u; mr = c == 0u;
-            }
-            uint64_t hc = (P & ((P >> 1) | (pr << (t.w - 1)))) | (M & ((M >> 1) | (mr << (t.w - 1))));
-            // row below: inside the tile from shared memory, for the tile's last row from the lattice (or the wrap)
-            uint64_t Pd = 0, Md = 0;
-            if (r + 1 < t.h) { Pd = sm.plus[r + 1]; Md = sm.minus[r + 1]; }
-            else {
-                int ny = gy + 1;
-                if (ny == g.L) ny = g.open ? -1 : 0;
-                if (ny >= 0 && ny != gy) {
-                    cl_load_row(g, c0, c1, t.rep, t.x0, ny, &Pd, &Md);
-                    if (t.w < CL_T) { Pd &= (1ull << t.w) - 1; Md &= (1ull << t.w) - 1; }
-                }
-            }
-            uint64_t vc = (P & Pd) | (M & Md);
-            if (rng.thr) {
-                hc = cl_draw_bonds(hc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 0u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
-                vc = cl_draw_bonds(vc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 1u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
-            }
-            ln.HB[k] = hc; ln.VB[k] = vc;
-            ln.RS[k] = (P | M) & ~(hc << 1);
-            for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
-                const uint16_t i = (uint16_t)(r * CL_T + cl_ctz64(m));
-                sm.par[i] = i;
+    const int r = lane, gy = t.y0 + r;
+    ln.HB = ln.VB = ln.RS = 0;
+    if (r < t.h) {
+        const uint64_t P = ln.P, M = ln.M;
+        // right neighbour of the tile's last column: the next tile's first column, or the wrap, or nothing
+        uint64_t pr = 0, mr = 0;
+        int nx = t.x0 + t.w;
+        if (nx == g.L) nx = g.open ? -1 : 0;
+        if (nx >= 0) {
+            const uint32_t c = cl_site_code(g, c0, c1, t.rep, nx, gy);
+            pr = c == 2u; mr = c == 0u;
+        }
+        uint64_t hc = (P & ((P >> 1) | (pr << (t.w - 1)))) | (M & ((M >> 1) | (mr << (t.w - 1))));
+        // row below: inside the tile from shared memory, for the tile's last row from the lattice (or the wrap)
+        uint64_t Pd = 0, Md = 0;
+        if (r + 1 < t.h) { Pd = sm.plus[r + 1]; Md = sm.minus[r + 1]; }
+        else {
+            int ny = gy + 1;
+            if (ny == g.L) ny = g.open ? -1 : 0;
+            if (ny >= 0 && ny != gy) {
+                cl_load_row(g, c0, c1, t.rep, t.x0, ny, &Pd, &Md);
+                if (t.w < CL_T) { Pd &= (1ull << t.w) - 1; Md &= (1ull << t.w) - 1; }
             }
         }
-        sm.rs[r] = ln.RS[k];
-        sm.hb[r] = ln.HB[k];
+        uint64_t vc = (P & Pd) | (M & Md);
+        if (rng.thr) {
+            const uint32_t thr = rng.thr[t.rep];
+            hc = cl_draw_bonds(hc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 0u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+            vc = cl_draw_bonds(vc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 1u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+        }
+        ln.HB = hc; ln.VB = vc;
+        ln.RS = (P | M) & ~(hc << 1);
+        cl_for_bits(ln.RS, [&](int x) { sm.par[r * CL_T + x] = (uint16_t)(r * CL_T + x); });
     }
+    sm.rs[r] = ln.RS;
+    sm.hb[r] = ln.HB;
 }
 
-// Phase 3: one union per pair of runs joined by a vertical bond (skipped when the bond to the left joins the same pair)
+// Phase 3: one union per pair of runs joined by a vertical bond (skipped when the bond to the left joins the same
+// pair).  Consecutive bonds often share a run: the root a union returned is the starting point of the next find.
 BC_HD void cl_phase_unions(int lane, const ClTileId& t, ClTileSmem& sm, const ClLane& ln) {
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k;
-        if (r + 1 >= t.h) continue;  // the last row's bonds leave the tile
-        const uint64_t vb = ln.VB[k], rs_t = ln.RS[k], rs_d = sm.rs[r + 1];
-        for (uint64_t m = vb & ~((vb & ln.HB[k] & sm.hb[r + 1]) << 1); m; m &= m - 1) {
-            const int x = cl_ctz64(m);
-            cl_union(sm.par, (uint16_t)(r * CL_T + cl_run_start(rs_t, x)), (uint16_t)((r + 1) * CL_T + cl_run_start(rs_d, x)));
-        }
-    }
+    const int r = lane;
+    if (r + 1 >= t.h) return;  // the last row's bonds leave the tile
+    const uint64_t vb = ln.VB, rs_t = ln.RS, rs_d = sm.rs[r + 1];
+    int last_a = -1, last_b = -1;
+    uint16_t root = 0;
+    cl_for_bits(vb & ~((vb & ln.HB & sm.hb[r + 1]) << 1), [&](int x) {
+        const int a = cl_run_start(rs_t, x), b = cl_run_start(rs_d, x);
+        const uint16_t ua = a == last_a ? root : (uint16_t)(r * CL_T + a), ub = b == last_b ? root : (uint16_t)((r + 1) * CL_T + b);
+        root = cl_union(sm.par, ua, ub);
+        last_a = a; last_b = b;
+    });
 }
 
-// Phase 4: every run start points at its root
-BC_HD void cl_phase_compress(int lane, ClTileSmem& sm, const ClLane& ln) {
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k)
-        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
-            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
-            const uint16_t root = cl_find(sm.par, i);
-            if (root != i) sm.par[i] = root;
-        }
-}
-
-// Phase 5: roots of the perimeter sites (lane l: columns 2l, 2l+1 of the top and bottom row, its own two rows of the
-// left and right column), flagged as "touches the perimeter"
+// Phase 4: roots of the perimeter sites (thread l: column l of the top and bottom row, its own row in the left and
+// right column), flagged as "touches the perimeter".  Read-only walks: nothing is compressed yet.
 BC_HD void cl_phase_perimeter(int lane, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint16_t* proot) {
     BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k;
-        BC_UNROLL
-        for (int e = 0; e < 4; ++e) {
-            // e = 0, 1: column x = r of the top / bottom row; e = 2, 3: row y = r of the left / right column
-            const int row = e == 0 ? 0 : (e == 1 ? t.h - 1 : r), col = e < 2 ? r : (e == 2 ? 0 : t.w - 1);
-            const uint64_t occ = e < 2 ? (sm.plus[row] | sm.minus[row]) : (ln.P[k] | ln.M[k]);
-            const uint64_t rs = e < 2 ? sm.rs[row] : ln.RS[k];
-            uint16_t root = CL_NONE;
-            if (row < t.h && col < t.w && ((occ >> col) & 1ull)) {
-                root = sm.par[row * CL_T + cl_run_start(rs, col)];
-                cl_or32(&sm.flag[root >> 5], 1u << (root & 31u));
-            }
-            proot[64 * e + r] = root;
+    for (int e = 0; e < 4; ++e) {
+        // e = 0, 1: column x = lane of the top / bottom row; e = 2, 3: row y = lane of the left / right column
+        const int row = e == 0 ? 0 : (e == 1 ? t.h - 1 : lane), col = e < 2 ? lane : (e == 2 ? 0 : t.w - 1);
+        const uint64_t occ = e < 2 ? (sm.plus[row] | sm.minus[row]) : (ln.P | ln.M);
+        const uint64_t rs = e < 2 ? sm.rs[row] : ln.RS;
+        uint16_t root = CL_NONE;
+        if (row < t.h && col < t.w && ((occ >> col) & 1ull)) {
+            root = cl_find_ro(sm.par, (uint16_t)(row * CL_T + cl_run_start(rs, col)));
+            cl_or32(&sm.flag[root >> 5], 1u << (root & 31u));
         }
+        proot[64 * e + lane] = root;
     }
 }
 
-// Phase 6: flags into the labels; flagged roots become nodes of the global union-find
+// Phase 5: every run start points at its root and carries the root's flag; flagged roots become nodes of the global
+// union-find.  Read-only walks (through CL_IDX: entries already finished carry the flag), every entry is written by
+// its owner alone -- a path-halving store of another thread, issued with a parent it read before the owner's store,
+// would put a non-root ancestor back into a finished entry, and the consumers take a run start's entry for the ROOT.
 BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint32_t* gparent_rep) {
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k)
-        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
-            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
-            const uint16_t root = sm.par[i];
-            if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
-                sm.par[i] = root | CL_FLAG;
-                if (root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
-            }
-        }
+    cl_for_bits(ln.RS, [&](int x) {
+        const uint16_t i = (uint16_t)(lane * CL_T + x);
+        const uint16_t root = cl_find_ro(sm.par, i);
+        const uint16_t f = ((sm.flag[root >> 5] >> (root & 31u)) & 1u) ? CL_FLAG : (uint16_t)0;
+        sm.par[i] = root | f;
+        if (f && root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
+    });
 }
 
 // ---- consumers of a labelled tile -------------------------------------------------------------------------------
-// Reload what cl_label_kernel left: labels into shared memory (done by the caller), masks and runs of the lane's rows.
+// Reload what cl_label_kernel left: labels into shared memory (done by the caller), masks and runs of the thread's row.
 BC_HD void cl_phase_reload(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1,
                            const uint64_t* hb_tile, ClLane& ln) {
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k) {
-        const int r = 2 * lane + k;
-        ln.P[k] = ln.M[k] = ln.HB[k] = ln.RS[k] = 0;
-        if (r >= t.h) continue;
-        cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + r, &ln.P[k], &ln.M[k]);
-        if (t.w < CL_T) { ln.P[k] &= (1ull << t.w) - 1; ln.M[k] &= (1ull << t.w) - 1; }
-        ln.HB[k] = hb_tile[r];
-        ln.RS[k] = (ln.P[k] | ln.M[k]) & ~(ln.HB[k] << 1);
-    }
+    ln.P = ln.M = ln.HB = ln.VB = ln.RS = 0;
+    if (lane >= t.h) return;
+    cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + lane, &ln.P, &ln.M);
+    if (t.w < CL_T) { ln.P &= (1ull << t.w) - 1; ln.M &= (1ull << t.w) - 1; }
+    ln.HB = hb_tile[lane];
+    ln.RS = (ln.P | ln.M) & ~(ln.HB << 1);
 }
 
 // smallest site of the cluster of tile-local root entry `e` (root | flag)
@@ -440,34 +442,33 @@ BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, u
     return root;
 }
 
-// Flip phase 1: the lane's roots decide (one Philox call serves the 128 sites around a root)
-BC_HD void cl_phase_decide(int lane, const ClGeom& g, const ClTileId& t, const ClRng& rng, ClTileSmem& sm, const ClLane& ln,
+// Flip phase 1: the thread's roots decide (one Philox call serves the 128 sites around a root)
+BC_HD void cl_phase_decide(int lane, const ClGeom& g, const ClTileId& t, const ClRng& rng, ClLabelSmem& sm, const ClLane& ln,
                            uint32_t* gparent_rep) {
     uint32_t blk = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
-    BC_UNROLL
-    for (int k = 0; k < 2; ++k)
-        for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
-            const uint16_t i = (uint16_t)((2 * lane + k) * CL_T + cl_ctz64(m));
-            const uint16_t e = sm.par[i];
-            if ((e & CL_IDX) != i) continue;
-            const uint32_t root = cl_cluster_site(g, t, e, gparent_rep);
-            if (cl_flip_bit(root, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep, &blk, w)) cl_or32(&sm.flag[i >> 5], 1u << (i & 31u));
-        }
+    cl_for_bits(ln.RS, [&](int x) {
+        const uint16_t i = (uint16_t)(lane * CL_T + x);
+        const uint16_t e = sm.par[i];
+        if ((e & CL_IDX) != i) return;
+        const uint32_t root = cl_cluster_site(g, t, e, gparent_rep);
+        if (cl_flip_bit(root, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep, &blk, w)) cl_or32(&sm.flag[i >> 5], 1u << (i & 31u));
+    });
 }
 
-// Flip phase 2: mask of the sites of row k of the lane whose cluster flips
-BC_HD uint64_t cl_flip_mask(int lane, int k, const ClTileSmem& sm, const ClLane& ln) {
-    uint64_t F = 0;
-    for (uint64_t m = ln.RS[k]; m; m &= m - 1) {
-        const int x = cl_ctz64(m);
-        const uint16_t root = sm.par[(2 * lane + k) * CL_T + x] & CL_IDX;
-        if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
-            const uint64_t rest = m & (m - 1);                      // run starts behind this one
-            const uint64_t upto = rest ? ((rest & (~rest + 1)) - 1) : ~0ull;  // bits below the next run start
-            F |= upto & ~((1ull << x) - 1);
-        }
-    }
-    return F & (ln.P[k] | ln.M[k]);
+// Flip phase 2: mask of the sites of the thread's row whose cluster flips
+BC_HD uint64_t cl_flip_mask(int lane, const ClLabelSmem& sm, const ClLane& ln) {
+    uint64_t starts = 0;  // run starts whose cluster flips
+    cl_for_bits(ln.RS, [&](int x) {
+        const uint16_t root = sm.par[lane * CL_T + x] & CL_IDX;
+        starts |= (uint64_t)((sm.flag[root >> 5] >> (root & 31u)) & 1u) << x;
+    });
+    // A run = its start and the sites up to the next start: fill(x) = starts(x) | (fill(x-1) & ~RS(x)) is the carry
+    // chain of an addition with generate = starts and propagate = ~RS: in X + starts with X = starts | ~RS the carry
+    // INTO position x + 1 is exactly fill(x).  (Zero sites behind a run inherit its bit; masked by the occupancy.)
+    const uint64_t X = starts | ~ln.RS;
+    const uint64_t carry = (X + starts) ^ X ^ starts;
+    const uint64_t F = (carry >> 1) | ((starts | (~ln.RS & carry)) & (1ull << 63));
+    return F & (ln.P | ln.M);
 }
 
 // Flip phase 3: apply a flip mask to the 64 spin bytes of a row (code 0 <-> code 2: xor 2)
@@ -492,14 +493,14 @@ BC_HD void cl_apply_flips(const ClGeom& g, uint8_t* c0, uint8_t* c1, uint32_t re
     }
 }
 
-// Label phase for the measurements: the smallest site of the cluster of every site of row k of the lane
+// Label phase for the measurements: the smallest site of the cluster of every site of the thread's row
 // (0xFFFFFFFF for a zero spin) into `out` (the row's 64 entries of a row-major label array; clipped tiles: w entries)
-BC_HD void cl_row_labels(int lane, int k, const ClGeom& g, const ClTileId& t, const ClTileSmem& sm, const ClLane& ln,
+BC_HD void cl_row_labels(int lane, const ClGeom& g, const ClTileId& t, const ClLabelSmem& sm, const ClLane& ln,
                          uint32_t* gparent_rep, uint32_t* out) {
     uint32_t cur = 0xFFFFFFFFu;
-    const uint64_t S = ln.P[k] | ln.M[k];
+    const uint64_t S = ln.P | ln.M;
     for (int x = 0; x < t.w; ++x) {
-        if ((ln.RS[k] >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[(2 * lane + k) * CL_T + x], gparent_rep);
+        if ((ln.RS >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[lane * CL_T + x], gparent_rep);
         out[x] = ((S >> x) & 1ull) ? cur : 0xFFFFFFFFu;
     }
 }

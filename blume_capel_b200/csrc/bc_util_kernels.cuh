@@ -102,6 +102,98 @@ unpack16_kernel(int8_t* __restrict__ spins, const uint8_t* __restrict__ c0, cons
     __stcs(dst + 1, b);
 }
 
+// ---- 2-bit wire format ---------------------------------------------------------------------------------------
+// Host <-> device transfers of whole lattices are PCIe-bound (one byte per site each way); the wire format packs four
+// sites into a byte: row-major like the reference's lattice (main.cpp:98-101), byte b of a row holds the codes
+// (spin + 1) of sites x = 4b .. 4b+3 in bits 0-1, 2-3, 4-5, 6-7; rows are padded to whole bytes.  Conversion to and
+// from the compact colour arrays happens on the device.  Vector forms for L % 64 == 0: one thread converts 64
+// consecutive sites of a row = two 16-byte chunks of each colour array <-> 16 packed bytes.
+__device__ __forceinline__ uint32_t pack2_word(uint32_t ev, uint32_t od) {  // 4 even + 4 odd site codes -> 2 bytes (low half)
+    const uint32_t t = ev | (od << 2);          // per byte: two sites (even, odd) in 4 bits
+    const uint32_t u = t | (t >> 4);            // bytes 0 and 2: four sites each
+    return __byte_perm(u, 0u, 0x4420);          // (byte 0, byte 2, 0, 0)
+}
+__device__ __forceinline__ void unpack2_half(uint32_t two_bytes, uint32_t* ev, uint32_t* od) {  // inverse of pack2_word
+    const uint32_t u = __byte_perm(two_bytes, 0u, 0x4140);       // byte 0 -> byte 0, byte 1 -> byte 2
+    const uint32_t t = (u | (u << 4)) & 0x0F0F0F0Fu;              // one (even, odd) pair per byte
+    *ev = t & 0x03030303u;
+    *od = (t >> 2) & 0x03030303u;
+}
+
+__global__ void __launch_bounds__(256)
+pack2_kernel(uint8_t* __restrict__ packed, const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, const Geom g, int rep_first) {
+    const uint32_t per_row = (uint32_t)g.L >> 6;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= (uint32_t)g.Ly * per_row) return;
+    const uint32_t r = blockIdx.y, y = idx / per_row, m = idx - y * per_row;
+    const size_t src = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (size_t)m * 32;
+    const bool odd_row = ((y + (uint32_t)g.y_glob0) & 1u) != 0;  // colour 0 holds x = 2k + (row & 1)
+    const uint8_t* ev = (odd_row ? c1 : c0) + src;
+    const uint8_t* od = (odd_row ? c0 : c1) + src;
+    const uint4 e0 = *reinterpret_cast<const uint4*>(ev), e1 = *reinterpret_cast<const uint4*>(ev + 16);
+    const uint4 o0 = *reinterpret_cast<const uint4*>(od), o1 = *reinterpret_cast<const uint4*>(od + 16);
+    uint4 out;
+    out.x = pack2_word(e0.x, o0.x) | (pack2_word(e0.y, o0.y) << 16);
+    out.y = pack2_word(e0.z, o0.z) | (pack2_word(e0.w, o0.w) << 16);
+    out.z = pack2_word(e1.x, o1.x) | (pack2_word(e1.y, o1.y) << 16);
+    out.w = pack2_word(e1.z, o1.z) | (pack2_word(e1.w, o1.w) << 16);
+    __stcs(reinterpret_cast<uint4*>(packed + ((size_t)r * g.Ly + y) * ((size_t)g.L >> 2) + (size_t)m * 16), out);
+}
+
+__global__ void __launch_bounds__(256)
+unpack2_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g, int rep_first) {
+    const uint32_t per_row = (uint32_t)g.L >> 6;
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    if (idx >= (uint32_t)g.Ly * per_row) return;
+    const uint32_t r = blockIdx.y, y = idx / per_row, m = idx - y * per_row;
+    const uint4 in = __ldcs(reinterpret_cast<const uint4*>(packed + ((size_t)r * g.Ly + y) * ((size_t)g.L >> 2) + (size_t)m * 16));
+    uint4 e0, e1, o0, o1;
+    unpack2_half(in.x, &e0.x, &o0.x); unpack2_half(in.x >> 16, &e0.y, &o0.y);
+    unpack2_half(in.y, &e0.z, &o0.z); unpack2_half(in.y >> 16, &e0.w, &o0.w);
+    unpack2_half(in.z, &e1.x, &o1.x); unpack2_half(in.z >> 16, &e1.y, &o1.y);
+    unpack2_half(in.w, &e1.z, &o1.z); unpack2_half(in.w >> 16, &e1.w, &o1.w);
+    const size_t dst = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (size_t)m * 32;
+    const bool odd_row = ((y + (uint32_t)g.y_glob0) & 1u) != 0;
+    uint8_t* ev = (odd_row ? c1 : c0) + dst;
+    uint8_t* od = (odd_row ? c0 : c1) + dst;
+    *reinterpret_cast<uint4*>(ev) = e0; *reinterpret_cast<uint4*>(ev + 16) = e1;
+    *reinterpret_cast<uint4*>(od) = o0; *reinterpret_cast<uint4*>(od + 16) = o1;
+}
+
+// any L: one thread per packed byte (four sites; rows padded to whole bytes)
+__global__ void pack2_any_kernel(uint8_t* __restrict__ packed, const uint8_t* __restrict__ c0, const uint8_t* __restrict__ c1, const Geom g,
+                                 int rep_first, int n_rep) {
+    const long long row_bytes = (g.L + 3) >> 2, per_rep = (long long)g.Ly * row_bytes;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_rep * n_rep) return;
+    const int r = (int)(gid / per_rep);
+    const long long rem = gid - (long long)r * per_rep;
+    const int y = (int)(rem / row_bytes), b = (int)(rem - (long long)y * row_bytes);
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i) {
+        const int x = 4 * b + i;
+        uint32_t code = 1u;
+        if (x < g.L) {
+            const size_t src = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (x >> 1);
+            code = ((x + y + g.y_glob0) & 1) ? c1[src] : c0[src];
+        }
+        v |= code << (2 * i);
+    }
+    packed[gid] = (uint8_t)v;
+}
+__global__ void unpack2_any_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g,
+                                   int rep_first, int n_rep) {
+    const long long row_bytes = (g.L + 3) >> 2, per_rep = (long long)g.Ly * g.L;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_rep * n_rep) return;
+    const int r = (int)(gid / per_rep);
+    const long long rem = gid - (long long)r * per_rep;
+    const int y = (int)(rem / g.L), x = (int)(rem - (long long)y * g.L);
+    const uint32_t code = (packed[((size_t)r * g.Ly + y) * row_bytes + (x >> 2)] >> (2 * (x & 3))) & 3u;
+    const size_t dst = ((size_t)(rep_first + r) * g.rows_arr + g.row_first + y) * g.Wc + (x >> 1);
+    if ((x + y + g.y_glob0) & 1) c1[dst] = (uint8_t)code; else c0[dst] = (uint8_t)code;
+}
+
 // iid uniform {-1,0,1} (main.cpp:166-171) from Philox stream INIT, indexed by the GLOBAL site index x + y*L
 __global__ void init_kernel(uint8_t* __restrict__ c0, uint8_t* __restrict__ c1, const Geom g, int rep_first,
                             int n_rep, uint32_t key0, uint32_t key1) {

@@ -40,8 +40,7 @@ static int cluster_args(bc_engine* e, const char* who, bool random_bonds, int64_
 
 // labels every tile and merges the clusters across tile borders (two launches)
 static int label_clusters(bc_engine* e, const ClArgs& A) {
-    const unsigned grid = (A.n_tiles + CL_WARPS - 1) / CL_WARPS;
-    cl_label_kernel<<<grid, 32 * CL_WARPS, 0, e->stream>>>(A);
+    cl_label_kernel<<<A.n_tiles, CL_LANES, 0, e->stream>>>(A);
     cl_border_kernel<<<A.n_tiles, 128, 0, e->stream>>>(A);
     e->launches += 2;
     BC_CUDA(e, cudaGetLastError());
@@ -55,7 +54,7 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
         int rc = cluster_args(e, "bc_cluster_update", true, e->cluster_step, &A);
         if (rc == BC_OK) rc = label_clusters(e, A);
         if (rc != BC_OK) return rc;
-        cl_flip_kernel<<<(A.n_tiles + CL_WARPS - 1) / CL_WARPS, 32 * CL_WARPS, 0, e->stream>>>(A);
+        cl_flip_kernel<<<A.n_tiles, CL_LANES, 0, e->stream>>>(A);
         ++e->launches;
         BC_CUDA(e, cudaGetLastError());
         if (e->ghost) { rc = exchange_both(e); if (rc != BC_OK) return rc; }  // one-rank slab: refresh its ghost rows
@@ -80,7 +79,7 @@ static int cluster_labels(bc_engine* e, const char* who, int kind, int64_t mstep
     A.labels = e->cl_labels;
     rc = label_clusters(e, A);
     if (rc != BC_OK) return rc;
-    cl_labels_kernel<<<(A.n_tiles + CL_WARPS - 1) / CL_WARPS, 32 * CL_WARPS, 0, e->stream>>>(A);
+    cl_labels_kernel<<<A.n_tiles, CL_LANES, 0, e->stream>>>(A);
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     return BC_OK;

@@ -53,6 +53,11 @@ SYMBOLS = {
     "bc_download_all": (C.c_int, [_P, _P]),
     "bc_upload_all_async": (C.c_int, [_P, _P]),
     "bc_download_all_async": (C.c_int, [_P, _P]),
+    "bc_packed_size": (C.c_int64, [_P, C.c_int]),
+    "bc_upload_packed": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "bc_download_packed": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "bc_pack_spins": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
+    "bc_unpack_spins": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
     "bc_get_sweep_counter": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "bc_set_sweep_counter": (C.c_int, [_P, C.c_int64]),
     "bc_sweep": (C.c_int64, [_P, C.c_int64, C.c_int64, _P]),
@@ -217,6 +222,22 @@ class Engine:
         assert out.dtype == np.int8 and out.flags.c_contiguous and out.size == self.n_replicas * self.rows * self.L
         self._check(self._lib.bc_download_all_async(self._h, out.ctypes.data))
 
+    # -- 2-bit wire format (four sites per byte; conversion on the device)
+    def packed_size(self, n_lattices: Optional[int] = None) -> int:
+        return self._check(self._lib.bc_packed_size(self._h, self.n_replicas if n_lattices is None else n_lattices))
+
+    def upload_packed(self, packed: np.ndarray, replica: int = -1, wait: bool = True):
+        assert packed.dtype == np.uint8 and packed.flags.c_contiguous
+        assert packed.size == self.packed_size(self.n_replicas if replica < 0 else 1)
+        self._check(self._lib.bc_upload_packed(self._h, replica, packed.ctypes.data, 0 if wait else 1))
+
+    def download_packed(self, replica: int = -1, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
+        n = self.packed_size(self.n_replicas if replica < 0 else 1)
+        a = out if out is not None else np.empty(n, np.uint8)
+        assert a.dtype == np.uint8 and a.flags.c_contiguous and a.size == n
+        self._check(self._lib.bc_download_packed(self._h, replica, a.ctypes.data, 0 if wait else 1))
+        return a
+
     @property
     def sweep_counter(self) -> int:
         t = C.c_int64()
@@ -323,3 +344,25 @@ class Engine:
         t = C.c_int64()
         self._check(self._lib.bc_tie_count(self._h, C.byref(t)))
         return t.value
+
+
+def pack_spins(spins: np.ndarray) -> np.ndarray:
+    """int8 spins (..., L) -> 2-bit wire format (rows padded to whole bytes), on the host."""
+    a = np.ascontiguousarray(spins, np.int8)
+    L = a.shape[-1]
+    rows = a.size // L
+    out = np.empty(rows * ((L + 3) // 4), np.uint8)
+    rc = load_library().bc_pack_spins(a.ctypes.data, L, rows, out.ctypes.data)
+    if rc != 0:
+        raise BCError(rc, "bc_pack_spins")
+    return out
+
+
+def unpack_spins(packed: np.ndarray, L: int) -> np.ndarray:
+    p = np.ascontiguousarray(packed, np.uint8)
+    rows = p.size // ((L + 3) // 4)
+    out = np.empty((rows, L), np.int8)
+    rc = load_library().bc_unpack_spins(p.ctypes.data, L, rows, out.ctypes.data)
+    if rc != 0:
+        raise BCError(rc, "bc_unpack_spins")
+    return out

@@ -117,6 +117,18 @@ int bc_download_all(bc_engine* e, int8_t* spins);
 int bc_upload_all_async(bc_engine* e, const int8_t* spins);
 int bc_download_all_async(bc_engine* e, int8_t* spins);
 
+/* 2-bit wire format: whole-lattice transfers are PCIe-bound at one byte per site, so the same transfers are also
+ * offered packed, four sites per byte: row-major like the reference's lattice, byte b of a row holds the codes
+ * spin + 1 of sites x = 4b .. 4b+3 in bits 0-1, 2-3, 4-5, 6-7, rows padded to whole bytes.  The conversion to and from
+ * the engine's layout runs on the device.  replica -1 = all replicas (bc_packed_size(e, n_replicas) bytes); async != 0:
+ * enqueue and return like the *_async calls above (pinned memory, valid until bc_sync).  bc_pack_spins /
+ * bc_unpack_spins convert between int8 spins and the wire format on the host (rows of L sites). */
+int64_t bc_packed_size(const bc_engine* e, int n_lattices);
+int bc_upload_packed(bc_engine* e, int replica, const uint8_t* packed, int async);
+int bc_download_packed(bc_engine* e, int replica, uint8_t* packed, int async);
+int bc_pack_spins(const int8_t* spins, int L, int64_t rows, uint8_t* packed);
+int bc_unpack_spins(const uint8_t* packed, int L, int64_t rows, int8_t* spins);
+
 /* Sweep counter = the full RNG state besides the seed (Philox is counter based), so
  * (lattice, seed, counter) is an exact checkpoint. */
 int bc_get_sweep_counter(const bc_engine* e, int64_t* t);

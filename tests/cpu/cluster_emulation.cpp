@@ -1,8 +1,8 @@
 // cluster_emulation.cpp -- TEST INFRASTRUCTURE: runs the phases of the cluster kernels (bc_cluster_tile.cuh, every
 // function of which is host + device) lane by lane on the CPU, in the order and with the synchronisation points of
 // cl_label_kernel / cl_border_kernel / cl_flip_kernel / cl_labels_kernel (bc_cluster_kernels.cuh), so that the tile
-// algorithm can be compared with the oracle in the development container, which has no GPU.  A warp's __syncwarp()
-// is "every lane has finished the phase"; atomics are plain read-modify-writes.  Built by tests/test_cluster_cpu.py:
+// algorithm can be compared with the oracle in the development container, which has no GPU.  A CTA's __syncthreads()
+// is "every thread has finished the phase" (threads of a phase run in a seeded random order); atomics are plain read-modify-writes.  Built by tests/test_cluster_cpu.py:
 //     g++ -O2 -std=c++17 -shared -fPIC -o tests/cpu/libcluster_emulation.so tests/cpu/cluster_emulation.cpp
 #include <cstdint>
 #include <cstring>
@@ -42,24 +42,43 @@ void build(Lattice& lt, int L, int open, int ghost, const int8_t* spins) {
     lt.out = ClTileOut{lt.par.data(), lt.hb.data(), lt.vbb.data(), lt.proot.data(), lt.gparent.data()};
 }
 
+// lanes of a phase in a seeded random order: a phase must not depend on the order its threads run in
+struct Order {
+    int idx[CL_LANES];
+    uint64_t state;
+    explicit Order(uint64_t seed) : state(seed * 0x9E3779B97F4A7C15ull + 1) { for (int i = 0; i < CL_LANES; ++i) idx[i] = i; }
+    const int* next() {
+        for (int i = CL_LANES - 1; i > 0; --i) {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            const int j = (int)((state >> 33) % (uint64_t)(i + 1));
+            const int tmp = idx[i]; idx[i] = idx[j]; idx[j] = tmp;
+        }
+        return idx;
+    }
+};
+
 void label(Lattice& lt, const ClRng& rng) {
     for (uint32_t tile = 0; tile < lt.n_tiles; ++tile) {
         ClTileSmem sm;
         std::memset(&sm, 0xAB, sizeof(sm));  // shared memory is not zero-initialised
-        ClLane ln[32];
+        ClLane ln[CL_LANES];
+        Order ord(tile);
         const ClTileId t = cl_tile_id(lt.g, tile);
-        for (int l = 0; l < 32; ++l) cl_phase_load(l, lt.g, t, lt.c0.data(), lt.c1.data(), sm, ln[l]);
-        for (int l = 0; l < 32; ++l) cl_phase_bonds(l, lt.g, t, lt.c0.data(), lt.c1.data(), rng, sm, ln[l]);
-        for (int l = 31; l >= 0; --l) cl_phase_unions(l, t, sm, ln[l]);  // any lane order must do
-        for (int l = 0; l < 32; ++l) cl_phase_compress(l, sm, ln[l]);
-        for (int l = 0; l < 32; ++l) cl_phase_perimeter(l, t, sm, ln[l], lt.out.proot + (size_t)tile * 256);
-        for (int l = 0; l < 32; ++l) cl_phase_finish(l, lt.g, t, sm, ln[l], lt.out.gparent);
+        const int* o = ord.next();
+        for (int l = 0; l < CL_LANES; ++l) cl_phase_load(o[l], lt.g, t, lt.c0.data(), lt.c1.data(), sm, ln[o[l]]);
+        o = ord.next();
+        for (int l = 0; l < CL_LANES; ++l) cl_phase_bonds(o[l], lt.g, t, lt.c0.data(), lt.c1.data(), rng, sm, ln[o[l]]);
+        o = ord.next();
+        for (int l = 0; l < CL_LANES; ++l) cl_phase_unions(o[l], t, sm, ln[o[l]]);
+        o = ord.next();
+        for (int l = 0; l < CL_LANES; ++l) cl_phase_perimeter(o[l], t, sm, ln[o[l]], lt.out.proot + (size_t)tile * 256);
+        o = ord.next();
+        for (int l = 0; l < CL_LANES; ++l) cl_phase_finish(o[l], lt.g, t, sm, ln[o[l]], lt.out.gparent);
         std::memcpy(lt.out.par + (size_t)tile * CL_SITES, sm.par, sizeof(sm.par));
-        for (int l = 0; l < 32; ++l)
-            for (int k = 0; k < 2; ++k) {
-                lt.out.hb[(size_t)tile * CL_T + 2 * l + k] = ln[l].HB[k];
-                if (2 * l + k == t.h - 1) lt.out.vbb[tile] = ln[l].VB[k];
-            }
+        for (int l = 0; l < CL_LANES; ++l) {
+            lt.out.hb[(size_t)tile * CL_T + l] = ln[l].HB;
+            if (l == t.h - 1) lt.out.vbb[tile] = ln[l].VB;
+        }
     }
     // cl_border_kernel
     for (uint32_t tile = 0; tile < lt.n_tiles; ++tile)
@@ -83,11 +102,11 @@ void label(Lattice& lt, const ClRng& rng) {
         }
 }
 
-void reload(Lattice& lt, const ClTileId& t, ClTileSmem& sm, ClLane (&ln)[32]) {
+void reload(Lattice& lt, const ClTileId& t, ClLabelSmem& sm, ClLane (&ln)[CL_LANES]) {
     std::memset(&sm, 0xCD, sizeof(sm));
     std::memcpy(sm.par, lt.out.par + (size_t)t.tile * CL_SITES, sizeof(sm.par));
     std::memset(sm.flag, 0, sizeof(sm.flag));
-    for (int l = 0; l < 32; ++l) cl_phase_reload(l, lt.g, t, lt.c0.data(), lt.c1.data(), lt.out.hb + (size_t)t.tile * CL_T, ln[l]);
+    for (int l = 0; l < CL_LANES; ++l) cl_phase_reload(l, lt.g, t, lt.c0.data(), lt.c1.data(), lt.out.hb + (size_t)t.tile * CL_T, ln[l]);
 }
 }  // namespace
 
@@ -103,15 +122,13 @@ int emu_cluster_update(int L, int open, int ghost, int8_t* spins, uint32_t thr, 
                     (uint32_t)((uint64_t)cstep >> 32)};
     label(lt, rng);
     for (uint32_t tile = 0; tile < lt.n_tiles; ++tile) {
-        ClTileSmem sm;
-        ClLane ln[32];
+        ClLabelSmem sm;
+        ClLane ln[CL_LANES];
         const ClTileId t = cl_tile_id(lt.g, tile);
         reload(lt, t, sm, ln);
-        for (int l = 0; l < 32; ++l) cl_phase_decide(l, lt.g, t, rng, sm, ln[l], lt.out.gparent);
-        for (int l = 0; l < 32; ++l)
-            for (int k = 0; k < 2; ++k)
-                if (2 * l + k < t.h)
-                    cl_apply_flips(lt.g, lt.c0.data(), lt.c1.data(), t.rep, t.x0, t.y0 + 2 * l + k, cl_flip_mask(l, k, sm, ln[l]));
+        for (int l = CL_LANES - 1; l >= 0; --l) cl_phase_decide(l, lt.g, t, rng, sm, ln[l], lt.out.gparent);
+        for (int l = 0; l < CL_LANES; ++l)
+            if (l < t.h) cl_apply_flips(lt.g, lt.c0.data(), lt.c1.data(), t.rep, t.x0, t.y0 + l, cl_flip_mask(l, sm, ln[l]));
     }
     for (int y = 0; y < L; ++y)
         for (int x = 0; x < L; ++x)
@@ -128,15 +145,12 @@ int emu_cluster_labels(int L, int open, int ghost, const int8_t* spins, int alwa
                     (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu), (uint32_t)((uint64_t)cstep >> 32)};
     label(lt, rng);
     for (uint32_t tile = 0; tile < lt.n_tiles; ++tile) {
-        ClTileSmem sm;
-        ClLane ln[32];
+        ClLabelSmem sm;
+        ClLane ln[CL_LANES];
         const ClTileId t = cl_tile_id(lt.g, tile);
         reload(lt, t, sm, ln);
-        for (int l = 0; l < 32; ++l)
-            for (int k = 0; k < 2; ++k) {
-                const int r = 2 * l + k;
-                if (r < t.h) cl_row_labels(l, k, lt.g, t, sm, ln[l], lt.out.gparent, labels + (size_t)(t.y0 + r) * L + t.x0);
-            }
+        for (int l = 0; l < CL_LANES; ++l)
+            if (l < t.h) cl_row_labels(l, lt.g, t, sm, ln[l], lt.out.gparent, labels + (size_t)(t.y0 + l) * L + t.x0);
     }
     return 0;
 }

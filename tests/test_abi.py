@@ -110,3 +110,15 @@ def test_header_is_plain_c_and_links(tmp_path):
                    capture_output=True, text=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split()[0] == "2"
+
+
+def test_wire_format_host_conversion_needs_no_gpu(bc):
+    """bc_pack_spins / bc_unpack_spins: four sites per byte, code spin + 1 in bits 2i..2i+1, rows padded to whole bytes."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for L in (1, 3, 4, 6, 64, 101):
+        s = rng.integers(-1, 2, size=(5, L), dtype=np.int8)
+        p = bc.pack_spins(s)
+        assert p.size == 5 * ((L + 3) // 4)
+        assert np.array_equal(bc.unpack_spins(p, L), s)
+    assert bc.pack_spins(np.array([[-1, 0, 1, 1, 0]], np.int8)).tolist() == [0b10100100, 0b01010101]

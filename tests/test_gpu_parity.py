@@ -537,3 +537,25 @@ def test_wavefront_kernel_large_and_launch_count(bc):
             e.close()
         assert np.array_equal(res[0][0], res[1][0]), L
         assert res[0][1] == 1 and res[1][1] >= 2 * n
+
+
+@pytest.mark.parametrize("L,boundary,n_rep,slab", [(64, 0, 3, False), (4096, 0, 1, False), (100, 0, 2, False), (33, 1, 2, False),
+                                                 (256, 0, 2, True)])
+def test_packed_wire_format_roundtrip(bc, L, boundary, n_rep, slab):
+    """bc_upload_packed / bc_download_packed (2 bits per site on the wire, converted on the device) move the same
+    lattices as the int8 calls: vector kernels for L % 64 == 0, per-byte kernels otherwise, slab geometry included."""
+    rng = np.random.default_rng(L)
+    s = rng.integers(-1, 2, size=(n_rep, L, L), dtype=np.int8)
+    e = bc.Engine(L, boundary, n_rep, 0, 5, slab=(1, 0, None) if slab else None)
+    e.set_params(*TC)
+    e.upload_packed(bc.pack_spins(s))
+    assert np.array_equal(e.download(), s)
+    e.sweep(3)
+    want = e.download()
+    got = bc.unpack_spins(e.download_packed(), L).reshape(n_rep, L, L)
+    assert np.array_equal(got, want)
+    one = bc.unpack_spins(e.download_packed(replica=n_rep - 1), L)
+    assert np.array_equal(one, want[n_rep - 1])
+    e.upload_packed(bc.pack_spins(s[0]), replica=n_rep - 1)
+    assert np.array_equal(e.download(n_rep - 1), s[0])
+    e.close()
