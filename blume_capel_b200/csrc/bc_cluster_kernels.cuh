@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(CL_LANES) cl_label_kernel(const __grid_constan
 #pragma unroll
     for (int i = lane; i < CL_SITES * 2 / 16; i += CL_LANES) dst[i] = src[i];
     A.out.hb[(size_t)tile * CL_T + lane] = ln.HB;
+    A.out.pm[(size_t)tile * 2 * CL_T + lane] = ln.P;
+    A.out.pm[(size_t)tile * 2 * CL_T + CL_T + lane] = ln.M;
     if (lane == t.h - 1) A.out.vbb[tile] = ln.VB;
 }
 
@@ -84,7 +86,7 @@ __device__ __forceinline__ void cl_reload_tile(const ClArgs& A, const ClTileId& 
 #pragma unroll
     for (int i = lane; i < CL_SITES * 2 / 16; i += CL_LANES) dst[i] = src[i];
     for (int i = 0; i < CL_SITES / 32 / CL_LANES; ++i) sm.flag[(CL_SITES / 32 / CL_LANES) * lane + i] = 0u;
-    cl_phase_reload(lane, A.g, t, A.c0, A.c1, A.out.hb + (size_t)t.tile * CL_T, ln);
+    cl_phase_reload(lane, t, A.out.pm + (size_t)t.tile * 2 * CL_T, A.out.hb + (size_t)t.tile * CL_T, ln);
     __syncthreads();
 }
 
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(CL_LANES) cl_flip_kernel(const __grid_constant
     cl_reload_tile(A, t, lane, sm, ln);
     cl_phase_decide(lane, A.g, t, A.rng, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);
     __syncthreads();
-    if (lane < t.h) cl_apply_flips(A.g, A.c0, A.c1, t.rep, t.x0, t.y0 + lane, cl_flip_mask(lane, sm, ln));
+    if (lane < t.h) cl_apply_flips(A.g, A.c0, A.c1, t.rep, t.x0, t.y0 + lane, ln.P, ln.M, cl_flip_mask(lane, sm, ln));
 }
 
 // Cluster labels for the measurements (cluster-size moments, gap-size histogram, cluster lists of the dumps):

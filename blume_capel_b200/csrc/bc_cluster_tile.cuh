@@ -304,6 +304,8 @@ struct ClLane {                   // registers of one thread: its tile row
 struct ClTileOut {
     uint16_t* par;        // [tile][4096]  raw copy of ClTileSmem::par (run-start entries: root | CL_FLAG)
     uint64_t* hb;         // [tile][64]
+    uint64_t* pm;         // [tile][2][64]  plus and minus masks of the rows (the flip kernel rewrites the spin bytes from
+                          //                them and never reads the lattice)
     uint64_t* vbb;        // [tile]        open bonds from the tile's last row into the tile below
     uint16_t* proot;      // [tile][256]   root of the perimeter sites: top row, bottom row, left column, right column
     uint32_t* gparent;    // [replica][L*L] global union-find, touched only at the site indices of flagged roots
@@ -430,12 +432,11 @@ BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileS
 
 // ---- consumers of a labelled tile -------------------------------------------------------------------------------
 // Reload what cl_label_kernel left: labels into shared memory (done by the caller), masks and runs of the thread's row.
-BC_HD void cl_phase_reload(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1,
-                           const uint64_t* hb_tile, ClLane& ln) {
+BC_HD void cl_phase_reload(int lane, const ClTileId& t, const uint64_t* pm_tile, const uint64_t* hb_tile, ClLane& ln) {
     ln.P = ln.M = ln.HB = ln.VB = ln.RS = 0;
     if (lane >= t.h) return;
-    cl_load_row(g, c0, c1, t.rep, t.x0, t.y0 + lane, &ln.P, &ln.M);
-    if (t.w < CL_T) { ln.P &= (1ull << t.w) - 1; ln.M &= (1ull << t.w) - 1; }
+    ln.P = pm_tile[lane];
+    ln.M = pm_tile[CL_T + lane];
     ln.HB = hb_tile[lane];
     ln.RS = (ln.P | ln.M) & ~(ln.HB << 1);
 }
@@ -481,23 +482,35 @@ BC_HD uint64_t cl_flip_mask(int lane, const ClLabelSmem& sm, const ClLane& ln) {
     return F & (ln.P | ln.M);
 }
 
-// Flip phase 3: apply a flip mask to the 64 spin bytes of a row (code 0 <-> code 2: xor 2)
-BC_HD void cl_apply_flips(const ClGeom& g, uint8_t* c0, uint8_t* c1, uint32_t rep, int x0, int gy, uint64_t F) {
+// Flip phase 3: the row's 64 spin bytes after the flips, written from the masks alone (code = 1 + plus - minus per
+// byte, no borrows between bytes); a row without a flipped site is not touched.  Even x live in array gy & 1.
+BC_HD void cl_apply_flips(const ClGeom& g, uint8_t* c0, uint8_t* c1, uint32_t rep, int x0, int gy, uint64_t P, uint64_t M, uint64_t F) {
     if (!F) return;
+    const uint64_t Pn = (P & ~F) | (M & F), Mn = (M & ~F) | (P & F);
     const size_t off = cl_row_offset(g, rep, gy) + (size_t)(x0 >> 1);
     uint8_t* ev = ((gy & 1) ? c1 : c0) + off;
     uint8_t* od = ((gy & 1) ? c0 : c1) + off;
+    const int vecs = (g.Wc - (x0 >> 1)) >= 32 ? 2 : ((g.Wc - (x0 >> 1)) >= 16 ? 1 : 0);
     const uint32_t fe = cl_squeeze(F), fo = cl_squeeze(F >> 1);
+    const uint32_t pe = cl_squeeze(Pn), po = cl_squeeze(Pn >> 1), me = cl_squeeze(Mn), mo = cl_squeeze(Mn >> 1);
+    BC_UNROLL
     for (int v = 0; v < 2; ++v) {
-        const uint32_t he = (fe >> (16 * v)) & 0xFFFFu, ho = (fo >> (16 * v)) & 0xFFFFu;
-        if (he) {
-            uint4 a = *reinterpret_cast<uint4*>(ev + 16 * v);
-            a.x ^= cl_bytes(he) << 1; a.y ^= cl_bytes(he >> 4) << 1; a.z ^= cl_bytes(he >> 8) << 1; a.w ^= cl_bytes(he >> 12) << 1;
+        if (v >= vecs) break;
+        const int sh = 16 * v;
+        if ((fe >> sh) & 0xFFFFu) {
+            uint4 a;
+            a.x = 0x01010101u + cl_bytes(pe >> sh) - cl_bytes(me >> sh);
+            a.y = 0x01010101u + cl_bytes(pe >> (sh + 4)) - cl_bytes(me >> (sh + 4));
+            a.z = 0x01010101u + cl_bytes(pe >> (sh + 8)) - cl_bytes(me >> (sh + 8));
+            a.w = 0x01010101u + cl_bytes(pe >> (sh + 12)) - cl_bytes(me >> (sh + 12));
             *reinterpret_cast<uint4*>(ev + 16 * v) = a;
         }
-        if (ho) {
-            uint4 b = *reinterpret_cast<uint4*>(od + 16 * v);
-            b.x ^= cl_bytes(ho) << 1; b.y ^= cl_bytes(ho >> 4) << 1; b.z ^= cl_bytes(ho >> 8) << 1; b.w ^= cl_bytes(ho >> 12) << 1;
+        if ((fo >> sh) & 0xFFFFu) {
+            uint4 b;
+            b.x = 0x01010101u + cl_bytes(po >> sh) - cl_bytes(mo >> sh);
+            b.y = 0x01010101u + cl_bytes(po >> (sh + 4)) - cl_bytes(mo >> (sh + 4));
+            b.z = 0x01010101u + cl_bytes(po >> (sh + 8)) - cl_bytes(mo >> (sh + 8));
+            b.w = 0x01010101u + cl_bytes(po >> (sh + 12)) - cl_bytes(mo >> (sh + 12));
             *reinterpret_cast<uint4*>(od + 16 * v) = b;
         }
     }

@@ -129,6 +129,7 @@ struct bc_engine {
     // cluster labelling (allocated on first use): what a labelled tile leaves between kernels (bc_cluster_tile.cuh)
     uint16_t* cl_par = nullptr;             // [tile][4096] labels
     uint64_t* cl_hb = nullptr;              // [tile][64] open bonds to the right
+    uint64_t* cl_pm = nullptr;              // [tile][2][64] plus / minus masks of the rows
     uint64_t* cl_vbb = nullptr;             // [tile] open bonds into the tile below
     uint16_t* cl_proot = nullptr;           // [tile][256] roots of the perimeter sites
     uint32_t* cl_gparent = nullptr;         // [replica][L*L] global union-find over flagged tile roots (sparse)
@@ -256,7 +257,7 @@ extern "C" void bc_destroy(bc_engine* e) {
     cudaFree(e->d_bar);
     if (e->ev_group) cudaEventDestroy(e->ev_group);
     cudaFree(e->d_clock);
-    cudaFree(e->cl_par); cudaFree(e->cl_hb); cudaFree(e->cl_vbb); cudaFree(e->cl_proot); cudaFree(e->cl_gparent);
+    cudaFree(e->cl_par); cudaFree(e->cl_hb); cudaFree(e->cl_pm); cudaFree(e->cl_vbb); cudaFree(e->cl_proot); cudaFree(e->cl_gparent);
     cudaFree(e->cl_labels); cudaFree(e->d_bond_thr); cudaFree(e->d_csize); cudaFree(e->d_cmom);
     cudaFree(e->cl_sort[0]); cudaFree(e->cl_sort[1]); cudaFree(e->cl_sort_hist); cudaFree(e->cl_count);
     cudaFree(e->cl_sites); cudaFree(e->cl_starts); cudaFree(e->cl_ordinal); cudaFree(e->cl_signs); cudaFree(e->cl_nclusters);

@@ -11,6 +11,7 @@ static int cluster_alloc(bc_engine* e) {
     const size_t N = (size_t)e->L * (size_t)e->L;
     BC_CUDA(e, cudaMalloc(&e->cl_par, n_tiles * CL_SITES * sizeof(uint16_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_hb, n_tiles * CL_T * sizeof(uint64_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_pm, n_tiles * 2 * CL_T * sizeof(uint64_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_vbb, n_tiles * sizeof(uint64_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_proot, n_tiles * 256 * sizeof(uint16_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_gparent, (size_t)e->n_rep * N * sizeof(uint32_t)));
@@ -30,7 +31,7 @@ static int cluster_args(bc_engine* e, const char* who, bool random_bonds, int64_
     A->g.open = e->boundary == BC_OPEN;
     A->g.tiles_x = A->g.tiles_y = (e->L + CL_T - 1) / CL_T;
     A->c0 = e->d_c[0]; A->c1 = e->d_c[1];
-    A->out.par = e->cl_par; A->out.hb = e->cl_hb; A->out.vbb = e->cl_vbb; A->out.proot = e->cl_proot; A->out.gparent = e->cl_gparent;
+    A->out.par = e->cl_par; A->out.hb = e->cl_hb; A->out.pm = e->cl_pm; A->out.vbb = e->cl_vbb; A->out.proot = e->cl_proot; A->out.gparent = e->cl_gparent;
     A->rng.thr = random_bonds ? e->d_bond_thr : nullptr;  // per replica: p = 1 - exp(-2 J / T) (main.cpp:115)
     A->rng.k0 = (uint32_t)e->seed; A->rng.k1 = (uint32_t)(e->seed >> 32);
     A->rng.c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu); A->rng.c_hi = (uint32_t)((uint64_t)cstep >> 32);

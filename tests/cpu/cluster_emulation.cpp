@@ -17,7 +17,7 @@ struct Lattice {
     ClGeom g;
     std::vector<uint8_t> c0, c1;  // compact colour arrays of ONE replica (with or without ghost rows)
     std::vector<uint16_t> par;
-    std::vector<uint64_t> hb, vbb;
+    std::vector<uint64_t> hb, pm, vbb;
     std::vector<uint16_t> proot;
     std::vector<uint32_t> gparent;
     uint32_t n_tiles;
@@ -36,10 +36,10 @@ void build(Lattice& lt, int L, int open, int ghost, const int8_t* spins) {
             (((x + y) & 1) ? lt.c1 : lt.c0)[(size_t)(g.row_first + y) * g.Wc + (x >> 1)] = (uint8_t)(spins[(size_t)y * L + x] + 1);
     lt.n_tiles = (uint32_t)(g.tiles_x * g.tiles_y);
     lt.par.assign((size_t)lt.n_tiles * CL_SITES, 0xEEEE);
-    lt.hb.assign((size_t)lt.n_tiles * CL_T, 0); lt.vbb.assign(lt.n_tiles, 0);
+    lt.hb.assign((size_t)lt.n_tiles * CL_T, 0); lt.pm.assign((size_t)lt.n_tiles * 2 * CL_T, 0); lt.vbb.assign(lt.n_tiles, 0);
     lt.proot.assign((size_t)lt.n_tiles * 256, CL_NONE);
     lt.gparent.assign((size_t)L * L, 0xDDDDDDDDu);
-    lt.out = ClTileOut{lt.par.data(), lt.hb.data(), lt.vbb.data(), lt.proot.data(), lt.gparent.data()};
+    lt.out = ClTileOut{lt.par.data(), lt.hb.data(), lt.pm.data(), lt.vbb.data(), lt.proot.data(), lt.gparent.data()};
 }
 
 // lanes of a phase in a seeded random order: a phase must not depend on the order its threads run in
@@ -82,6 +82,8 @@ void label(Lattice& lt, const ClRng& rng) {
         std::memcpy(lt.out.par + (size_t)tile * CL_SITES, sm.par, sizeof(sm.par));
         for (int l = 0; l < CL_LANES; ++l) {
             lt.out.hb[(size_t)tile * CL_T + l] = ln[l].HB;
+            lt.out.pm[(size_t)tile * 2 * CL_T + l] = ln[l].P;
+            lt.out.pm[(size_t)tile * 2 * CL_T + CL_T + l] = ln[l].M;
             if (l == t.h - 1) lt.out.vbb[tile] = ln[l].VB;
         }
     }
@@ -111,7 +113,7 @@ void reload(Lattice& lt, const ClTileId& t, ClLabelSmem& sm, ClLane (&ln)[CL_LAN
     std::memset(&sm, 0xCD, sizeof(sm));
     std::memcpy(sm.par, lt.out.par + (size_t)t.tile * CL_SITES, sizeof(sm.par));
     std::memset(sm.flag, 0, sizeof(sm.flag));
-    for (int l = 0; l < CL_LANES; ++l) cl_phase_reload(l, lt.g, t, lt.c0.data(), lt.c1.data(), lt.out.hb + (size_t)t.tile * CL_T, ln[l]);
+    for (int l = 0; l < CL_LANES; ++l) cl_phase_reload(l, t, lt.out.pm + (size_t)t.tile * 2 * CL_T, lt.out.hb + (size_t)t.tile * CL_T, ln[l]);
 }
 }  // namespace
 
@@ -133,7 +135,7 @@ int emu_cluster_update(int L, int open, int ghost, int8_t* spins, uint32_t thr, 
         reload(lt, t, sm, ln);
         for (int l = CL_LANES - 1; l >= 0; --l) cl_phase_decide(l, lt.g, t, rng, sm, ln[l], lt.out.gparent);
         for (int l = 0; l < CL_LANES; ++l)
-            if (l < t.h) cl_apply_flips(lt.g, lt.c0.data(), lt.c1.data(), t.rep, t.x0, t.y0 + l, cl_flip_mask(l, sm, ln[l]));
+            if (l < t.h) cl_apply_flips(lt.g, lt.c0.data(), lt.c1.data(), t.rep, t.x0, t.y0 + l, ln[l].P, ln[l].M, cl_flip_mask(l, sm, ln[l]));
     }
     for (int y = 0; y < L; ++y)
         for (int x = 0; x < L; ++x)
