@@ -165,6 +165,7 @@ struct bc_engine {
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
     bool resident_attr_set[4] = {false, false, false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
+    int sm_count = 148;
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
     int opt_swp_min_rows = 32;  // ... with software-pipelined Philox draws from this many rows on (0 = never)
     int opt_force_generic = 0;
@@ -325,6 +326,7 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
         return (int)BC_ERR_CUDA;
     };
     if ((st = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", st);
+    if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || e->sm_count < 1) e->sm_count = 148;
     if ((st = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", st);
     if ((st = cudaEventCreate(&e->ev0)) != cudaSuccess) return bail("event", st);
     if ((st = cudaEventCreate(&e->ev1)) != cudaSuccess) return bail("event", st);

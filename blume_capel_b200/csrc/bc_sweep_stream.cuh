@@ -55,7 +55,7 @@ struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; }
 template <bool SMALL, bool MEASURE, bool OPEN, int PAIR, bool HALO = false>
 struct FastMinBlocks {
     static constexpr int value =
-        (MEASURE || SMALL || HALO || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+        (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
 };
 
 // HALO launches: CTA order inside a replica.  A replica has C = items / 128 CTAs in item order (strip-major); the

@@ -93,6 +93,17 @@ static LaunchPlan make_plan(const bc_engine* e) {
             p.pair = (e->opt_swp_min_rows > 0 && R >= e->opt_swp_min_rows) ? 2 : 1;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
+        // Wave fit.  The pipelined kernel (80 registers) runs 6 CTAs per SM, the plain pair-table kernel (72) runs 7.
+        // A grid of a few waves pays for a partly filled last wave: the bench batch is 4096 CTAs = 4.61 waves of
+        // 888 but 3.95 waves of 1036, and the per-GPU share of L = 65536 on 8 GPUs likewise; there the 2 % the
+        // pipelined draws gain per row are less than what the fifth wave costs (profiles/r02_tune_waves.jsonl:
+        // 1847 -> 1865 and 1780 -> 1805 updates/ns).  Strips of two heights that make the grid a whole number of
+        // waves were tried first and cost every instantiation 30 .. 150 bytes of spills.
+        if (p.pair == 2 && e->opt_swp_min_rows == 32 && e->opt_rows == 0) {
+            const long long s6 = 6LL * e->sm_count, s7 = 7LL * e->sm_count;
+            const long long w6 = (p.grid + s6 - 1) / s6, w7 = (p.grid + s7 - 1) / s7;
+            if (w7 < w6 && w6 <= 6) p.pair = 1;
+        }
     } else {
         const long long items = (long long)e->n_rep * L * ((L + 1) / 2);
         p.grid = (unsigned)((items + 255) / 256);

@@ -13,6 +13,7 @@
 // interleaves Wolff clusters, main.cpp:162); --seed makes the run reproducible (the reference seeds from
 // random_device).
 #include <cerrno>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -48,7 +49,7 @@ int main(int argc, const char* argv[]) {
         if (argc < 8) {
             std::cerr << "usage: bc_run run root burn nsteps T D J [--L n] [--boundary periodic|open] [--seed s]\n"
                          "              [--device d] [--burn-sweeps n] [--sweeps-per-sample n] [--obs file.csv]\n"
-                         "              [--cluster-every k] [--no-fk] [--mkdir] [--save-state f] [--load-state f]\n";
+                         "              [--cluster-every k] [--no-fk] [--mkdir] [--save-state f] [--load-state f] [--time-dumps]\n";
             return 2;
         }
         run = std::atoi(argv[1]); root = argv[2]; burn = std::atoi(argv[3]); nsteps = std::atoi(argv[4]);
@@ -56,7 +57,7 @@ int main(int argc, const char* argv[]) {
         argi = 8;
     }
     int L = 64, device = 0, boundary = BC_PERIODIC;
-    bool have_seed = false, write_fk = true, do_mkdir = false;
+    bool have_seed = false, write_fk = true, do_mkdir = false, time_dumps = false;
     uint64_t seed = 0;
     int64_t burn_sweeps = -1, sweeps_per_sample = -1, cluster_every = 0;
     std::string obs_path, save_state, load_state;
@@ -75,6 +76,7 @@ int main(int argc, const char* argv[]) {
         else if (a == "--load-state") load_state = next();
         else if (a == "--no-fk") write_fk = false;
         else if (a == "--mkdir") do_mkdir = true;
+        else if (a == "--time-dumps") time_dumps = true;
         else { std::cerr << "bc_run: unknown flag " << a << std::endl; return 2; }
     }
     if (!have_seed) { std::random_device rd; seed = ((uint64_t)rd() << 32) | rd(); }  // like main.cpp:307-309
@@ -186,14 +188,22 @@ int main(int argc, const char* argv[]) {
                          (long long)o.Q, (long long)o.B, E, m, q);
         // the clusters are formed on the GPU (labelling + sort by cluster); the host only prints decimals
         const std::string name = std::to_string(i) + ".txt";
-        int64_t n_sites = 0, n_clusters = 0;
-        if (bc_cluster_lists(eng, 0, 0, 0, l_sites.data(), l_starts.data(), l_signs.data(), &n_sites, &n_clusters) != BC_OK)
-            return die(eng, "bc_cluster_lists");
-        bcgap::write_file(spin_dir + name, bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters));  // main.cpp:369-370
-        if (write_fk) {  // main.cpp:371-372: bonds open with probability 1 - exp(-2J/T), bond counter = the sample index
-            if (bc_cluster_lists(eng, 0, 1, i, l_sites.data(), l_starts.data(), l_signs.data(), &n_sites, &n_clusters) != BC_OK)
+        for (int kind = 0; kind < (write_fk ? 2 : 1); ++kind) {  // main.cpp:369-370 (spin/), :371-372 (fk/, bond counter = sample index)
+            int64_t n_sites = 0, n_clusters = 0;
+            const auto t0 = std::chrono::steady_clock::now();
+            if (bc_cluster_lists(eng, 0, kind, kind ? i : 0, l_sites.data(), l_starts.data(), l_signs.data(), &n_sites, &n_clusters) != BC_OK)
                 return die(eng, "bc_cluster_lists");
-            bcgap::write_file(fk_dir + name, bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters));
+            const auto t1 = std::chrono::steady_clock::now();
+            const std::string text = bcgap::lists_to_gap(l_sites.data(), l_starts.data(), l_signs.data(), n_clusters);
+            const auto t2 = std::chrono::steady_clock::now();
+            bcgap::write_file((kind ? fk_dir : spin_dir) + name, text);
+            const auto t3 = std::chrono::steady_clock::now();
+            if (time_dumps) {
+                auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+                std::fprintf(stderr, "{\"dump\": \"%s/%d\", \"L\": %d, \"clusters\": %lld, \"sites\": %lld, \"bytes\": %zu, "
+                                     "\"gpu_lists_ms\": %.2f, \"format_ms\": %.2f, \"write_ms\": %.2f}\n", kind ? "fk" : "spin", i, L,
+                             (long long)n_clusters, (long long)n_sites, text.size(), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+            }
         }
     }
     if (obs_file) std::fclose(obs_file);

@@ -272,12 +272,30 @@ def test_headline_plan_matches_oracle(bc, oracle, L, n_rep):
 
 
 def test_headline_plan_is_what_bench_runs(bc):
-    """bench.py's workload (64 replicas of L = 4096) must resolve to plan 4 with 64-row strips by itself."""
+    """bench.py's workload (64 replicas of L = 4096) resolves by itself to 64-row strips with the pair table; of the two
+    64-row kernels the plan takes the one whose resident CTAs fit the 4096-CTA grid in whole waves (7 CTAs per SM:
+    3.95 waves; the pipelined kernel's 6 per SM: 4.61).  Both are compared with the oracle at 64-row strips above /
+    below; an explicit "swp_min_rows" keeps the pipelined kernel."""
     e = bc.Engine(4096, bc.PERIODIC, 64, 0, 1)
     e.set_params(*TC)
     plan = e.plan()
+    e.set_option("swp_min_rows", 16)
+    forced = e.plan()
     e.close()
-    assert plan["pipelined"] and plan["rows_per_thread"] == 64, plan
+    assert plan["pair"] and plan["rows_per_thread"] == 64, plan
+    assert forced["pipelined"] and forced["rows_per_thread"] == 64, forced
+
+
+@pytest.mark.parametrize("L,n_rep", [(1024, 2), (2048, 1)])
+def test_headline_plan_without_pipelined_draws_matches_oracle(bc, oracle, L, n_rep):
+    """64-row strips with the pair table and without pipelined draws (what the auto plan picks for the bench batch)."""
+    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, n_rep, 20, 0xBE7C5 + L, measure_every=7,
+                                            opts=(("rows_per_thread", 64), ("swp_min_rows", 0), ("resident", 0)))
+    assert plan["pair"] and not plan["pipelined"] and plan["rows_per_thread"] == 64, plan
+    assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
+    for r in range(n_rep):
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
 
 
 @pytest.mark.parametrize("L,n_rep,rows,boundary", [(128, 2, 0, 0), (256, 1, 8, 0), (256, 2, 16, 1), (512, 2, 32, 0),
