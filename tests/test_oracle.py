@@ -105,8 +105,16 @@ def test_oracle_statistics_vs_exact_enumeration(oracle):
     assert abs(E.mean() - exact["E"]) < 5 * err(E)
     assert abs(np.abs(m).mean() - exact["absm"]) < 5 * err(np.abs(m))
     assert abs(q.mean() - exact["q"]) < 5 * err(q)
-    u4 = 1 - (m**4).mean() / (3 * (m**2).mean() ** 2)
-    assert abs(u4 - exact["U4"]) < 0.01
+    # U4 is a ratio of moments: jackknife over 50 bins for its error bar
+    nb = 50
+    mb = m[: len(m) // nb * nb].reshape(nb, -1)
+
+    def u4_of(x):
+        return 1 - (x**4).mean() / (3 * (x**2).mean() ** 2)
+
+    jk = np.array([u4_of(np.delete(mb, i, axis=0)) for i in range(nb)])
+    u4_err = math.sqrt((nb - 1) / nb * ((jk - jk.mean()) ** 2).sum())
+    assert abs(u4_of(mb) - exact["U4"]) < 5 * u4_err and u4_err < 0.01, (u4_of(mb), exact["U4"], u4_err)
 
 
 def test_J0_limit(oracle):
