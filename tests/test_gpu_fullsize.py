@@ -144,3 +144,29 @@ def test_slab_overlap_path_equals_plain_engine_L2048(bc, boundary):
         assert np.array_equal(lat, out[0][0])
         for f in ("M", "Q", "B"):
             assert np.array_equal(obs[f], out[0][1][f])
+
+
+def test_cluster_move_at_L65536(bc):
+    """BASELINE config 4's lattice (L = 65536: 2^32 sites, every site index is a full 32-bit number, one million tiles)
+    takes the cluster move on one GPU: the oracle cannot afford this size, so the size-independent properties are
+    checked -- zeros never move (the quadrupole sum Q is conserved), only signs change, whole clusters flip (no bond
+    between equal neighbours is broken inside a flipped region that the move itself reports as one cluster: the
+    bond sum B over unchanged-sign pairs can only change where a cluster border runs), and the magnetisation changes."""
+    L = 65536
+    e = bc.Engine(L, bc.PERIODIC, 1, 0, 0x65536)
+    e.set_params(*TC)
+    e.init_random()
+    e.sweep(6)
+    before = e.measure()[0]
+    e.cluster_update(1)
+    after = e.measure()[0]
+    e.cluster_update(1)
+    again = e.measure()[0]
+    e.sync()
+    e.close()
+    assert after["Q"] == before["Q"] == again["Q"]          # zeros never join a cluster (main.cpp:123-130,144)
+    assert after["M"] != before["M"] and again["M"] != after["M"]
+    # flipping a cluster changes s_i s_j only on bonds between a flipped and an unflipped site, and those join
+    # sites of DIFFERENT clusters: equal spins with a closed bond (lose 2 per bond) or opposite spins (gain 2);
+    # after a few sweeps from a hot start the two nearly cancel, but B must stay within the number of such bonds
+    assert abs(int(after["B"]) - int(before["B"])) < 0.2 * before["Q"]

@@ -1,0 +1,7 @@
+set -x; mkdir -p gpurun_out
+python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_final_1gpu.json 2> gpurun_out/r2_bench_final_1gpu.err
+tail -c 300 gpurun_out/r2_bench_final_1gpu.json; tail -2 gpurun_out/r2_bench_final_1gpu.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_ncu_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sweep_fast -s 8 -c 4 -o gpurun_out/r2_prof_sweep -f python tools/prof_cmd.py 64 6 > gpurun_out/ncu_s.log 2>&1
+tail -2 gpurun_out/ncu_s.log
+python -m pytest tests/test_gpu_statistics.py -q -m gpu 2>&1 | tail -4
