@@ -24,7 +24,22 @@ struct ClArgs {
     ClRng rng;
     uint32_t n_tiles;      // tiles of all replicas
     uint32_t* labels;      // cl_labels_kernel: [replica][L*L] smallest site of the cluster, 0xFFFFFFFF for a zero spin
+    // the global union-find: one piece per rank ([replica][rows per rank * L] each; a whole lattice: one piece)
+    uint32_t* gbase[CL_MAX_RANKS];
+    uint32_t sites_per_rank;   // 0 = one piece
+    size_t rep_stride;         // entries between the pieces of consecutive replicas
+    // slab of a multi-rank decomposition: the perimeter roots of the rank below (peer memory) and its first global row
+    const uint16_t* proot_below;
+    int y_glob0_below;
 };
+
+__device__ __forceinline__ ClGlobal cl_global_of(const ClArgs& A, uint32_t rep) {
+    ClGlobal G;
+#pragma unroll
+    for (int k = 0; k < CL_MAX_RANKS; ++k) G.base[k] = A.gbase[k] ? A.gbase[k] + (size_t)rep * A.rep_stride : nullptr;
+    G.sites_per_rank = A.sites_per_rank;
+    return G;
+}
 
 // One CTA of 64 threads per tile, thread l = tile row l (10.75 KB of shared memory: 21 tiles per SM)
 __global__ void __launch_bounds__(CL_LANES) cl_label_kernel(const __grid_constant__ ClArgs A) {
@@ -42,7 +57,7 @@ __global__ void __launch_bounds__(CL_LANES) cl_label_kernel(const __grid_constan
     while (__syncthreads_or(cl_phase_jump(lane, sm, ln))) {}
     cl_phase_perimeter(lane, t, sm, ln, A.out.proot + (size_t)tile * 256);
     __syncthreads();
-    cl_phase_finish(lane, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);
+    cl_phase_finish(lane, A.g, t, sm, ln, cl_global_of(A, t.rep));
     __syncthreads();
     // what the following kernels need: labels (raw 8 KB copy), bond masks of the rows, bonds into the tile below
     const uint4* src = reinterpret_cast<const uint4*>(sm.par);
@@ -64,6 +79,7 @@ __global__ void __launch_bounds__(128) cl_border_kernel(const __grid_constant__ 
     const int j = threadIdx.x & 63, down = threadIdx.x >> 6;
     uint32_t a, b;
     ClTileId n = t;
+    ClGeom gn = A.g;  // geometry the neighbour tile's site indices are computed with
     if (!down) {
         if (j >= t.h || !((A.out.hb[(size_t)tile * CL_T + j] >> (t.w - 1)) & 1ull)) return;
         n = cl_tile_id(A.g, tile - (uint32_t)t.tx + (uint32_t)((t.tx + 1) % A.g.tiles_x));
@@ -71,12 +87,17 @@ __global__ void __launch_bounds__(128) cl_border_kernel(const __grid_constant__ 
         b = A.out.proot[(size_t)n.tile * 256 + 128 + j];
     } else {
         if (j >= t.w || !((A.out.vbb[tile] >> j) & 1ull)) return;
+        const bool last = t.ty + 1 == A.g.tiles_y;
         n = cl_tile_id(A.g, tile - (uint32_t)(t.ty * A.g.tiles_x) + (uint32_t)(((t.ty + 1) % A.g.tiles_y) * A.g.tiles_x));
         a = A.out.proot[(size_t)tile * 256 + 64 + j];
-        b = A.out.proot[(size_t)n.tile * 256 + j];
+        if (last && A.g.multi) {  // the tile below belongs to the next rank: same tile geometry, its rows, its perimeter roots
+            gn.y_glob0 = A.y_glob0_below;
+            b = A.proot_below[(size_t)n.tile * 256 + j];
+        } else {
+            b = A.out.proot[(size_t)n.tile * 256 + j];
+        }
     }
-    uint32_t* gp = A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L;
-    cl_gunion(gp, cl_global_site(A.g, t, a), cl_global_site(A.g, n, b));
+    cl_gunion(cl_global_of(A, t.rep), cl_global_site(A.g, t, a), cl_global_site(gn, n, b));
 }
 
 // reload a labelled tile: labels into shared memory, masks and runs of the thread's row into registers
@@ -97,7 +118,7 @@ __global__ void __launch_bounds__(CL_LANES) cl_flip_kernel(const __grid_constant
     const ClTileId t = cl_tile_id(A.g, blockIdx.x);
     ClLane ln;
     cl_reload_tile(A, t, lane, sm, ln);
-    cl_phase_decide(lane, A.g, t, A.rng, sm, ln, A.out.gparent + (size_t)t.rep * (size_t)A.g.L * (size_t)A.g.L);
+    cl_phase_decide(lane, A.g, t, A.rng, sm, ln, cl_global_of(A, t.rep));
     __syncthreads();
     if (lane < t.h) cl_apply_flips(A.g, A.c0, A.c1, t.rep, t.x0, t.y0 + lane, ln.P, ln.M, cl_flip_mask(lane, sm, ln));
 }
@@ -112,7 +133,7 @@ __global__ void __launch_bounds__(CL_LANES) cl_labels_kernel(const __grid_consta
     cl_reload_tile(A, t, lane, sm, ln);
     const size_t N = (size_t)A.g.L * (size_t)A.g.L;
     if (lane < t.h)
-        cl_row_labels(lane, A.g, t, sm, ln, A.out.gparent + (size_t)t.rep * N,
+        cl_row_labels(lane, A.g, t, sm, ln, cl_global_of(A, t.rep),
                       A.labels + (size_t)t.rep * N + (size_t)(t.y0 + lane) * (size_t)A.g.L + (size_t)t.x0);
 }
 

@@ -79,7 +79,7 @@ BC_HD void cl_or32(uint32_t* p, uint32_t v) {
 }
 BC_HD uint32_t cl_cas32(uint32_t* p, uint32_t cmp, uint32_t val) {
 #if defined(__CUDA_ARCH__)
-    return atomicCAS(p, cmp, val);
+    return atomicCAS_system(p, cmp, val);
 #else
     const uint32_t old = *p;
     if (old == cmp) *p = val;
@@ -129,6 +129,9 @@ BC_HD uint32_t cl_bytes(uint32_t n) { return ((n & 0xFu) * 0x00204081u) & 0x0101
 struct ClGeom {
     int L, Wc, rows_arr, row_first, open;
     int tiles_x, tiles_y;
+    int Ly;        // rows this handle owns (L, or L / n_ranks for a slab of a multi-rank decomposition)
+    int y_glob0;   // global row of its first row: bond draws and cluster names use GLOBAL coordinates
+    int multi;     // slab of a multi-rank decomposition: the row below the last owned row is the bottom ghost row
 };
 struct ClTileId {
     uint32_t rep;
@@ -145,11 +148,11 @@ BC_HD ClTileId cl_tile_id(const ClGeom& g, uint32_t tile) {
     t.tx = (int)(in - (uint32_t)t.ty * (uint32_t)g.tiles_x);
     t.x0 = t.tx * CL_T; t.y0 = t.ty * CL_T;
     t.w = g.L - t.x0 < CL_T ? g.L - t.x0 : CL_T;
-    t.h = g.L - t.y0 < CL_T ? g.L - t.y0 : CL_T;
+    t.h = g.Ly - t.y0 < CL_T ? g.Ly - t.y0 : CL_T;
     return t;
 }
 BC_HD uint32_t cl_global_site(const ClGeom& g, const ClTileId& t, uint32_t local) {
-    return (uint32_t)(t.y0 + (int)(local >> 6)) * (uint32_t)g.L + (uint32_t)(t.x0 + (int)(local & 63u));
+    return (uint32_t)(g.y_glob0 + t.y0 + (int)(local >> 6)) * (uint32_t)g.L + (uint32_t)(t.x0 + (int)(local & 63u));
 }
 BC_HD size_t cl_row_offset(const ClGeom& g, uint32_t rep, int gy) {
     return ((size_t)rep * (size_t)g.rows_arr + (size_t)(g.row_first + gy)) * (size_t)g.Wc;
@@ -247,25 +250,40 @@ BC_HD uint16_t cl_union(uint16_t* par, uint16_t a, uint16_t b) {
     }
     return rb;
 }
-// the same over global site indices (clusters that cross tile borders)
-BC_HD uint32_t cl_gfind(volatile uint32_t* par, uint32_t a) {
-    uint32_t p = par[a];
+// The same over GLOBAL site indices (clusters that cross tile borders).  The array is indexed by site; when the lattice
+// is split into row slabs over several GPUs every rank holds the entries of its own rows and maps the other ranks'
+// pieces through peer memory (parents point at smaller sites, i.e. at the same or a lower rank; the compare-and-swap
+// and the loads are system-scope and cross NVLink).
+constexpr int CL_MAX_RANKS = 8;
+struct ClGlobal {
+    uint32_t* base[CL_MAX_RANKS];  // base[k]: rank k's piece (this replica's); a single piece: everything in base[0]
+    uint32_t sites_per_rank;       // rows per rank * L; 0 = a single piece
+};
+BC_HD uint32_t* cl_gslot(const ClGlobal& G, uint32_t site) {
+    if (G.sites_per_rank == 0u) return G.base[0] + site;
+    const uint32_t k = site / G.sites_per_rank;
+    return G.base[k] + (site - k * G.sites_per_rank);
+}
+BC_HD uint32_t cl_gfind(const ClGlobal& G, uint32_t a) {
+    volatile uint32_t* sa = cl_gslot(G, a);
+    uint32_t p = *sa;
     while (p != a) {
-        const uint32_t gp = par[p];
-        if (gp != p) par[a] = gp;
-        a = p;
+        volatile uint32_t* sp = cl_gslot(G, p);
+        const uint32_t gp = *sp;
+        if (gp != p) *sa = gp;
+        a = p; sa = sp;
         p = gp;
     }
     return a;
 }
-BC_HD void cl_gunion(uint32_t* par, uint32_t a, uint32_t b) {
-    uint32_t ra = cl_gfind(par, a), rb = cl_gfind(par, b);
+BC_HD void cl_gunion(const ClGlobal& G, uint32_t a, uint32_t b) {
+    uint32_t ra = cl_gfind(G, a), rb = cl_gfind(G, b);
     while (ra != rb) {
         if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
-        const uint32_t old = cl_cas32(par + ra, ra, rb);
+        const uint32_t old = cl_cas32(cl_gslot(G, ra), ra, rb);
         if (old == ra) break;
-        ra = cl_gfind(par, old);
-        rb = cl_gfind(par, rb);
+        ra = cl_gfind(G, old);
+        rb = cl_gfind(G, rb);
     }
 }
 
@@ -330,7 +348,8 @@ BC_HD void cl_phase_load(int lane, const ClGeom& g, const ClTileId& t, const uin
 // Phase 2: candidate bonds (equal non-zero neighbours), random bonds, runs.
 BC_HD void cl_phase_bonds(int lane, const ClGeom& g, const ClTileId& t, const uint8_t* c0, const uint8_t* c1, const ClRng& rng,
                           ClTileSmem& sm, ClLane& ln) {
-    const int r = lane, gy = t.y0 + r;
+    const int r = lane, gy = t.y0 + r;             // row of the handle's own piece (array row row_first + gy)
+    const uint32_t yg = (uint32_t)(g.y_glob0 + gy);  // global row: the bond draws are functions of global coordinates
     ln.HB = ln.VB = ln.RS = 0;
     if (r < t.h) {
         const uint64_t P = ln.P, M = ln.M;
@@ -347,8 +366,10 @@ BC_HD void cl_phase_bonds(int lane, const ClGeom& g, const ClTileId& t, const ui
         uint64_t Pd = 0, Md = 0;
         if (r + 1 < t.h) { Pd = sm.plus[r + 1]; Md = sm.minus[r + 1]; }
         else {
+            // below the tile: the handle's next row; below its last row the wrap (whole lattice) or the bottom ghost
+            // row, array row row_first + Ly (slab of a multi-rank decomposition); nothing below an open lattice
             int ny = gy + 1;
-            if (ny == g.L) ny = g.open ? -1 : 0;
+            if (ny == g.Ly) ny = (g.open && yg + 1u == (uint32_t)g.L) ? -1 : (g.multi ? g.Ly : 0);
             if (ny >= 0 && ny != gy) {
                 cl_load_row(g, c0, c1, t.rep, t.x0, ny, &Pd, &Md);
                 if (t.w < CL_T) { Pd &= (1ull << t.w) - 1; Md &= (1ull << t.w) - 1; }
@@ -357,8 +378,8 @@ BC_HD void cl_phase_bonds(int lane, const ClGeom& g, const ClTileId& t, const ui
         uint64_t vc = (P & Pd) | (M & Md);
         if (rng.thr) {
             const uint32_t thr = rng.thr[t.rep];
-            hc = cl_draw_bonds(hc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 0u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
-            vc = cl_draw_bonds(vc, (uint32_t)gy, (uint32_t)t.x0 >> 5, 1u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+            hc = cl_draw_bonds(hc, yg, (uint32_t)t.x0 >> 5, 0u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
+            vc = cl_draw_bonds(vc, yg, (uint32_t)t.x0 >> 5, 1u, thr, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep);
         }
         ln.HB = hc; ln.VB = vc;
         ln.RS = (P | M) & ~(hc << 1);
@@ -419,13 +440,13 @@ BC_HD void cl_phase_perimeter(int lane, const ClTileId& t, ClTileSmem& sm, const
 
 // Phase 6: the root's flag into every run start's entry (written by its owner, read by nobody else in this phase);
 // flagged roots become nodes of the global union-find
-BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, uint32_t* gparent_rep) {
+BC_HD void cl_phase_finish(int lane, const ClGeom& g, const ClTileId& t, ClTileSmem& sm, const ClLane& ln, const ClGlobal& G) {
     cl_for_bits(ln.RS, [&](int x) {
         const uint16_t i = (uint16_t)(lane * CL_T + x);
         const uint16_t root = sm.par[i];
         if ((sm.flag[root >> 5] >> (root & 31u)) & 1u) {
             sm.par[i] = root | CL_FLAG;
-            if (root == i) { const uint32_t s = cl_global_site(g, t, i); gparent_rep[s] = s; }
+            if (root == i) { const uint32_t s = cl_global_site(g, t, i); *cl_gslot(G, s) = s; }
         }
     });
 }
@@ -442,11 +463,12 @@ BC_HD void cl_phase_reload(int lane, const ClTileId& t, const uint64_t* pm_tile,
 }
 
 // smallest site of the cluster of tile-local root entry `e` (root | flag)
-BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, uint32_t* gparent_rep) {
+BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, const ClGlobal& G) {
     const uint32_t s = cl_global_site(g, t, e & CL_IDX);
     if (!(e & CL_FLAG)) return s;
-    const uint32_t root = cl_gfind(gparent_rep, s);
-    if (gparent_rep[s] != root) gparent_rep[s] = root;  // later lookups of this tile root take one hop
+    const uint32_t root = cl_gfind(G, s);
+    uint32_t* slot = cl_gslot(G, s);
+    if (*slot != root) *slot = root;  // later lookups of this tile root take one hop
     return root;
 }
 
@@ -454,14 +476,14 @@ BC_HD uint32_t cl_cluster_site(const ClGeom& g, const ClTileId& t, uint16_t e, u
 // thread's own row is made up front by all threads together (an unflagged root is a site of the row; inside the loop
 // over the run starts, where the threads meet their roots at different iterations, it ran at a seventh of the lanes).
 BC_HD void cl_phase_decide(int lane, const ClGeom& g, const ClTileId& t, const ClRng& rng, ClLabelSmem& sm, const ClLane& ln,
-                           uint32_t* gparent_rep) {
+                           const ClGlobal& G) {
     uint32_t blk = cl_global_site(g, t, (uint32_t)lane * CL_T) >> 7, w[4];
     cl_philox(blk, rng.c_lo, rng.c_hi, CL_STREAM_FLIP << 1, rng.k0, rng.k1 ^ t.rep, w);
     cl_for_bits(ln.RS, [&](int x) {
         const uint16_t i = (uint16_t)(lane * CL_T + x);
         const uint16_t e = sm.par[i];
         if ((e & CL_IDX) != i) return;
-        const uint32_t root = cl_cluster_site(g, t, e, gparent_rep);
+        const uint32_t root = cl_cluster_site(g, t, e, G);
         if (cl_flip_bit(root, rng.c_lo, rng.c_hi, rng.k0, rng.k1 ^ t.rep, &blk, w)) cl_or32(&sm.flag[i >> 5], 1u << (i & 31u));
     });
 }
@@ -519,7 +541,7 @@ BC_HD void cl_apply_flips(const ClGeom& g, uint8_t* c0, uint8_t* c1, uint32_t re
 // Label phase for the measurements: the smallest site of the cluster of every site of the thread's row
 // (0xFFFFFFFF for a zero spin) into `out` (the row's 64 entries of a row-major label array; clipped tiles: w entries)
 BC_HD void cl_row_labels(int lane, const ClGeom& g, const ClTileId& t, const ClLabelSmem& sm, const ClLane& ln,
-                         uint32_t* gparent_rep, uint32_t* out) {
+                         const ClGlobal& G, uint32_t* out) {
     uint32_t cur = 0xFFFFFFFFu;
     const uint64_t S = ln.P | ln.M;
     const bool vec = (g.L & 3) == 0;  // the row's entries are 16-byte aligned: four labels per store
@@ -528,7 +550,7 @@ BC_HD void cl_row_labels(int lane, const ClGeom& g, const ClTileId& t, const ClL
         BC_UNROLL
         for (int k = 0; k < 4; ++k) {
             const int x = x4 + k;
-            if ((ln.RS >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[lane * CL_T + x], gparent_rep);
+            if ((ln.RS >> x) & 1ull) cur = cl_cluster_site(g, t, sm.par[lane * CL_T + x], G);
             v[k] = ((S >> x) & 1ull) ? cur : 0xFFFFFFFFu;
         }
         if (vec && x4 + 4 <= t.w) {

@@ -134,6 +134,13 @@ struct bc_engine {
     uint16_t* cl_proot = nullptr;           // [tile][256] roots of the perimeter sites
     uint32_t* cl_gparent = nullptr;         // [replica][L*L] global union-find over flagged tile roots (sparse)
     uint32_t* cl_labels = nullptr;          // [replica][L*L] smallest site of every site's cluster (measurements)
+    // cluster move on a slab of a multi-rank decomposition: the other ranks' pieces of the global union-find and the
+    // perimeter roots of the rank below, mapped through CUDA IPC (bc_slab_cluster_export / _connect)
+    uint32_t* cl_peer_gparent[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const uint16_t* cl_peer_proot_below = nullptr;
+    void* cl_ipc_opened[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool cl_connected = false;
+    int* d_cl_barrier = nullptr;            // one int all-reduced over NCCL: a stream-ordered barrier between the phases
     uint32_t* d_bond_thr = nullptr;         // [replica] bond threshold p * 2^32, p = 1 - exp(-2 J / T)
     // cluster member lists (bc_cluster_sort.cuh): sort buffers, the sorted list, per-replica counts, dump-writer arrays
     uint2* cl_sort[2] = {nullptr, nullptr};
@@ -248,6 +255,8 @@ extern "C" void bc_destroy(bc_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->halo_stream) cudaStreamSynchronize(e->halo_stream);
     for (void* p : e->ipc_opened) if (p) cudaIpcCloseMemHandle(p);
+    for (void* p : e->cl_ipc_opened) if (p) cudaIpcCloseMemHandle(p);
+    cudaFree(e->d_cl_barrier);
     cudaFree(e->d_flags); cudaFree(e->d_halo_err); cudaFree(e->d_halo_clock); cudaFree(e->d_halo_done);
     if (e->comm && g_nccl.handle) g_nccl.CommDestroy(e->comm);
     if (e->ev_boundary) cudaEventDestroy(e->ev_boundary);

@@ -6,21 +6,24 @@
 // ---------------------------------------------------------------------------------------------
 static int cluster_alloc(bc_engine* e) {
     if (e->cl_par) return BC_OK;
-    const size_t tiles_1d = (size_t)(e->L + CL_T - 1) / CL_T, n_tiles = tiles_1d * tiles_1d * (size_t)e->n_rep;
+    const size_t tiles_x = (size_t)(e->L + CL_T - 1) / CL_T, tiles_y = (size_t)(e->Ly + CL_T - 1) / CL_T;
+    const size_t n_tiles = tiles_x * tiles_y * (size_t)e->n_rep;
     if (n_tiles > 0x7FFFFFFFull) return fail(e, BC_ERR_UNSUPPORTED, "cluster labelling: too many tiles for one launch");
-    const size_t N = (size_t)e->L * (size_t)e->L;
+    const size_t own_sites = (size_t)e->Ly * (size_t)e->L;
+    BC_CUDA(e, cudaSetDevice(e->device));
     BC_CUDA(e, cudaMalloc(&e->cl_par, n_tiles * CL_SITES * sizeof(uint16_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_hb, n_tiles * CL_T * sizeof(uint64_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_pm, n_tiles * 2 * CL_T * sizeof(uint64_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_vbb, n_tiles * sizeof(uint64_t)));
     BC_CUDA(e, cudaMalloc(&e->cl_proot, n_tiles * 256 * sizeof(uint16_t)));
-    BC_CUDA(e, cudaMalloc(&e->cl_gparent, (size_t)e->n_rep * N * sizeof(uint32_t)));
+    BC_CUDA(e, cudaMalloc(&e->cl_gparent, (size_t)e->n_rep * own_sites * sizeof(uint32_t)));
     return BC_OK;
 }
 
 static int cluster_args(bc_engine* e, const char* who, bool random_bonds, int64_t cstep, ClArgs* A) {
-    if (e->ghost && e->nranks > 1)
-        return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": not available on a slab of a multi-rank decomposition");
+    const bool multi = e->ghost && e->nranks > 1;
+    if (multi && !e->cl_connected)
+        return fail(e, BC_ERR_STATE, std::string(who) + ": a slab of a multi-rank decomposition needs bc_slab_cluster_connect first");
     for (int r = 0; r < e->n_rep; ++r)
         if (random_bonds && !e->params_set[r]) return fail(e, BC_ERR_STATE, std::string(who) + ": bc_set_params not called for every replica");
     BC_CUDA(e, cudaSetDevice(e->device));
@@ -29,23 +32,99 @@ static int cluster_args(bc_engine* e, const char* who, bool random_bonds, int64_
     memset(A, 0, sizeof(*A));
     A->g.L = e->L; A->g.Wc = e->Wc; A->g.rows_arr = e->rows_arr; A->g.row_first = e->row_first;
     A->g.open = e->boundary == BC_OPEN;
-    A->g.tiles_x = A->g.tiles_y = (e->L + CL_T - 1) / CL_T;
+    A->g.Ly = e->Ly; A->g.y_glob0 = e->y_glob0; A->g.multi = multi ? 1 : 0;
+    A->g.tiles_x = (e->L + CL_T - 1) / CL_T; A->g.tiles_y = (e->Ly + CL_T - 1) / CL_T;
     A->c0 = e->d_c[0]; A->c1 = e->d_c[1];
     A->out.par = e->cl_par; A->out.hb = e->cl_hb; A->out.pm = e->cl_pm; A->out.vbb = e->cl_vbb; A->out.proot = e->cl_proot; A->out.gparent = e->cl_gparent;
     A->rng.thr = random_bonds ? e->d_bond_thr : nullptr;  // per replica: p = 1 - exp(-2 J / T) (main.cpp:115)
     A->rng.k0 = (uint32_t)e->seed; A->rng.k1 = (uint32_t)(e->seed >> 32);
     A->rng.c_lo = (uint32_t)((uint64_t)cstep & 0xFFFFFFFFu); A->rng.c_hi = (uint32_t)((uint64_t)cstep >> 32);
     A->n_tiles = (uint32_t)((size_t)A->g.tiles_x * A->g.tiles_y * e->n_rep);
+    A->rep_stride = (size_t)e->Ly * (size_t)e->L;
+    if (multi) {
+        for (int k = 0; k < e->nranks; ++k) A->gbase[k] = k == e->rank ? e->cl_gparent : e->cl_peer_gparent[k];
+        A->sites_per_rank = (uint32_t)((size_t)e->Ly * (size_t)e->L);
+        A->proot_below = e->cl_peer_proot_below;
+        A->y_glob0_below = ((e->rank + 1) % e->nranks) * e->Ly;
+    } else {
+        A->gbase[0] = e->cl_gparent;
+        A->sites_per_rank = 0;
+    }
     return BC_OK;
 }
 
-// labels every tile and merges the clusters across tile borders (two launches)
+// Stream-ordered barrier over the ranks of a slab decomposition: the cluster move's phases read and write other
+// ranks' memory (the union-find pieces, the perimeter roots of the rank below), so a phase may only start when every
+// rank has finished the previous one.  One int all-reduced on the engine stream; no host synchronisation.
+static int cluster_barrier(bc_engine* e) {
+    if (!(e->ghost && e->nranks > 1)) return BC_OK;
+    if (!e->d_cl_barrier) {
+        BC_CUDA(e, cudaMalloc(&e->d_cl_barrier, sizeof(int)));
+        BC_CUDA(e, cudaMemsetAsync(e->d_cl_barrier, 0, sizeof(int), e->stream));
+    }
+    BC_NCCL(e, g_nccl.AllReduce(e->d_cl_barrier, e->d_cl_barrier, 1, ncclInt32, ncclSum, e->comm, e->stream));
+    return BC_OK;
+}
+
+// Peer mapping for the cluster move on slabs: every rank exports 128 bytes (CUDA IPC handles of its piece of the global
+// union-find and of its perimeter roots); the caller all-gathers the blobs and hands every rank all of them.
+struct ClIpcBlob {
+    cudaIpcMemHandle_t gparent, proot;
+};
+static_assert(sizeof(ClIpcBlob) == 128, "two 64-byte CUDA IPC handles");
+
+extern "C" int bc_slab_cluster_export(bc_engine* e, void* blob128) {
+    if (!e || !blob128) return BC_ERR_ARG;
+    if (!e->ghost || e->nranks < 2) return fail(e, BC_ERR_STATE, "bc_slab_cluster_export: needs a slab handle with n_ranks >= 2");
+    if (e->nranks > CL_MAX_RANKS) return fail(e, BC_ERR_UNSUPPORTED, "bc_slab_cluster_export: at most 8 ranks");
+    int rc = cluster_alloc(e);
+    if (rc != BC_OK) return rc;
+    ClIpcBlob b;
+    BC_CUDA(e, cudaIpcGetMemHandle(&b.gparent, e->cl_gparent));
+    BC_CUDA(e, cudaIpcGetMemHandle(&b.proot, e->cl_proot));
+    std::memcpy(blob128, &b, sizeof(b));
+    return BC_OK;
+}
+
+extern "C" int bc_slab_cluster_connect(bc_engine* e, const void* blobs /* n_ranks x 128 bytes, in rank order */) {
+    if (!e || !blobs) return BC_ERR_ARG;
+    if (!e->ghost || e->nranks < 2) return fail(e, BC_ERR_STATE, "bc_slab_cluster_connect: needs a slab handle with n_ranks >= 2");
+    if (e->nranks > CL_MAX_RANKS) return fail(e, BC_ERR_UNSUPPORTED, "bc_slab_cluster_connect: at most 8 ranks");
+    if (e->cl_connected) return BC_OK;
+    BC_CUDA(e, cudaSetDevice(e->device));
+    int rc = cluster_alloc(e);
+    if (rc != BC_OK) return rc;
+    const int below = (e->rank + 1) % e->nranks;
+    for (int k = 0; k < e->nranks; ++k) {
+        if (k == e->rank) continue;
+        ClIpcBlob b;
+        std::memcpy(&b, static_cast<const char*>(blobs) + (size_t)k * sizeof(ClIpcBlob), sizeof(b));
+        void* p = nullptr;
+        BC_CUDA(e, cudaIpcOpenMemHandle(&p, b.gparent, cudaIpcMemLazyEnablePeerAccess));
+        e->cl_peer_gparent[k] = static_cast<uint32_t*>(p);
+        e->cl_ipc_opened[k] = p;
+        if (k == below) {
+            void* q = nullptr;
+            BC_CUDA(e, cudaIpcOpenMemHandle(&q, b.proot, cudaIpcMemLazyEnablePeerAccess));
+            e->cl_peer_proot_below = static_cast<const uint16_t*>(q);
+            e->cl_ipc_opened[8] = q;
+        }
+    }
+    e->cl_connected = true;
+    return BC_OK;
+}
+
+// labels every tile and merges the clusters across tile borders (two launches; between them, and after them, a barrier
+// over the ranks of a slab decomposition: the merge reads the rank below's perimeter roots and links into other ranks'
+// pieces of the union-find, and what follows walks them)
 static int label_clusters(bc_engine* e, const ClArgs& A) {
     cl_label_kernel<<<A.n_tiles, CL_LANES, 0, e->stream>>>(A);
+    int rc = cluster_barrier(e);
+    if (rc != BC_OK) return rc;
     cl_border_kernel<<<A.n_tiles, 128, 0, e->stream>>>(A);
     e->launches += 2;
     BC_CUDA(e, cudaGetLastError());
-    return BC_OK;
+    return cluster_barrier(e);
 }
 
 extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
@@ -58,7 +137,9 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
         cl_flip_kernel<<<A.n_tiles, CL_LANES, 0, e->stream>>>(A);
         ++e->launches;
         BC_CUDA(e, cudaGetLastError());
-        if (e->ghost) { rc = exchange_both(e); if (rc != BC_OK) return rc; }  // one-rank slab: refresh its ghost rows
+        if (e->ghost) { rc = exchange_both(e); if (rc != BC_OK) return rc; }  // refresh the ghost rows
+        rc = cluster_barrier(e);  // the next update re-initialises union-find entries other ranks may still be walking
+        if (rc != BC_OK) return rc;
         ++e->cluster_step;
         ++e->state_version;
     }
@@ -72,6 +153,8 @@ extern "C" int bc_cluster_update(bc_engine* e, int64_t n_updates) {
 // with the cluster move's counters).
 static int cluster_labels(bc_engine* e, const char* who, int kind, int64_t mstep) {
     const size_t N = (size_t)e->L * (size_t)e->L;
+    if (e->ghost && e->nranks > 1)
+        return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": cluster measurements are not available on a slab of a multi-rank decomposition");
     if (N > 0xFFFFFFFFull) return fail(e, BC_ERR_UNSUPPORTED, std::string(who) + ": site labels are 32-bit (L <= 32768)");
     ClArgs A;
     int rc = cluster_args(e, who, kind == 1, ((int64_t)1 << 62) + mstep, &A);

@@ -40,6 +40,8 @@ SYMBOLS = {
     "bc_create_slab": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _P]),
     "bc_slab_ipc_export": (C.c_int, [_P, _P]),
     "bc_slab_ipc_connect": (C.c_int, [_P, _P, _P]),
+    "bc_slab_cluster_export": (C.c_int, [_P, _P]),
+    "bc_slab_cluster_connect": (C.c_int, [_P, _P]),
     "bc_local_rows": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bc_destroy": (None, [_P]),
     "bc_last_error": (C.c_char_p, [_P]),
@@ -212,6 +214,16 @@ class Engine:
         p = C.create_string_buffer(prev_blob, 192) if prev_blob is not None else None
         n = C.create_string_buffer(next_blob, 192) if next_blob is not None else None
         self._check(self._lib.bc_slab_ipc_connect(self._h, p, n))
+
+    def cluster_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self._lib.bc_slab_cluster_export(self._h, buf))
+        return buf.raw
+
+    def cluster_connect(self, blobs):
+        """blobs: the 128-byte cluster_export() of every rank, in rank order (enables cluster_update on the decomposition)."""
+        raw = b"".join(blobs)
+        self._check(self._lib.bc_slab_cluster_connect(self._h, C.create_string_buffer(raw, len(raw))))
 
     def upload_async(self, spins: np.ndarray):
         """All replicas, no wait: `spins` (pinned, C-contiguous int8) must stay untouched until sync()."""

@@ -87,6 +87,11 @@ int bc_local_rows(const bc_engine* e, int* rows, int* first_global_row);
  * process per GPU, never two ranks on one GPU.  Collective: all ranks connect at the same point. */
 int bc_slab_ipc_export(bc_engine* e, void* blob192);
 int bc_slab_ipc_connect(bc_engine* e, const void* prev_blob192, const void* next_blob192);
+/* Cluster move on slabs (n_ranks >= 2, at most 8): every rank exports 128 bytes (CUDA IPC handles of its piece of the
+ * global union-find over cluster roots and of its tiles' perimeter roots), the caller all-gathers them and hands every
+ * rank the n_ranks blobs in rank order.  Collective; afterwards bc_cluster_update works on the decomposition. */
+int bc_slab_cluster_export(bc_engine* e, void* blob128);
+int bc_slab_cluster_connect(bc_engine* e, const void* blobs);
 
 /* ---- parameters -------------------------------------------------------------------- */
 
@@ -162,8 +167,10 @@ int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int64_t n_sweep
  * main.cpp:113-154,158-163): n_updates Swendsen-Wang updates of every replica -- bonds between equal non-zero
  * neighbours with probability 1 - exp(-2J/T) (main.cpp:115; zeros never join, main.cpp:123-130,144), every
  * cluster flipped with probability 1/2.  Same stationary distribution as the reference's Wolff move, all
- * clusters at once instead of one.  Every replica uses its own bond probability (a handle may hold a (T, D) grid);
- * available on plain handles and on one-rank slab handles.  Has its own RNG counter. */
+ * clusters at once instead of one.  Every replica uses its own bond probability (a handle may hold a (T, D) grid).
+ * On a slab of a multi-rank decomposition the move is collective (every rank calls it) and needs
+ * bc_slab_cluster_connect; clusters that cross slab borders are merged through peer memory, the result is identical
+ * to the single-GPU move.  Has its own RNG counter. */
 int bc_cluster_update(bc_engine* e, int64_t n_updates);
 int bc_get_cluster_counter(const bc_engine* e, int64_t* c);
 int bc_set_cluster_counter(bc_engine* e, int64_t c);

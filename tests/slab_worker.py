@@ -95,6 +95,15 @@ def gpu_slab(boundary, p2p=False, L=None, rows=0, fused=1):
     e.set_params(*TC)
     e.init_random()
     obs = e.sweep(n, 2)
+    # the cluster move on the decomposition: union-find pieces and perimeter roots of the other ranks over peer memory
+    mine_b = torch.frombuffer(bytearray(e.cluster_export()), dtype=torch.uint8).cuda()
+    all_b = [torch.empty_like(mine_b) for _ in range(world)]
+    dist.all_gather(all_b, mine_b)
+    e.cluster_connect([bytes(t.cpu().numpy().tobytes()) for t in all_b])
+    dist.barrier()
+    for _ in range(2):
+        e.cluster_update(1)
+        e.sweep(2)
     if p2p:  # a second lattice through upload: exercises the out-of-cadence exchange
         e.upload(e.download(0), 0)
         obs2 = e.sweep(3, 0)
@@ -107,6 +116,9 @@ def gpu_slab(boundary, p2p=False, L=None, rows=0, fused=1):
         s.set_params(*TC)
         s.init_random()
         so = s.sweep(n, 2)
+        for _ in range(2):
+            s.cluster_update(1)
+            s.sweep(2)
         if p2p:
             s.sweep(3, 0)
         whole = s.download(0)

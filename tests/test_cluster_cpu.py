@@ -25,7 +25,7 @@ def emu():
         cxx = "/usr/bin/g++" if os.access("/usr/bin/g++", os.X_OK) else "g++"
         subprocess.run([cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
     lib = C.CDLL(LIB)
-    lib.emu_cluster_update.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64]
+    lib.emu_cluster_update.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int64]
     lib.emu_cluster_labels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32,
                                        C.c_int64, C.c_void_p]
     return lib
@@ -49,7 +49,7 @@ def test_tile_algorithm_matches_oracle(emu, oracle, L, boundary, T, zeros):
         want = s.copy()
         oracle.cluster_update(want, T, 1.0, seed, rep, cstep, boundary)
         got = s.copy()
-        emu.emu_cluster_update(L, boundary, ghost, got.ctypes.data, thr, seed, rep, cstep)
+        emu.emu_cluster_update(L, boundary, ghost, 1, got.ctypes.data, thr, seed, rep, cstep)
         assert np.array_equal(got, want), (L, boundary, ghost)
         for kind in (0, 1):
             lab = np.zeros((L, L), np.uint32)
@@ -58,3 +58,23 @@ def test_tile_algorithm_matches_oracle(emu, oracle, L, boundary, T, zeros):
             ref = oracle.cluster_labels(s, kind, T, 1.0, seed, rep, 7, boundary).astype(np.int64)
             ref[ref < 0] = 0xFFFFFFFF
             assert np.array_equal(lab.astype(np.int64), ref), (L, boundary, ghost, kind)
+
+
+@pytest.mark.parametrize("L,boundary,n_ranks,T", [(128, 0, 2, 0.608), (256, 0, 4, 0.608), (256, 1, 2, 0.608), (512, 0, 8, 0.3),
+                                                  (192, 0, 3, 1.2), (128, 1, 2, 0.3)])
+@pytest.mark.parametrize("zeros", [0.3, 0.0])
+def test_multi_rank_slab_decomposition_matches_oracle(emu, oracle, L, boundary, n_ranks, T, zeros):
+    """The cluster move on a lattice split into row slabs (BASELINE config 4): every rank labels the tiles of its rows
+    (the row below its last one is the bottom ghost row), the global union-find is sharded by rows and the border merge
+    crosses ranks through the rank below's perimeter roots; the result must be the single-lattice oracle's."""
+    rng = np.random.default_rng(77 * L + n_ranks)
+    s = rng.choice(np.array([-1, 0, 1], np.int8), size=(L, L), p=[(1 - zeros) / 2, zeros, (1 - zeros) / 2]).astype(np.int8)
+    if zeros == 0.0:
+        s[:] = -1
+        s[L // 3, :] = 1  # one stripe, so that two clusters span every slab border ... of a torus: one, wrapped
+    seed, rep, cstep = 0x51AB + L, 1, 2
+    want = s.copy()
+    oracle.cluster_update(want, T, 1.0, seed, rep, cstep, boundary)
+    got = s.copy()
+    assert emu.emu_cluster_update(L, boundary, 1, n_ranks, got.ctypes.data, oracle.bond_threshold(T, 1.0), seed, rep, cstep) == 0
+    assert np.array_equal(got, want), (L, boundary, n_ranks)
