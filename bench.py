@@ -321,6 +321,30 @@ def slab_record(bc, torch, dist, rank, world, local_rank, L=SLAB_L, sweeps=SLAB_
             final = e.measure()[0]
             e.sync()
             plan = e.plan()
+            # the cluster move on the same decomposition (after the observables that are compared with the goldens):
+            # union-find pieces and perimeter roots of the other ranks over peer memory, NCCL barriers between phases
+            cluster = None
+            try:
+                if n_ranks > 1:
+                    mine = torch.frombuffer(bytearray(e.cluster_export()), dtype=torch.uint8).cuda()
+                    allb = [torch.empty_like(mine) for _ in range(n_ranks)]
+                    dist.all_gather(allb, mine)
+                    e.cluster_connect([bytes(t.cpu().numpy().tobytes()) for t in allb])
+                    dist.barrier()
+                e.cluster_update(1)
+                e.sync()
+                e.timer_start()
+                e.cluster_update(3)
+                cms = e.timer_stop() / 3
+                after = e.measure()[0]
+                if n_ranks > 1:
+                    t_c = torch.tensor([cms], dtype=torch.float64, device=f"cuda:{local_rank}")
+                    dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+                    cms = t_c.item()
+                cluster = {"ms_per_update": cms, "sites_per_ns": float(L) * L / (cms * 1e6),
+                           "zeros_conserved": int(after["Q"]) == int(final["Q"]), "M_after": int(after["M"])}
+            except Exception as ex:
+                cluster = {"error": str(ex)}
         finally:
             e.close()
         if n_ranks > 1:
@@ -331,7 +355,7 @@ def slab_record(bc, torch, dist, rank, world, local_rank, L=SLAB_L, sweeps=SLAB_
         return {"ms": ms, "updates_per_ns": ups, "updates_per_ns_per_gpu": ups / n_ranks,
                 "hbm_frac_per_gpu": ups / n_ranks * ALGO_BYTES_PER_UPDATE / peak, "gpu_launches_per_rank": int(launches),
                 "plan": plan, "obs_after_2": [int(early[f]) for f in ("M", "Q", "B")],
-                "obs_final": [int(final[f]) for f in ("M", "Q", "B")]}
+                "obs_final": [int(final[f]) for f in ("M", "Q", "B")], "cluster_move": cluster}
 
     # the same lattice on one GPU (rank 0 only; the other ranks wait at the barrier)
     single = None
@@ -359,7 +383,11 @@ def slab_record(bc, torch, dist, rank, world, local_rank, L=SLAB_L, sweeps=SLAB_
             out["equals_oracle_after_2"] = (out["obs_after_2"] == g2) if g2 else None
             gf = gold.get("gpu_n1", {}).get(str(total_sweeps))
             out["equals_committed_golden"] = (out["obs_final"] == gf) if gf else None
-            checks = [out.get("equals_single_gpu"), out["equals_oracle_after_2"], out["equals_committed_golden"]]
+            cm, cs = out.get("cluster_move") or {}, (single or {}).get("cluster_move") or {}
+            if "M_after" in cm and "M_after" in cs:  # four cluster moves later the magnetisation is still the one-GPU run's
+                cm["equals_single_gpu"] = cm["M_after"] == cs["M_after"]
+            checks = [out.get("equals_single_gpu"), out["equals_oracle_after_2"], out["equals_committed_golden"],
+                      cm.get("equals_single_gpu"), cm.get("zeros_conserved")]
             out["ok"] = all(c is not False for c in checks) and any(c for c in checks)
         rec[transport] = out
     if rank == 0 and single and "error" not in single:
