@@ -45,6 +45,19 @@ def test_argument_errors_need_no_gpu(bc):
     assert lib.bc_create(None, 32, 0, 1, 0, 0, 0) == -1
 
 
+def test_new_entry_points_check_their_arguments(bc):
+    """Round-2 entry points reject NULL handles / buffers before touching a device."""
+    lib = bc.load_library()
+    buf = C.create_string_buffer(256)
+    n = C.c_int64()
+    assert lib.bc_gap_histogram(None, 0, 0, 0, buf) == -1
+    assert lib.bc_cluster_lists(None, 0, 0, 0, buf, buf, buf, C.byref(n), C.byref(n)) == -1
+    assert lib.bc_upload_packed(None, 0, buf, 0) == -1 and lib.bc_download_packed(None, 0, buf, 0) == -1
+    assert lib.bc_packed_size(None, 1) == -1
+    assert lib.bc_slab_cluster_export(None, buf) == -1 and lib.bc_slab_cluster_connect(None, buf) == -1
+    assert lib.bc_pack_spins(None, 4, 1, buf) == -1 and lib.bc_unpack_spins(buf, 0, 1, buf) == -1
+
+
 def test_fails_loudly_without_a_gpu(bc):
     """No CPU fallback: on a box without CUDA, bc_create must fail with BC_ERR_CUDA."""
     lib = bc.load_library()

@@ -153,3 +153,45 @@ def test_bc_gap_stats_cli_on_gpu(tmp_path):
     subprocess.run([tool, "run", str(tmp_path / "gapo"), "0.608", "1.966", "1.0", "--L", "64", "--runs", "4", "--samples", "2",
                     "--burn-sweeps", "40", "--boundary", "open", "--seed", "2"], check=True)
     assert len((tmp_path / "gapo" / "64" / "0.txt").read_text().split("\n")[1].split()) == 63
+
+
+def test_cluster_measurements_on_a_one_rank_slab(bc, oracle):
+    """Slab handles that hold the whole lattice (ghost rows in the colour arrays) take the cluster measurements too."""
+    L, seed = 128, 0x51AC
+    e = bc.Engine(L, 0, 2, 0, seed, slab=(1, 0, None))
+    e.set_params(*TC)
+    e.init_random()
+    e.sweep(20)
+    s = e.download()
+    got = e.gap_histogram(1, mstep=3, variant=0)
+    mom = e.cluster_moments(1, mstep=3)
+    for r in range(2):
+        assert np.array_equal(got[r], oracle.gap_histogram(s[r], 1, TC[0], TC[2], seed, r, 3, 0, 0))
+        assert (mom[r]["sum_size_sq"], mom[r]["max_size"], mom[r]["n_clusters"]) == oracle.cluster_moments(s[r], 1, TC[0], TC[2], seed, r, 3, 0)
+    sites, starts, signs = e.cluster_lists(1, 0, 0)
+    lab = oracle.cluster_labels(s[1], 0, TC[0], TC[2], seed, 1, 0, 0).reshape(-1)
+    occ = np.flatnonzero(s[1].reshape(-1) != 0)
+    assert np.array_equal(sites.astype(np.int64), occ[np.argsort(lab[occ], kind="stable")])
+    e.close()
+
+
+def test_cluster_list_cache_follows_the_lattice(bc, oracle):
+    """The labelling and the sort are cached per (lattice state, kind, mstep): a sweep, a cluster move or an upload
+    in between must invalidate them."""
+    L = 64
+    e = bc.Engine(L, 0, 1, 0, 3)
+    e.set_params(*TC)
+    e.init_random()
+    a = e.cluster_lists(0, 0, 0)
+    b = e.cluster_lists(0, 0, 0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    e.sweep(1)
+    c = e.cluster_lists(0, 0, 0)
+    s = e.download(0)
+    assert len(c[0]) == int((s != 0).sum()) and not (len(a[0]) == len(c[0]) and np.array_equal(a[0], c[0]))
+    e.upload(np.ones((1, L, L), np.int8))
+    d = e.cluster_lists(0, 0, 0)
+    assert len(d[2]) == 1 and len(d[0]) == L * L and d[2][0] == 1  # one cluster: the whole all-plus lattice
+    h = e.gap_histogram(0, 0, 0)
+    assert np.array_equal(h[0], oracle.gap_histogram(np.ones((L, L), np.int8), 0, TC[0], TC[2], 3, 0, 0, 0, 0)) and h.sum() == L * L - 1
+    e.close()

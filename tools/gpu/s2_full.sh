@@ -1,0 +1,5 @@
+set -x; mkdir -p gpurun_out
+nvidia-smi -L
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 > gpurun_out/s2_gpu_tests.log; tail -15 gpurun_out/s2_gpu_tests.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/s2_bench_1gpu.json 2> gpurun_out/s2_bench_1gpu.err
+tail -c 600 gpurun_out/s2_bench_1gpu.json; tail -2 gpurun_out/s2_bench_1gpu.err
