@@ -34,6 +34,9 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
+#ifndef BC_SWP_7
+#define BC_SWP_7 0  // 1: the pipelined kernel at 7 CTAs / SM (72 registers)
+#endif
 
 //   HALO  = true : half-sweep of a slab in peer-memory mode, ONE launch for the whole slab: the first CTAs of every
 //                  replica hold the two boundary strips (first and last strip of the slab); they wait for the
@@ -50,12 +53,14 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 // Software pipelining of the Philox draws (update_chunk16_sp) needs ~8 more registers: it pays for the plain
 // periodic pair-table kernel at 6 CTAs/SM (80 registers: 1778 -> 1813 updates/ns) and loses wherever it spills
 // (72 registers) or drops the measuring / open variants to 5 CTAs/SM.
+template <int PAIR>
+struct TieDefer { static constexpr bool value = PAIR > 0; };  // deferred tie repair: the pair-table kernels (!SMALL)
 template <bool MEASURE, bool OPEN, int PAIR>
 struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; };
 template <bool SMALL, bool MEASURE, bool OPEN, int PAIR, bool HALO = false>
 struct FastMinBlocks {
     static constexpr int value =
-        (MEASURE || SMALL || FastSwp<MEASURE, OPEN, PAIR>::value) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+        (MEASURE || SMALL || (FastSwp<MEASURE, OPEN, PAIR>::value && !BC_SWP_7)) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
 };
 
 // HALO launches: CTA order inside a replica.  A replica has C = items / 128 CTAs in item order (strip-major); the
@@ -115,6 +120,87 @@ __device__ __forceinline__ void halo_epilogue(const SweepParams& P) {
     }
 }
 
+// Tie repair (cold, warp-cooperative).  The row loop of the pair-table kernels is branch-free per site: a site whose
+// coarse compare ties (coarse draw == coarse threshold, about 2^-15 per uphill attempt) is REJECTED there and only
+// lowers a running minimum; once per block of B rows (B = 2 in the unrolled loops, else 1) the warp votes on that
+// minimum and, if any lane saw a tie, runs this function.  The warp takes its flagged threads one by one and
+// re-evaluates the 16 B sites of the flagged thread's block, one site per lane, with the scalar form of the rule --
+// exactly the oracle's per-site function (bc_oracle.c: coarse compare, tie -> u31 = (u15 << 16 | f16) < thr31 with
+// f16 from the fine stream) -- on the site's ORIGINAL value (the flagged thread's own-chunk staging slots, which
+// still hold the block's rows; the stored row cannot tell a rejected tie from an accepted move) and the unchanged
+// other colour (global memory, read a microsecond ago: L2 hits), and rewrites the byte if the exact rule accepts.
+// Sites without a tie are left untouched.  Geometry and Philox context are recomputed from the launch parameters,
+// so nothing stays live in the row loop for this path.  r0 = first strip row of the block, slot0 = own-ring slot of
+// that row, own_slots = the CTA's own ring [4][FAST_THREADS] x 16 bytes; tab = coarse table + exact thresholds
+// (shared memory); acc = {sum c, sum c^2, sum c*S, ties} of the calling lane.
+template <int COL, bool MEASURE, bool OPEN, bool HALO>
+__device__ __forceinline__ void fix_tied_block(const SweepParams& P, const unsigned bid_launch, const int64_t t_add,
+                                               const bool tied, const uint32_t r0, const uint32_t B, const uint32_t slot0,
+                                               const uint8_t* own_slots, const uint32_t* tab, uint32_t* acc) {
+    const unsigned flagged = __ballot_sync(0xFFFFFFFFu, tied);
+    __syncwarp();  // the helper lanes' byte stores come after the flagged threads' row stores
+    bool halo_cta;
+    const unsigned bid = HALO ? halo_cta_order(P, bid_launch, &halo_cta) : bid_launch;
+    const uint32_t ipr = (uint32_t)(P.strips * P.cpr), cpr = (uint32_t)P.cpr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t rows = (uint32_t)P.rows_per_strip, Wc = (uint32_t)P.Wc, total = (uint32_t)P.rows_arr * Wc;
+    const uint16_t* tab16 = reinterpret_cast<const uint16_t*>(tab);  // shared memory: coarse thresholds ...
+    const uint32_t* tab31 = tab + TAB16_WORDS;                       // ... and the exact ones behind them
+    int64_t t = P.t + t_add;
+    if (P.t_ptr) t += *P.t_ptr;
+    const uint32_t ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);
+    // the CTA lies inside one replica (pair-table kernels: items per replica % 128 == 0)
+    const unsigned long long gid0 = (unsigned long long)bid * FAST_THREADS;
+    const uint32_t rep = (uint32_t)(gid0 / ipr);
+    const uint32_t rem0 = (uint32_t)(gid0 - (unsigned long long)rep * ipr) + (threadIdx.x & ~31u);
+    const size_t rep_base = (size_t)rep * (size_t)P.rows_arr * (size_t)Wc;
+    const uint8_t* oth_rep = P.other + rep_base;
+    const uint32_t k0 = P.key0, k1 = P.key1 ^ rep;
+    const uint32_t rr = lane >> 4, site = lane & 15u;                // lane -> (row of the block, site of the chunk)
+    if (rr < B) {
+        for (unsigned todo = flagged; todo; todo &= todo - 1u) {
+            const uint32_t src = (uint32_t)__ffs(todo) - 1u;
+            // the flagged thread's work item -> (strip, chunk), as in sweep_fast_body
+            const uint32_t rem = rem0 + src, strip = rem / cpr, j = rem - strip * cpr;
+            const uint32_t y = (uint32_t)P.row_first + ((uint32_t)P.strip_base + strip * (uint32_t)P.strip_stride) * rows + r0 + rr;
+            const uint32_t yg = y + (uint32_t)P.y_rng_off, o = y * Wc;
+            const int par = (int)((yg + COL) & 1u);
+            const uint8_t* oth_col = oth_rep + (size_t)j * 16;
+            const uint32_t c = own_slots[((((slot0 + rr) & 3u) * FAST_THREADS) + (threadIdx.x & ~31u) + src) * 16u + site];
+            const uint32_t up = o == 0 ? (OPEN ? 1u : oth_col[total - Wc + site]) : oth_col[o - Wc + site];
+            const uint32_t dn = o + Wc == total ? (OPEN ? 1u : oth_col[site]) : oth_col[o + Wc + site];
+            uint32_t hor;  // the horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
+            if (par) hor = site < 15u ? oth_col[o + site + 1u]
+                                      : ((OPEN && j + 1 == cpr) ? 1u : oth_rep[o + ((j + 1 == cpr) ? 0u : j + 1) * 16]);
+            else hor = site > 0u ? oth_col[o + site - 1u]
+                                 : ((OPEN && j == 0) ? 1u : oth_rep[o + ((j == 0) ? cpr - 1 : j - 1) * 16 + 15]);
+            const uint32_t S = up + dn + oth_col[o + site] + hor;      // main.cpp:97-103 in code space
+            uint32_t q[4];
+            philox4x32_10(2u * j + (site >> 3), yg, ctr2, ctr3_of(t, STREAM_COARSE, COL), k0, k1, q);
+            const uint32_t s8 = site & 7u;
+            const uint32_t rw = (s8 >> 1) == 0 ? q[0] : ((s8 >> 1) == 1 ? q[1] : ((s8 >> 1) == 2 ? q[2] : q[3]));
+            const uint32_t h = (s8 & 1u) ? (rw >> 16) : (rw & 0xFFFFu);
+            const uint32_t fl = h >> 15;
+            const uint32_t e = 18u * c + 9u * fl + S;                  // table entry
+            if ((h & 0x7FFFu) != tab16[e]) continue;                   // no tie at this site
+            philox4x32_10(2u * j + (site >> 3), yg, ctr2, ctr3_of(t, STREAM_FINE, COL), k0, k1, q);
+            const uint32_t fw = (s8 >> 1) == 0 ? q[0] : ((s8 >> 1) == 1 ? q[1] : ((s8 >> 1) == 2 ? q[2] : q[3]));
+            const uint32_t f16 = (s8 & 1u) ? (fw >> 16) : (fw & 0xFFFFu);
+            ++acc[3];
+            if (exact_accept(h, f16, tab31[e])) {
+                const uint32_t cn = c ^ (((2u * c + fl) % 3u) + 1u);  // proposal, main.cpp:94 in code space
+                (P.own + rep_base + (size_t)j * 16)[o + site] = (uint8_t)cn;
+                if (MEASURE) {
+                    acc[0] += cn - c;
+                    acc[1] += cn * cn - c * c;
+                    if (COL == 1) acc[2] += (cn - c) * S;
+                }
+            }
+        }
+    }
+    __syncwarp();  // the flagged threads read their rows back (halo transfer)
+}
+
 // The kernel body; `bid` is the CTA's index among the CTAs that work on P's lattices (blockIdx.x for an ordinary
 // launch, blockIdx.x minus the group's first CTA for a group launch, see sweep_group_kernel).
 template <int COL, bool SMALL, bool MEASURE, bool OPEN, bool HALO, int PAIR>
@@ -122,15 +208,20 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     bool halo_cta = false;  // HALO: this CTA holds (part of) a boundary strip
     const unsigned bid = HALO ? halo_cta_order(P, bid_launch, &halo_cta) : bid_launch;
     static_assert(!(PAIR && SMALL) && !(HALO && SMALL), "the pair table and the slab halo logic are one replica per CTA");
-    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS];
+    // coarse table(s); the pair-table kernels keep the replica's exact thresholds behind it for the tie repair
+    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS + (PAIR ? TABLE_ENTRIES : 0)];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
     // DEEP: inputs are requested two rows ahead instead of one (the row above is then carried in registers and
     // the ring holds rows y, y+1 and the two rows in flight).  Measured (tools/tune_libs2.sh): +1..3 % for the
     // periodic pair-table kernels at 8..16 rows per thread, -1 % for the pipelined kernel, -2 % with open edges.
     constexpr bool DEEP = BC_DEEP_PREFETCH == 2 || (BC_DEEP_PREFETCH == 1 && PAIR == 1 && !OPEN);
-    __shared__ uint4 s_own[DEEP ? 4 : 2][FAST_THREADS];     // thread-private own chunks (current / next rows)
-    __shared__ uint32_t s_side[DEEP ? 4 : 2][FAST_THREADS];  // thread-private side words
+    // DEFER (the pair-table kernels): ties are repaired out of the per-site path, once per block of two rows, from the
+    // ORIGINAL own chunks of the block -- the own ring then keeps four rows in every variant (see end_block)
+    constexpr bool DEFER = TieDefer<PAIR>::value;
+    constexpr int OM = (DEEP || DEFER) ? 3 : 1;              // own / side ring: slot of strip row r = r & OM
+    __shared__ uint4 s_own[OM + 1][FAST_THREADS];            // thread-private own chunks (current / next rows)
+    __shared__ uint32_t s_side[OM + 1][FAST_THREADS];        // thread-private side words
 
     // Programmatic dependent launch: let the next half-sweep's grid be scheduled as soon as SMs free up; its
     // CTAs run their prologue (table staging, index arithmetic) and then block in griddepcontrol.wait until
@@ -146,6 +237,9 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
     }
+    if (PAIR && threadIdx.x >= FAST_THREADS - TABLE_ENTRIES)
+        s_tab[TAB16_WORDS + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)] =
+            P.tab31[(size_t)rep0 * TABLE_ENTRIES + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)];
 #if BC_PAIR_TMA
     // Pair table by ONE bulk copy (TMA engine, UBLKCP): thread 0 arms an mbarrier with the byte count and issues the
     // copy; it completes in the background while the CTA computes its indices, waits for the previous grid and
@@ -224,15 +318,35 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     constexpr bool SWP = FastSwp<MEASURE, OPEN, PAIR>::value;
     uint32_t qn[4];
     if (SWP) coarse_draw(ctx, yg0, 0u, qn);
+    // One row.  DEFER (the pair-table kernels): branch-free update; a tie (rare) only lowers the running minimum
+    // `tiemin`; once per block of rows (4 rows in the unrolled loops, 1 otherwise) the warp votes on it and repairs
+    // the block out of line (fix_tied_block).  Otherwise (short strips, SMALL): ties are resolved inline, one test
+    // per 8 sites.
+    uint32_t tiemin = TIEMIN_INIT;
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
         if (SWP) {
             *reinterpret_cast<uint4*>(own_col + off) = update_chunk16_sp<COL, MEASURE, (PAIR > 0)>(
-                ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, n_ties);
+                ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, tiemin);
+        } else if (DEFER) {
+            *reinterpret_cast<uint4*>(own_col + off) =
+                update_chunk16_bf<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, tiemin);
         } else {
             *reinterpret_cast<uint4*>(own_col + off) =
                 update_chunk16<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
         }
+    };
+    // r0: first strip row of the block of `nrows` rows just stored; slot0: own-ring slot of row r0
+    auto end_block = [&](const uint32_t r0, const uint32_t nrows, const uint32_t slot0) {
+        if (!DEFER) return;
+        const bool tied = has_tie(tiemin);
+        if (__any_sync(0xFFFFFFFFu, tied)) {
+            uint32_t acc[4] = {a_c, a_c2, a_cS, 0u};
+            fix_tied_block<COL, MEASURE, OPEN, HALO>(P, bid_launch, t_add, tied, r0, nrows, slot0,
+                                                     reinterpret_cast<const uint8_t*>(&s_own[0][0]), s_tab, acc);
+            a_c = acc[0]; a_c2 = acc[1]; a_cS = acc[2]; n_ties += acc[3];
+        }
+        tiemin = TIEMIN_INIT;
     };
 
     // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour
@@ -308,26 +422,28 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
         auto march = [&](const uint32_t r, const int par, const bool last, const int sl) {
             if (!last) {
                 stage_other((sl + 3) & 3, off + 2 * Wc);
-                stage_row_inputs((sl + 1) & 1, off + Wc, 1 - par);
+                stage_row_inputs((sl + 1) & OM, off + Wc, 1 - par);
             }
             cp_async_commit();
             cp_async_wait<1>();  // everything but the group just committed has landed: row r is ready
             const uint4 upv = s_rows[sl & 3][tid], midv = s_rows[(sl + 1) & 3][tid], dnv = s_rows[(sl + 2) & 3][tid];
-            const uint4 ownv = s_own[sl & 1][tid];
-            const uint32_t side = s_side[sl & 1][tid];
+            const uint4 ownv = s_own[sl & OM][tid];
+            const uint32_t side = s_side[sl & OM][tid];
             update_row(yg0 + r, off, par, upv, midv, dnv, side, ownv);
             off += Wc;
         };
 
         if (SMALL || (rows & 3u)) {
-            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u));
+            for (uint32_t r = 0; r < rows; ++r) { march(r, (int)((yg0 + r + COL) & 1u), r + 1 == rows, (int)(r & 3u)); end_block(r, 1u, r & 3u); }
         } else {
             // yg0 is even and rows is a multiple of 4: parities alternate COL, 1-COL statically; static ring slots
             for (uint32_t r = 0; r < rows; r += 4) {
                 march(r, COL, false, 0);
                 march(r + 1, 1 - COL, false, 1);
+                end_block(r, 2u, 0u);
                 march(r + 2, COL, false, 2);
                 march(r + 3, 1 - COL, r + 4 == rows, 3);
+                end_block(r + 2, 2u, 2u);
             }
         }
     } else {
@@ -365,14 +481,16 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
         };
 
         if (SMALL || (rows & 3u)) {
-            for (uint32_t r = 0; r < rows; ++r) march(r, (int)((yg0 + r + COL) & 1u), r + 3 <= rows, (int)(r & 3u));
+            for (uint32_t r = 0; r < rows; ++r) { march(r, (int)((yg0 + r + COL) & 1u), r + 3 <= rows, (int)(r & 3u)); end_block(r, 1u, r & 3u); }
         } else {
             for (uint32_t r = 0; r < rows; r += 4) {
                 const bool more = r + 4 != rows;
                 march(r, COL, true, 0);
                 march(r + 1, 1 - COL, true, 1);
+                end_block(r, 2u, 0u);
                 march(r + 2, COL, more, 2);
                 march(r + 3, 1 - COL, more, 3);
+                end_block(r + 2, 2u, 2u);
             }
         }
     }

@@ -205,17 +205,134 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Branch-free forms for the streaming kernel's pair-table instantiations (sweep_fast_body with deferred tie repair).
+// ---------------------------------------------------------------------------------------------------------
+// Word wi of a chunk (4 sites): neighbour sums, table entry numbers and proposal XORs on packed bytes -- shared by the
+// hot path and the exact (tie) path so that both see the same numbers.
+__device__ __forceinline__ void site_word(const int wi, const int par, const uint32_t (&o)[4], const uint32_t (&u)[4],
+                                          const uint32_t (&m)[4], const uint32_t (&d)[4], const uint32_t side,
+                                          const uint32_t ones_r, const uint32_t ra, const uint32_t rb, uint32_t& S4,
+                                          uint32_t& idx4, uint32_t& xr) {
+    // horizontal neighbour that is not at the same k: k+1 for par = 1, k-1 for par = 0
+    const uint32_t sr = __funnelshift_r(m[wi], wi < 3 ? m[wi + 1] : side, 8);
+    const uint32_t sl = __funnelshift_l(wi > 0 ? m[wi - 1] : side, m[wi], 8);
+    const uint32_t sh = par ? sr : sl;
+    S4 = u[wi] + d[wi] + m[wi] + sh;  // bytes 0..8, no carries (main.cpp:97-103)
+    const uint32_t c4 = o[wi];
+    // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
+    const uint32_t fO = and_xor(prmt(ra, rb, 0xFDB9u), 0x03030303u, ones_r);  // one LOP3
+    // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
+    // u16 byte offset is applied by the IDP.4A that extracts each byte
+    idx4 = imad(c4, 18u, imad(fO, 9u, S4));
+    // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
+    const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
+    // (q1 + [q1 >= 4]) & 3: the shift drags the low bits of the next byte into bits 6..7, the byte sums stay
+    // below 256 (no carry) and the mask drops them.  Shift + add fuse into one LEA.HI: two ALU-pipe
+    // instructions, none on the FMA-heavy pipe that Philox saturates.
+    xr = (q1 + (q1 >> 2)) & 0x03030303u;
+}
+
+// Branch-free form of update_half8 (streaming pair-table kernels, deferred tie repair):
+// sites whose coarse compare ties are REJECTED here and only lower `tiemin`; the caller tests tiemin once per row
+// (has_tie) and repairs the row with exact_fix_row16.
+template <int COL, bool MEASURE, int HALF, bool PAIR>
+__device__ __forceinline__ void update_half8_bf(const RowCtx& C, const int par, const uint32_t (&o)[4],
+                                             const uint32_t (&u)[4], const uint32_t (&m)[4], const uint32_t (&d)[4],
+                                             const uint32_t side, const uint32_t ones_r, const uint32_t (&q)[4],
+                                             uint32_t (&nw)[4], uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
+                                             uint32_t& a_S, uint32_t& tiemin) {
+    const char* tabm = C.tabm;
+    constexpr int half = HALF;
+    // q = the coarse randoms of this half: one Philox call per 8 sites, 16 bits per site (coarse_draw)
+#pragma unroll
+    for (int w2 = 0; w2 < 2; ++w2) {
+        const int wi = 2 * half + w2;
+        const uint32_t ra = q[2 * w2], rb = q[2 * w2 + 1];
+        uint32_t S4, idx4, xr;
+        site_word(wi, par, o, u, m, d, side, ones_r, ra, rb, S4, idx4, xr);
+        uint32_t Z01, Z23;
+        if (PAIR) {
+            // Pair table: ONE lookup per two sites.  Byte offset 4*(b0-9) + 216*(b1-9) by one IDP.4A (the
+            // bias and the shared-space base are its accumulator), LDS.32 returns the packed word T with
+            // ra - T = lanes 0x8000 + u15 - E15 exactly: the flip bits of ra (bits 15, 31) are known to the
+            // table through the entry numbers and cancel, so no guard-bit OR and no PRMT to pack two
+            // thresholds (see pair_table_kernel).
+            const uint32_t a01 = __dp4a(idx4, 0x0000D804u, C.tab2s);
+            const uint32_t a23 = __dp4a(idx4, 0xD8040000u, C.tab2s);
+            uint32_t T01, T23;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(T01) : "r"(a01));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(T23) : "r"(a23));
+            Z01 = ra - T01;
+            Z23 = rb - T23;
+        } else {
+            // per-site table offsets: byte i of idx4, extracted on the FMA pipe (IDP.4A)
+            const uint32_t a0 = __dp4a(idx4, 0x00000002u, 0u);
+            const uint32_t a3 = __dp4a(idx4, 0x02000000u, 0u);
+            const uint32_t a1 = __dp4a(idx4, 0x00000200u, 0u);
+            const uint32_t a2 = __dp4a(idx4, 0x00020000u, 0u);
+            const uint32_t E0 = *reinterpret_cast<const uint16_t*>(tabm + a0);
+            const uint32_t E1 = *reinterpret_cast<const uint16_t*>(tabm + a1);
+            const uint32_t E2 = *reinterpret_cast<const uint16_t*>(tabm + a2);
+            const uint32_t E3 = *reinterpret_cast<const uint16_t*>(tabm + a3);
+            // Packed 2-site compare: both 15-bit draws of a word get a guard bit, Z lane = 0x8000 + u15 - E15
+            // in [0, 0xFFFF] (no cross-lane borrow): bit 15 clear <=> u15 < E15 (accept), lane == 0x8000 <=>
+            // tie.  E15 = thr31 >> 16 (32768 = always accept: lane = u15, never a tie).
+            Z01 = (ra | 0x80008000u) - __byte_perm(E0, E1, 0x5410);
+            Z23 = (rb | 0x80008000u) - __byte_perm(E2, E3, 0x5410);
+        }
+        const uint32_t msk = prmt(Z01, Z23, 0xFDB9u);       // 0xFF where u15 >= E15 (REJECT mask)
+        // tie <=> some lane == 0x8000, the most negative signed 16-bit value: one packed min per word pair
+        tiemin = min_s16x2(tiemin, min_s16x2(Z01, Z23));
+        const uint32_t v = o[wi] ^ (xr & ~msk);
+        if (MEASURE) {
+            a_c = __dp4a(v, ONES, a_c);
+            a_c2 = __dp4a(v, v, a_c2);
+            if (COL == 1) {
+                a_cS = __dp4a(v, S4, a_cS);
+                a_S = __dp4a(S4, ONES, a_S);
+            }
+        }
+        nw[wi] = v;
+    }
+}
+
+// tiemin = packed signed minimum of all compare lanes of a row: a lane == 0x8000 <=> a tie.  High lane: the word, as a
+// signed number, is below 0x80010000; low lane: shifted to the top.
+constexpr uint32_t TIEMIN_INIT = 0x7FFF7FFFu;  // running minimum: the caller initialises it and tests it when it likes
+__device__ __forceinline__ bool has_tie(const uint32_t tiemin) {
+    return (int32_t)tiemin < (int32_t)0x80010000u || (tiemin << 16) == 0x80000000u;
+}
+
+template <int COL, bool MEASURE, bool PAIR = false>
+__device__ __forceinline__ uint4 update_chunk16_bf(const RowCtx& C, const uint32_t y, const int par, const uint4& upv,
+                                                const uint4& midv, const uint4& dnv, const uint32_t side,
+                                                const uint4& ownv, uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS,
+                                                uint32_t& a_S, uint32_t& tiemin) {
+    uint32_t ones_r;  // ONES held in a register the compiler cannot fold back into an immediate
+    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
+    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
+    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
+    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
+    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
+    uint32_t nw[4], q[4];
+    coarse_draw(C, y, 0u, q);
+    update_half8_bf<COL, MEASURE, 0, PAIR>(C, par, o, u, m, d, side, ones_r, q, nw, a_c, a_c2, a_cS, a_S, tiemin);
+    coarse_draw(C, y, 1u, q);
+    update_half8_bf<COL, MEASURE, 1, PAIR>(C, par, o, u, m, d, side, ones_r, q, nw, a_c, a_c2, a_cS, a_S, tiemin);
+    return make_uint4(nw[0], nw[1], nw[2], nw[3]);
+}
+
 // Software-pipelined form for the streaming kernel: on entry qn holds the coarse draws of (row y, half 0); on exit
 // those of (row y_next, half 0).  The draws of the NEXT half are issued in the same basic block as the site
-// arithmetic of the current half (the rare-tie branch ends a block), so the scheduler can interleave the
-// IMAD.WIDE chain of Philox (FMA-heavy pipe) with the LOP3/PRMT work (ALU pipe) of independent data instead of
-// running them back to back.
+// arithmetic of the current half, so the scheduler can interleave the IMAD.WIDE chain of Philox (FMA-heavy pipe)
+// with the LOP3/PRMT work (ALU pipe) of independent data instead of running them back to back.
 template <int COL, bool MEASURE, bool PAIR>
 __device__ __forceinline__ uint4 update_chunk16_sp(const RowCtx& C, const uint32_t y, const uint32_t y_next, const int par,
                                                    const uint4& upv, const uint4& midv, const uint4& dnv,
                                                    const uint32_t side, const uint4& ownv, uint32_t (&qn)[4],
                                                    uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S,
-                                                   uint32_t& n_ties) {
+                                                   uint32_t& tiemin) {
     uint32_t ones_r;
     asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
     const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
@@ -225,9 +342,9 @@ __device__ __forceinline__ uint4 update_chunk16_sp(const RowCtx& C, const uint32
     uint32_t nw[4], q1[4];
     const uint32_t q0[4] = {qn[0], qn[1], qn[2], qn[3]};
     coarse_draw(C, y, 1u, q1);
-    update_half8<COL, MEASURE, 0, PAIR>(C, y, par, o, u, m, d, side, ones_r, q0, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    update_half8_bf<COL, MEASURE, 0, PAIR>(C, par, o, u, m, d, side, ones_r, q0, nw, a_c, a_c2, a_cS, a_S, tiemin);
     coarse_draw(C, y_next, 0u, qn);
-    update_half8<COL, MEASURE, 1, PAIR>(C, y, par, o, u, m, d, side, ones_r, q1, nw, a_c, a_c2, a_cS, a_S, n_ties);
+    update_half8_bf<COL, MEASURE, 1, PAIR>(C, par, o, u, m, d, side, ones_r, q1, nw, a_c, a_c2, a_cS, a_S, tiemin);
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
 }
 

@@ -13,20 +13,27 @@ for f in re.split(r"\n\s+Function : ", txt)[1:]:
     loops = []
     for addr, ins in lines:
         m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s*)?0x([0-9a-f]+)", ins)
-        if m and int(m.group(1), 16) < int(addr, 16) and int(addr, 16) - int(m.group(1), 16) > 0x400:
+        if m and int(m.group(1), 16) < int(addr, 16) and int(addr, 16) - int(m.group(1), 16) > 0x40:
             loops.append((int(m.group(1), 16), int(addr, 16)))
-    # the main loop: the largest backward branch that contains no other one (the out-of-line mbarrier wait of the
-    # pair-table kernels branches back over the whole function and is not a loop)
-    inner = [l for l in loops if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
-    loop_start, loop_end = max(inner, key=lambda l: l[1] - l[0]) if inner else (None, None)
+    # the main loop: the backward branch that encloses the most 16-byte row stores (the rolled loops of the cold tie
+    # path are loops too, and the out-of-line mbarrier wait of the pair-table kernels branches back over everything)
+    def n_stores(l):
+        return sum(1 for a, i in lines if l[0] <= int(a, 16) <= l[1] and "STG.E.128" in i)
+    cand = [l for l in loops if n_stores(l) > 0]
+    cand = [l for l in cand if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in cand)]  # innermost of those
+    loop_start, loop_end = max(cand, key=n_stores) if cand else (None, None)
     if loop_start is None:
         print(name, "no loop found, total", len(lines)); continue
     body = [(int(a, 16), i) for a, i in lines if loop_start <= int(a, 16) <= loop_end]
+    # cold regions: forward branches over a region that holds a loop of its own (the tie repair)
     cold = []
     for a, ins in body:
         m = re.search(r"BRA(?:\.U)?\s+(?:\S+,\s*)?0x([0-9a-f]+)", ins)
-        if m and int(m.group(1), 16) - a > 0x800 and int(m.group(1), 16) <= loop_end:
-            cold.append((a, int(m.group(1), 16)))
+        if m and int(m.group(1), 16) > a and int(m.group(1), 16) <= loop_end:
+            t = int(m.group(1), 16)
+            if any(a < l[0] and l[1] < t for l in loops) or t - a > 0x800:
+                cold.append((a, t))
+    cold = [c for c in cold if not any(o != c and o[0] <= c[0] and c[1] <= o[1] for o in cold)]
     body = [(a, i) for a, i in body if not any(c0 < a < c1 for c0, c1 in cold)]
     print(" cold regions skipped:", [(hex(a), hex(b)) for a, b in cold])
     ops = collections.Counter(); full = collections.Counter()
