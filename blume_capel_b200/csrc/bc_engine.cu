@@ -174,7 +174,6 @@ struct bc_engine {
     int opt_rows = 0;  // rows per thread, 0 = auto
     int sm_count = 148;
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
-    int opt_swp_min_rows = 32;  // ... with software-pipelined Philox draws from this many rows on (0 = never)
     int opt_force_generic = 0;
     std::string err;
 };
@@ -189,7 +188,7 @@ struct bc_engine {
     } while (0)
 
 typedef void (*fast_fn)(const SweepParams);
-static void pair_kernels(fast_fn (&out)[20]);
+static void pair_kernels(fast_fn (&out)[16]);
 
 static Geom geom_of(const bc_engine* e) {
     Geom g;
@@ -348,8 +347,8 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_bond_thr, (size_t)n_replicas * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if (L % 32 == 0 && L >= 128 &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
-    if (e->d_tab2) {  // 7 CTAs x 26 KB per SM need the large shared-memory carve-out
-        fast_fn pf[20];
+    if (e->d_tab2) {  // 7 CTAs x 30 KB per SM need the large shared-memory carve-out
+        fast_fn pf[16];
         pair_kernels(pf);
         for (fast_fn f : pf) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }

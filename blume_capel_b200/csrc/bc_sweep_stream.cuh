@@ -34,9 +34,6 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 #ifndef BC_FAST_MIN_BLOCKS
 #define BC_FAST_MIN_BLOCKS 6
 #endif
-#ifndef BC_SWP_7
-#define BC_SWP_7 0  // 1: the pipelined kernel at 7 CTAs / SM (72 registers)
-#endif
 
 //   HALO  = true : half-sweep of a slab in peer-memory mode, ONE launch for the whole slab: the first CTAs of every
 //                  replica hold the two boundary strips (first and last strip of the slab); they wait for the
@@ -49,18 +46,16 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 //   PAIR >= 1    : (needs !SMALL) the CTA also stages its replica's 54 x 54 pair table (11.4 KB) and looks the
 //                  thresholds of two sites up with one IDP.4A + one LDS.32; pays when a CTA marches over enough
 //                  rows to amortise the staging (host: LaunchPlan::pair).
-//   PAIR == 2    : additionally the software-pipelined Philox draws (plain periodic kernel only; long strips).
-// Software pipelining of the Philox draws (update_chunk16_sp) needs ~8 more registers: it pays for the plain
-// periodic pair-table kernel at 6 CTAs/SM (80 registers: 1778 -> 1813 updates/ns) and loses wherever it spills
-// (72 registers) or drops the measuring / open variants to 5 CTAs/SM.
-template <int PAIR>
-struct TieDefer { static constexpr bool value = PAIR > 0; };  // deferred tie repair: the pair-table kernels (!SMALL)
-template <bool MEASURE, bool OPEN, int PAIR>
-struct FastSwp { static constexpr bool value = PAIR == 2 && !MEASURE && !OPEN; };
+// (Round 1 and the first half of round 2 also had PAIR == 2, software-pipelined Philox draws at 80 registers / 6 CTAs per
+// SM; with the branch-free row loop below the plain pair-table kernel at 72 registers / 7 CTAs per SM is faster at
+// every strip height -- 1917 against 1840 updates/ns on the bench batch -- and the variant was removed.)
+// DEFER: tie repair out of the per-site path (fix_tied_block) in every kernel whose CTA lies inside one replica.
+template <bool SMALL>
+struct TieDefer { static constexpr bool value = !SMALL; };
 template <bool SMALL, bool MEASURE, bool OPEN, int PAIR, bool HALO = false>
 struct FastMinBlocks {
     static constexpr int value =
-        (MEASURE || SMALL || (FastSwp<MEASURE, OPEN, PAIR>::value && !BC_SWP_7)) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
+        (MEASURE || SMALL) ? BC_FAST_MIN_BLOCKS : BC_FAST_MIN_BLOCKS + 1;
 };
 
 // HALO launches: CTA order inside a replica.  A replica has C = items / 128 CTAs in item order (strip-major); the
@@ -125,7 +120,7 @@ __device__ __forceinline__ void halo_epilogue(const SweepParams& P) {
 // lowers a running minimum; once per block of B rows (B = 2 in the unrolled loops, else 1) the warp votes on that
 // minimum and, if any lane saw a tie, runs this function.  The warp takes its flagged threads one by one and
 // re-evaluates the 16 B sites of the flagged thread's block, one site per lane, with the scalar form of the rule --
-// exactly the oracle's per-site function (bc_oracle.c: coarse compare, tie -> u31 = (u15 << 16 | f16) < thr31 with
+// exactly the per-site function of the spec (coarse compare, tie -> u31 = (u15 << 16 | f16) < thr31 with
 // f16 from the fine stream) -- on the site's ORIGINAL value (the flagged thread's own-chunk staging slots, which
 // still hold the block's rows; the stored row cannot tell a rejected tie from an accepted move) and the unchanged
 // other colour (global memory, read a microsecond ago: L2 hits), and rewrites the byte if the exact rule accepts.
@@ -209,7 +204,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     const unsigned bid = HALO ? halo_cta_order(P, bid_launch, &halo_cta) : bid_launch;
     static_assert(!(PAIR && SMALL) && !(HALO && SMALL), "the pair table and the slab halo logic are one replica per CTA");
     // coarse table(s); the pair-table kernels keep the replica's exact thresholds behind it for the tie repair
-    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS + (PAIR ? TABLE_ENTRIES : 0)];
+    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS + (SMALL ? 0 : TABLE_ENTRIES)];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
     // DEEP: inputs are requested two rows ahead instead of one (the row above is then carried in registers and
@@ -218,7 +213,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     constexpr bool DEEP = BC_DEEP_PREFETCH == 2 || (BC_DEEP_PREFETCH == 1 && PAIR == 1 && !OPEN);
     // DEFER (the pair-table kernels): ties are repaired out of the per-site path, once per block of two rows, from the
     // ORIGINAL own chunks of the block -- the own ring then keeps four rows in every variant (see end_block)
-    constexpr bool DEFER = TieDefer<PAIR>::value;
+    constexpr bool DEFER = TieDefer<SMALL>::value;
     constexpr int OM = (DEEP || DEFER) ? 3 : 1;              // own / side ring: slot of strip row r = r & OM
     __shared__ uint4 s_own[OM + 1][FAST_THREADS];            // thread-private own chunks (current / next rows)
     __shared__ uint32_t s_side[OM + 1][FAST_THREADS];        // thread-private side words
@@ -237,7 +232,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
     }
-    if (PAIR && threadIdx.x >= FAST_THREADS - TABLE_ENTRIES)
+    if (!SMALL && threadIdx.x >= FAST_THREADS - TABLE_ENTRIES)
         s_tab[TAB16_WORDS + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)] =
             P.tab31[(size_t)rep0 * TABLE_ENTRIES + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)];
 #if BC_PAIR_TMA
@@ -315,9 +310,6 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     ctx.j = j; ctx.ctr2 = ctr2; ctx.ctr3 = ctr3; ctx.k0 = k0; ctx.k1 = k1; ctx.t = t; ctx.tabm = tabm;
     ctx.t31_rep = P.tab31 + (size_t)rep * TABLE_ENTRIES;
     ctx.tab2s = PAIR ? (uint32_t)__cvta_generic_to_shared(s_tab2) - TAB2_BIAS : 0u;
-    constexpr bool SWP = FastSwp<MEASURE, OPEN, PAIR>::value;
-    uint32_t qn[4];
-    if (SWP) coarse_draw(ctx, yg0, 0u, qn);
     // One row.  DEFER (the pair-table kernels): branch-free update; a tie (rare) only lowers the running minimum
     // `tiemin`; once per block of rows (4 rows in the unrolled loops, 1 otherwise) the warp votes on it and repairs
     // the block out of line (fix_tied_block).  Otherwise (short strips, SMALL): ties are resolved inline, one test
@@ -325,10 +317,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     uint32_t tiemin = TIEMIN_INIT;
     auto update_row = [&](const uint32_t y, const uint32_t off, const int par, const uint4& upv, const uint4& midv,
                           const uint4& dnv, const uint32_t side, const uint4& ownv) {
-        if (SWP) {
-            *reinterpret_cast<uint4*>(own_col + off) = update_chunk16_sp<COL, MEASURE, (PAIR > 0)>(
-                ctx, y, y + 1, par, upv, midv, dnv, side, ownv, qn, a_c, a_c2, a_cS, a_S, tiemin);
-        } else if (DEFER) {
+        if (DEFER) {
             *reinterpret_cast<uint4*>(own_col + off) =
                 update_chunk16_bf<COL, MEASURE, (PAIR > 0)>(ctx, y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, tiemin);
         } else {

@@ -323,29 +323,4 @@ __device__ __forceinline__ uint4 update_chunk16_bf(const RowCtx& C, const uint32
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
 }
 
-// Software-pipelined form for the streaming kernel: on entry qn holds the coarse draws of (row y, half 0); on exit
-// those of (row y_next, half 0).  The draws of the NEXT half are issued in the same basic block as the site
-// arithmetic of the current half, so the scheduler can interleave the IMAD.WIDE chain of Philox (FMA-heavy pipe)
-// with the LOP3/PRMT work (ALU pipe) of independent data instead of running them back to back.
-template <int COL, bool MEASURE, bool PAIR>
-__device__ __forceinline__ uint4 update_chunk16_sp(const RowCtx& C, const uint32_t y, const uint32_t y_next, const int par,
-                                                   const uint4& upv, const uint4& midv, const uint4& dnv,
-                                                   const uint32_t side, const uint4& ownv, uint32_t (&qn)[4],
-                                                   uint32_t& a_c, uint32_t& a_c2, uint32_t& a_cS, uint32_t& a_S,
-                                                   uint32_t& tiemin) {
-    uint32_t ones_r;
-    asm volatile("mov.u32 %0, 0x01010101;" : "=r"(ones_r));
-    const uint32_t o[4] = {ownv.x, ownv.y, ownv.z, ownv.w};
-    const uint32_t u[4] = {upv.x, upv.y, upv.z, upv.w};
-    const uint32_t m[4] = {midv.x, midv.y, midv.z, midv.w};
-    const uint32_t d[4] = {dnv.x, dnv.y, dnv.z, dnv.w};
-    uint32_t nw[4], q1[4];
-    const uint32_t q0[4] = {qn[0], qn[1], qn[2], qn[3]};
-    coarse_draw(C, y, 1u, q1);
-    update_half8_bf<COL, MEASURE, 0, PAIR>(C, par, o, u, m, d, side, ones_r, q0, nw, a_c, a_c2, a_cS, a_S, tiemin);
-    coarse_draw(C, y_next, 0u, qn);
-    update_half8_bf<COL, MEASURE, 1, PAIR>(C, par, o, u, m, d, side, ones_r, q1, nw, a_c, a_c2, a_cS, a_S, tiemin);
-    return make_uint4(nw[0], nw[1], nw[2], nw[3]);
-}
-
 }  // namespace bc

@@ -35,7 +35,6 @@ extern "C" int bc_set_option(bc_engine* e, const char* name, int64_t value) {
     if (!e || !name) return BC_ERR_ARG;
     const std::string n(name);
     if (n == "rows_per_thread") { e->opt_rows = (int)value; return BC_OK; }
-    if (n == "swp_min_rows") { e->opt_swp_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
     if (n == "pair_min_rows") { e->opt_pair_min_rows = (int)value; if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; } return BC_OK; }
 #ifdef BC_EXPERIMENTAL
     if (n == "wave") { e->opt_wave = (int)value; return BC_OK; }
@@ -78,7 +77,7 @@ extern "C" int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, i
         if (block) *block = r.T * r.reps_per_cta;
         return BC_OK;
     }
-    if (fast) *fast = p.fast ? (p.pair ? 2 + p.pair : 1) : 0;  // 3 = pair table, 4 = + pipelined draws
+    if (fast) *fast = p.fast ? (p.pair ? 3 : 1) : 0;  // 3 = streaming kernel with the pair table
     if (rows_per_thread) *rows_per_thread = p.rows;
     if (grid) *grid = (int)p.grid;
     if (block) *block = p.fast ? FAST_THREADS : 256;

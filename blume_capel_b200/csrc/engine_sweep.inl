@@ -12,19 +12,17 @@ static fast_fn fast_open(bool open) {
 
 template <int COL, bool MEAS>
 static fast_fn fast_halo(bool open, int pair) {
-    if (pair == 2 && !open && !MEAS) return (fast_fn)sweep_fast_kernel<COL, false, false, false, true, 2>;
     if (pair) return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true, 1> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true, 1>;
     return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, true> : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, true>;
 }
 
 template <int COL, bool MEAS>
-static fast_fn fast_pair(bool open, bool swp = false) {
-    if (swp && !open && !MEAS) return (fast_fn)sweep_fast_kernel<COL, false, false, false, false, 2>;
+static fast_fn fast_pair(bool open) {
     return open ? (fast_fn)sweep_fast_kernel<COL, false, MEAS, true, false, 1>
                 : (fast_fn)sweep_fast_kernel<COL, false, MEAS, false, false, 1>;
 }
 
-static void pair_kernels(fast_fn (&out)[20]) {
+static void pair_kernels(fast_fn (&out)[16]) {
     int n = 0;
     for (int open = 0; open < 2; ++open) {
         out[n++] = fast_pair<0, false>(open); out[n++] = fast_pair<0, true>(open);
@@ -32,8 +30,6 @@ static void pair_kernels(fast_fn (&out)[20]) {
         out[n++] = fast_halo<0, false>(open, 1); out[n++] = fast_halo<0, true>(open, 1);
         out[n++] = fast_halo<1, false>(open, 1); out[n++] = fast_halo<1, true>(open, 1);
     }
-    out[n++] = fast_pair<0, false>(false, true); out[n++] = fast_pair<1, false>(false, true);
-    out[n++] = fast_halo<0, false>(false, 2); out[n++] = fast_halo<1, false>(false, 2);
 }
 
 static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = false, int pair = 0) {
@@ -42,8 +38,8 @@ static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = 
         return meas ? fast_halo<1, true>(open, pair) : fast_halo<1, false>(open, pair);
     }
     if (pair && !small) {
-        if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open, pair == 2);
-        return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open, pair == 2);
+        if (col == 0) return meas ? fast_pair<0, true>(open) : fast_pair<0, false>(open);
+        return meas ? fast_pair<1, true>(open) : fast_pair<1, false>(open);
     }
     if (col == 0) {
         if (!small) return meas ? fast_open<0, false, true>(open) : fast_open<0, false, false>(open);
@@ -56,8 +52,7 @@ static fast_fn pick_fast(int col, bool small, bool meas, bool open, bool halo = 
 struct LaunchPlan {
     bool fast = false;
     bool small = false;
-    int pair = 0;  // 1: pair-table kernels (one replica per CTA, enough rows per thread to amortise the 11.4 KB
-                   // table); 2: with software-pipelined draws as well (long strips)
+    int pair = 0;  // 1: pair-table kernels (one replica per CTA, enough rows per thread to amortise the 11.4 KB table)
     int cpr = 0, strips = 0, rows = 0;
     unsigned grid = 0;
 };
@@ -77,10 +72,10 @@ static LaunchPlan make_plan(const bc_engine* e) {
         if (e->opt_rows > 0 && rows_valid(Ly, p.cpr, e->opt_rows)) {
             R = e->opt_rows;
         } else {
-            const long long want = 148LL * 768;  // enough threads to fill the chip (6-7 CTAs of 128 per SM)
-            // 64 rows amortise the per-strip prologue (pair table, first draws) best, but only when the grid still
-            // has four full waves of CTAs (1821 -> 1841 updates/ns on 64 x L=4096)
-            if (rows_valid(Ly, p.cpr, 64) && (long long)e->n_rep * (Ly / 64) * p.cpr >= 4 * want) R = 64;
+            // the tallest strip that still leaves enough threads to fill the chip (7 CTAs of 128 per SM); with the
+            // branch-free row loop 32 rows beat 64 on the bench batch (1938 against 1919 updates/ns: twice the CTAs,
+            // a fuller last wave) and 16 (1904: the per-strip prologue -- pair table, first rows -- weighs more)
+            const long long want = 148LL * 768;
             const int cand[5] = {32, 16, 8, 4, 2};
             for (int i = 0; i < 5 && !R; ++i)
                 if (rows_valid(Ly, p.cpr, cand[i]) && (long long)e->n_rep * (Ly / cand[i]) * p.cpr >= want) R = cand[i];
@@ -90,20 +85,9 @@ static LaunchPlan make_plan(const bc_engine* e) {
         p.strips = Ly / R;
         p.small = (R & 1) != 0 || (((long long)p.strips * p.cpr) % FAST_THREADS) != 0;
         if (!p.small && e->d_tab2 && e->opt_pair_min_rows > 0 && R >= e->opt_pair_min_rows)
-            p.pair = (e->opt_swp_min_rows > 0 && R >= e->opt_swp_min_rows) ? 2 : 1;
+            p.pair = 1;
         const long long items = (long long)e->n_rep * p.strips * p.cpr;
         p.grid = (unsigned)((items + FAST_THREADS - 1) / FAST_THREADS);
-        // Wave fit.  The pipelined kernel (80 registers) runs 6 CTAs per SM, the plain pair-table kernel (72) runs 7.
-        // A grid of a few waves pays for a partly filled last wave: the bench batch is 4096 CTAs = 4.61 waves of
-        // 888 but 3.95 waves of 1036, and the per-GPU share of L = 65536 on 8 GPUs likewise; there the 2 % the
-        // pipelined draws gain per row are less than what the fifth wave costs (profiles/r02_tune_waves.jsonl:
-        // 1847 -> 1865 and 1780 -> 1805 updates/ns).  Strips of two heights that make the grid a whole number of
-        // waves were tried first and cost every instantiation 30 .. 150 bytes of spills.
-        if (p.pair == 2 && e->opt_swp_min_rows == 32 && e->opt_rows == 0) {
-            const long long s6 = 6LL * e->sm_count, s7 = 7LL * e->sm_count;
-            const long long w6 = (p.grid + s6 - 1) / s6, w7 = (p.grid + s7 - 1) / s7;
-            if (w7 < w6 && w6 <= 6) p.pair = 1;
-        }
     } else {
         const long long items = (long long)e->n_rep * L * ((L + 1) / 2);
         p.grid = (unsigned)((items + 255) / 256);

@@ -348,7 +348,7 @@ class Engine:
     def plan(self) -> dict:
         f, r, g, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         self._check(self._lib.bc_describe_plan(self._h, C.byref(f), C.byref(r), C.byref(g), C.byref(b)))
-        return {"fast": bool(f.value), "resident": f.value == 2, "pair": f.value in (3, 4), "pipelined": f.value == 4, "rows_per_thread": r.value, "grid": g.value,
+        return {"fast": bool(f.value), "resident": f.value == 2, "pair": f.value == 3, "rows_per_thread": r.value, "grid": g.value,
                 "block": b.value}
 
     @property

@@ -227,7 +227,6 @@ int bc_timer_stop(bc_engine* e, float* ms);
  *   "rows_per_thread" n   rows each thread of the streaming kernel marches over (0 = auto)
  *   "pair_min_rows" n     streaming kernel: use the 54 x 54 pair table (one threshold lookup per two sites)
  *                         when a thread marches over >= n rows (default 8; 0 = never)
- *   "swp_min_rows" n      ... with software-pipelined Philox draws when it marches over >= n rows (default 32)
  *   "resident" -1|0|1     shared-memory-resident kernel for L <= 448, any L (auto: L <= 128 / off / force)
  *   "use_graph" 0|1, "graph_block" n   CUDA-graph replay of blocks of n unmeasured sweeps
  *   "pdl" 0|1             programmatic dependent launch between half-sweeps
@@ -239,8 +238,7 @@ int bc_timer_stop(bc_engine* e, float* ms);
  *   "force_generic" 0|1   one-thread-per-site kernel for every size (second implementation, for tests) */
 int bc_set_option(bc_engine* e, const char* name, int64_t value);
 /* The launch geometry bc_sweep would use now (any pointer may be NULL).  *fast: 0 = one thread per site,
- * 1 = streaming kernel, 2 = shared-memory-resident kernel, 3 = streaming kernel with the pair table,
- * 4 = pair table + software-pipelined Philox draws (plain periodic sweeps; measuring sweeps use 3). */
+ * 1 = streaming kernel, 2 = shared-memory-resident kernel, 3 = streaming kernel with the pair table. */
 int bc_describe_plan(bc_engine* e, int* fast, int* rows_per_thread, int* grid, int* block);
 /* Ties (coarse 15-bit draw == coarse threshold) resolved by the fine stream so far. */
 int bc_tie_count(bc_engine* e, int64_t* ties);

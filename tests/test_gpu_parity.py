@@ -46,6 +46,7 @@ def run_pair(bc, oracle, L, boundary, n_rep, n_sweeps, seed, params=TC, opts=(),
     for r in range(n_rep):
         ref_obs.append(oracle.sweep(ref[r], tab, seed, r, 0, n_sweeps, measure_every, boundary))
     plan = eng.plan()
+    plan["ties"] = eng.tie_count
     eng.close()
     return got, ref, obs, ref_obs, plan
 
@@ -256,46 +257,32 @@ def test_single_rank_slab_equals_plain_engine(bc, oracle, boundary):
         assert (m[r]["M"], m[r]["Q"], m[r]["B"]) == oracle.observables(ref, boundary)
 
 
-@pytest.mark.parametrize("L,n_rep", [(1024, 2), (2048, 2)])
-def test_headline_plan_matches_oracle(bc, oracle, L, n_rep):
-    """The exact plan the bench line runs (bench.py: 64 x L=4096 -> 64-row strips, pair table + software-pipelined
-    draws, bc_describe_plan == 4; measured sweeps fall back to the pair-table kernel) against the oracle at a size
-    the oracle can afford, measured and unmeasured sweeps mixed, graph replay included (32 > graph_block)."""
+@pytest.mark.parametrize("L,n_rep,rows", [(1024, 2, 32), (2048, 2, 32), (1024, 2, 64), (2048, 1, 64)])
+def test_headline_plan_matches_oracle(bc, oracle, L, n_rep, rows):
+    """The exact plan the bench line runs (bench.py: 64 x L=4096 -> 32-row strips, pair-table kernel with the
+    branch-free row loop and the warp-cooperative tie repair, bc_describe_plan == 3) against the oracle at a size the
+    oracle can afford, measured and unmeasured sweeps mixed, graph replay included (36 > graph_block); 64-row
+    strips (the round-1 plan) as well.  Thousands of ties per run: the tie counts must agree too."""
     n, every = 36, 9
+    oracle.tie_count(reset=True)
     got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, n_rep, n, 0xBE7C4 + L, measure_every=every,
-                                            opts=(("rows_per_thread", 64), ("swp_min_rows", 32), ("resident", 0)))
-    assert plan["pipelined"] and plan["pair"] and plan["rows_per_thread"] == 64, plan
+                                            opts=(("rows_per_thread", rows), ("resident", 0)))
+    assert plan["pair"] and plan["rows_per_thread"] == rows, plan
     assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
     for r in range(n_rep):
         for f in ("sweep", "M", "Q", "B"):
             assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
+    assert plan["ties"] == oracle.tie_count() > 1000, (plan, oracle.tie_count())
 
 
 def test_headline_plan_is_what_bench_runs(bc):
-    """bench.py's workload (64 replicas of L = 4096) resolves by itself to 64-row strips with the pair table; of the two
-    64-row kernels the plan takes the one whose resident CTAs fit the 4096-CTA grid in whole waves (7 CTAs per SM:
-    3.95 waves; the pipelined kernel's 6 per SM: 4.61).  Both are compared with the oracle at 64-row strips above /
-    below; an explicit "swp_min_rows" keeps the pipelined kernel."""
+    """bench.py's workload (64 replicas of L = 4096) resolves by itself to 32-row strips with the pair table
+    (8192 CTAs, 7 per SM: 7.9 waves)."""
     e = bc.Engine(4096, bc.PERIODIC, 64, 0, 1)
     e.set_params(*TC)
     plan = e.plan()
-    e.set_option("swp_min_rows", 16)
-    forced = e.plan()
     e.close()
-    assert plan["pair"] and plan["rows_per_thread"] == 64, plan
-    assert forced["pipelined"] and forced["rows_per_thread"] == 64, forced
-
-
-@pytest.mark.parametrize("L,n_rep", [(1024, 2), (2048, 1)])
-def test_headline_plan_without_pipelined_draws_matches_oracle(bc, oracle, L, n_rep):
-    """64-row strips with the pair table and without pipelined draws (what the auto plan picks for the bench batch)."""
-    got, ref, obs, ref_obs, plan = run_pair(bc, oracle, L, bc.PERIODIC, n_rep, 20, 0xBE7C5 + L, measure_every=7,
-                                            opts=(("rows_per_thread", 64), ("swp_min_rows", 0), ("resident", 0)))
-    assert plan["pair"] and not plan["pipelined"] and plan["rows_per_thread"] == 64, plan
-    assert np.array_equal(got, ref), f"lattice differs, plan={plan}"
-    for r in range(n_rep):
-        for f in ("sweep", "M", "Q", "B"):
-            assert np.array_equal(obs[:, r][f], ref_obs[r][f]), (r, f, plan)
+    assert plan["pair"] and plan["rows_per_thread"] == 32 and plan["grid"] == 8192, plan
 
 
 @pytest.mark.parametrize("L,n_rep,rows,boundary", [(128, 2, 0, 0), (256, 1, 8, 0), (256, 2, 16, 1), (512, 2, 32, 0),
@@ -303,7 +290,7 @@ def test_headline_plan_without_pipelined_draws_matches_oracle(bc, oracle, L, n_r
 def test_fused_halo_slab_kernels_match_oracle(bc, oracle, L, n_rep, rows, boundary):
     """The HALO instantiations of the streaming kernel (a slab's half-sweep as ONE launch: boundary CTAs first,
     in-kernel wait on the neighbours' epoch flags, halo rows stored into the neighbours' ghost rows, epoch signal
-    from the last boundary CTA; plain / pair-table / pipelined variants, graph replay) on ONE GPU: a one-rank slab
+    from the last boundary CTA; plain / pair-table variants, graph replay) on ONE GPU: a one-rank slab
     connected to itself is its own ring neighbour.  Lattices and fused observables against the oracle."""
     n, every, seed = (20, 5, 0x4A10 + L + rows) if L <= 1024 else (4, 2, 0x4A10)
     e = bc.Engine(L, boundary, n_rep, 0, seed, slab=(1, 0, None))

@@ -51,7 +51,7 @@ def test_slab_nccl_two_gpus(boundary):
 def test_slab_peer_store_halo_two_gpus(boundary, L, rows, fused):
     """Halo rows stored directly into the neighbour's ghost rows over NVLink (CUDA IPC peer pointers +
     epoch flags) instead of NCCL send/recv.  fused = 1: the whole half-sweep of a slab is one launch of the HALO
-    kernels (plain, pair-table and pipelined variants depending on the strip height; L = 8192 has two CTAs per
+    kernels (plain and pair-table variants depending on the strip height; L = 8192 has two CTAs per
     boundary strip); fused = 0: boundary strips, push kernel, signal kernel, interior as separate launches."""
     import torch
     if torch.cuda.device_count() < 2:
