@@ -49,9 +49,12 @@ constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
 // (Round 1 and the first half of round 2 also had PAIR == 2, software-pipelined Philox draws at 80 registers / 6 CTAs per
 // SM; with the branch-free row loop below the plain pair-table kernel at 72 registers / 7 CTAs per SM is faster at
 // every strip height -- 1917 against 1840 updates/ns on the bench batch -- and the variant was removed.)
-// DEFER: tie repair out of the per-site path (fix_tied_block) in every kernel whose CTA lies inside one replica.
-template <bool SMALL>
-struct TieDefer { static constexpr bool value = !SMALL; };
+// DEFER: tie repair out of the per-site path (fix_tied_block) in the pair-table kernels.  The per-site-table kernels
+// (strips of fewer than 8 rows: small, launch-bound batches) keep the inline repair: with the out-of-line one they
+// gain 3..5 % where they are throughput-bound (64 x L=4096 at 4 rows per thread: 1427 -> 1500 updates/ns) but a
+// single L=2048 lattice, 3.5 us per launch, loses 11 % to the larger kernel image and prologue.
+template <int PAIR>
+struct TieDefer { static constexpr bool value = PAIR > 0; };
 template <bool SMALL, bool MEASURE, bool OPEN, int PAIR, bool HALO = false>
 struct FastMinBlocks {
     static constexpr int value =
@@ -204,7 +207,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     const unsigned bid = HALO ? halo_cta_order(P, bid_launch, &halo_cta) : bid_launch;
     static_assert(!(PAIR && SMALL) && !(HALO && SMALL), "the pair table and the slab halo logic are one replica per CTA");
     // coarse table(s); the pair-table kernels keep the replica's exact thresholds behind it for the tie repair
-    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS + (SMALL ? 0 : TABLE_ENTRIES)];
+    __shared__ __align__(16) uint32_t s_tab[(SMALL ? FAST_MAX_REPL_PER_CTA : 1) * TAB16_WORDS + (PAIR ? TABLE_ENTRIES : 0)];
     __shared__ __align__(16) uint32_t s_tab2[PAIR ? TAB2_WORDS : 4];
     __shared__ uint4 s_rows[4][FAST_THREADS];    // thread-private ring of other-colour rows
     // DEEP: inputs are requested two rows ahead instead of one (the row above is then carried in registers and
@@ -213,7 +216,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     constexpr bool DEEP = BC_DEEP_PREFETCH == 2 || (BC_DEEP_PREFETCH == 1 && PAIR == 1 && !OPEN);
     // DEFER (the pair-table kernels): ties are repaired out of the per-site path, once per block of two rows, from the
     // ORIGINAL own chunks of the block -- the own ring then keeps four rows in every variant (see end_block)
-    constexpr bool DEFER = TieDefer<SMALL>::value;
+    constexpr bool DEFER = TieDefer<PAIR>::value;
     constexpr int OM = (DEEP || DEFER) ? 3 : 1;              // own / side ring: slot of strip row r = r & OM
     __shared__ uint4 s_own[OM + 1][FAST_THREADS];            // thread-private own chunks (current / next rows)
     __shared__ uint32_t s_side[OM + 1][FAST_THREADS];        // thread-private side words
@@ -232,7 +235,7 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
                        ? reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)r * TAB16_WORDS + i % TAB16_WORDS]
                        : 0u;
     }
-    if (!SMALL && threadIdx.x >= FAST_THREADS - TABLE_ENTRIES)
+    if (PAIR && threadIdx.x >= FAST_THREADS - TABLE_ENTRIES)
         s_tab[TAB16_WORDS + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)] =
             P.tab31[(size_t)rep0 * TABLE_ENTRIES + threadIdx.x - (FAST_THREADS - TABLE_ENTRIES)];
 #if BC_PAIR_TMA

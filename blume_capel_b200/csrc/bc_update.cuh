@@ -222,11 +222,11 @@ __device__ __forceinline__ void site_word(const int wi, const int par, const uin
     const uint32_t c4 = o[wi];
     // flips (bit 15 of each halfword) as byte masks via PRMT sign replication; fO = f + 1
     const uint32_t fO = and_xor(prmt(ra, rb, 0xFDB9u), 0x03030303u, ones_r);  // one LOP3
-    // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S <= 62; the factor 2 of the
-    // u16 byte offset is applied by the IDP.4A that extracts each byte
-    idx4 = imad(c4, 18u, imad(fO, 9u, S4));
     // proposal xor x = c ^ p = ((2c + f) mod 3) + 1   (main.cpp:94 in code space)
     const uint32_t q1 = imad(c4, 2u, fO);            // 2c + f + 1 in 1..6
+    // table entry numbers (biased by +9 through f+1): 18c + 9(f+1) + S = 9 q1 + S <= 62 -- one IMAD on top of q1; the
+    // factor 2 of the u16 byte offset is applied by the IDP.4A that extracts each byte
+    idx4 = imad(q1, 9u, S4);
     // (q1 + [q1 >= 4]) & 3: the shift drags the low bits of the next byte into bits 6..7, the byte sums stay
     // below 256 (no carry) and the mask drops them.  Shift + add fuse into one LEA.HI: two ALU-pipe
     // instructions, none on the FMA-heavy pipe that Philox saturates.
