@@ -275,6 +275,37 @@ def test_headline_plan_matches_oracle(bc, oracle, L, n_rep, rows):
     assert plan["ties"] == oracle.tie_count() > 1000, (plan, oracle.tie_count())
 
 
+@pytest.mark.parametrize("boundary,rows,slab", [(0, 8, False), (1, 8, False), (0, 16, False), (1, 16, False), (0, 8, True), (1, 16, True)])
+def test_tie_repair_at_lattice_edges(bc, oracle, boundary, rows, slab):
+    """The out-of-line tie repair of the pair-table kernels where its addressing is special: a small lattice for many
+    sweeps, so that ties (about 1400 per run) fall on the first and last rows (periodic wrap / open edge rows), on the
+    first and last chunk of a row (neighbour word from the other end of the row / the open edge) and, on a one-rank
+    slab, on the rows that travel to the neighbour's ghost rows after the repair.  Lattices, fused observables and tie
+    counts against the oracle."""
+    L, n_rep, n, every, seed = 256, 2, 400, 50, 0x71E + rows + boundary
+    oracle.tie_count(reset=True)
+    e = bc.Engine(L, boundary, n_rep, 0, seed, slab=(1, 0, None)) if slab else bc.Engine(L, boundary, n_rep, 0, seed)
+    if slab:
+        e.ipc_connect(None, None)
+    e.set_option("rows_per_thread", rows)
+    e.set_option("resident", 0)
+    e.set_params(*TC)
+    e.init_random()
+    plan = e.plan()
+    assert plan["pair"] and plan["rows_per_thread"] == rows, plan
+    obs = e.sweep(n, every)
+    got, ties = e.download(), e.tie_count
+    e.close()
+    tab = oracle.build_table(*TC)
+    for r in range(n_rep):
+        ref = oracle.init_random(L, seed, r)
+        ro = oracle.sweep(ref, tab, seed, r, 0, n, every, boundary)
+        assert np.array_equal(got[r], ref), (boundary, rows, slab, r)
+        for f in ("sweep", "M", "Q", "B"):
+            assert np.array_equal(obs[:, r][f], ro[f]), f
+    assert ties == oracle.tie_count() > 500, (ties, oracle.tie_count())
+
+
 def test_headline_plan_is_what_bench_runs(bc):
     """bench.py's workload (64 replicas of L = 4096) resolves by itself to 32-row strips with the pair table
     (8192 CTAs, 7 per SM: 7.9 waves)."""
