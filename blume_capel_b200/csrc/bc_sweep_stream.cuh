@@ -18,10 +18,12 @@ namespace bc {
 //                  items/replica is a multiple of 128 (one replica, one table per CTA).
 //   SMALL = true : any strip height, up to 4 replicas per CTA (small lattices).
 // Per-site compare: table offsets extracted with IDP.4A (FMA-heavy pipe), LDS.U16
-// from a 27-word conflict-free table, two sites per packed 16-bit subtract, reject masks by PRMT sign
-// replication, ties (coarse draw == coarse threshold) by a packed signed minimum (VIMNMX3.S16x2).  The
-// two half-rate integer pipes (ALU: LOP3/PRMT/SHF, FMA-heavy: IMAD/IDP, quarter-rate IMAD.WIDE) bound
-// this kernel, not HBM; the instruction mix is balanced between them (tools/microbench/pipes.cu).
+// from a 27-word conflict-free table (PAIR: one LDS.32 from the 54 x 54 pair table per two sites), two sites per
+// packed 16-bit subtract, reject masks by PRMT sign replication, ties (coarse draw == coarse threshold) found by a
+// packed signed minimum (VIMNMX3.S16x2) and resolved with the fine stream -- inline, one test per 8 sites, in the
+// per-site-table kernels; out of the per-site path, one warp vote per two rows, in the pair-table kernels
+// (fix_tied_block).  The two half-rate integer pipes (ALU: LOP3/PRMT/SHF, FMA-heavy: IMAD/IDP, quarter-rate
+// IMAD.WIDE) bound this kernel, not HBM; the instruction mix is balanced between them (tools/microbench/pipes.cu).
 // ------------------------------------------------------------------------------------------
 constexpr int FAST_THREADS = 128;
 constexpr int FAST_MAX_REPL_PER_CTA = FAST_THREADS / 32;
@@ -342,8 +344,8 @@ __device__ __forceinline__ void sweep_fast_body(const SweepParams& P, const unsi
     };
 
     // ---- row marching.  Thread-private staging slots in shared memory (a ring of four other-colour
-    // ---- rows, two own chunks, two side words) filled by cp.async one row ahead: the inputs of row
-    // ---- y+1 are in flight while row y is computed, and they cost no registers while in flight.
+    // ---- rows, two or four own chunks and side words) filled by cp.async one or two rows ahead: the inputs of
+    // ---- the next rows are in flight while row y is computed, and they cost no registers while in flight.
     const uint32_t tid = threadIdx.x;
     auto stage_other = [&](const int slot, uint32_t o) {  // other-colour row at byte offset o (== total: wrap/open)
         if (o == total) {
