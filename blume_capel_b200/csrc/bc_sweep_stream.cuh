@@ -530,7 +530,7 @@ struct GroupParams {
 };
 
 template <int COL, bool MEASURE, bool OPEN, int PAIR>
-__global__ void __launch_bounds__(FAST_THREADS, BC_FAST_MIN_BLOCKS)
+__global__ void __launch_bounds__(FAST_THREADS, FastMinBlocks<false, MEASURE, OPEN, PAIR>::value)
 sweep_group_kernel(const __grid_constant__ GroupParams G) {
     int g = 0;
 #pragma unroll

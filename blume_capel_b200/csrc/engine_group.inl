@@ -108,7 +108,10 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
         target = e0->opt_rows;
     } else {
         const long long want = 148LL * 768;
-        for (int cand = 32; cand >= 2; cand >>= 1) {
+        // open lattices: 8-row strips at most (config 5, L = 128..1024 x 64 replicas: 1431 updates/ns against 1369 with
+        // the 16-row strips the thread count alone would allow -- the open-boundary kernels stage one row ahead only
+        // and carry the edge handling at the register limit; tools/tune_group.py)
+        for (int cand = gp.open ? 8 : 32; cand >= 2; cand >>= 1) {
             long long threads = 0;
             for (int g = 0; g < n_engines; ++g) {
                 const int R = group_best_rows(engines[g], cand);  // > 0: 2 rows are valid (checked above) and cand is 2^k
@@ -141,7 +144,7 @@ extern "C" int64_t bc_sweep_group(bc_engine* const* engines, int n_engines, int6
     // (a member with shorter strips only stages the 11.4 KB table more often; the results do not depend on it)
     gp.pair = have_tab2 && e0->opt_pair_min_rows > 0 && 2 * sites_long >= sites_all;
 
-    if (gp.pair) {  // 6 CTAs x 30 KB per SM need the large shared-memory carve-out (a per-device function attribute)
+    if (gp.pair) {  // 7 CTAs x 31 KB per SM need the large shared-memory carve-out (a per-device function attribute)
         bool& carveout_set = e0->group_carveout_set;
         if (!carveout_set) {
             for (int m = 0; m < 2; ++m)
