@@ -206,10 +206,9 @@ __device__ __forceinline__ uint4 update_chunk16(const RowCtx& C, const uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Branch-free forms for the streaming kernel's pair-table instantiations (sweep_fast_body with deferred tie repair).
+// Branch-free forms for the streaming kernel's pair-table instantiations (sweep_fast_body, tie repair out of line).
 // ---------------------------------------------------------------------------------------------------------
-// Word wi of a chunk (4 sites): neighbour sums, table entry numbers and proposal XORs on packed bytes -- shared by the
-// hot path and the exact (tie) path so that both see the same numbers.
+// Word wi of a chunk (4 sites): neighbour sums, table entry numbers and proposal XORs on packed bytes.
 __device__ __forceinline__ void site_word(const int wi, const int par, const uint32_t (&o)[4], const uint32_t (&u)[4],
                                           const uint32_t (&m)[4], const uint32_t (&d)[4], const uint32_t side,
                                           const uint32_t ones_r, const uint32_t ra, const uint32_t rb, uint32_t& S4,
@@ -233,9 +232,9 @@ __device__ __forceinline__ void site_word(const int wi, const int par, const uin
     xr = (q1 + (q1 >> 2)) & 0x03030303u;
 }
 
-// Branch-free form of update_half8 (streaming pair-table kernels, deferred tie repair):
-// sites whose coarse compare ties are REJECTED here and only lower `tiemin`; the caller tests tiemin once per row
-// (has_tie) and repairs the row with exact_fix_row16.
+// Branch-free form of update_half8 (streaming pair-table kernels): sites whose coarse compare ties are REJECTED here
+// and only lower the running minimum `tiemin`; the caller tests it once per block of rows (has_tie + warp vote) and
+// repairs the block out of line (fix_tied_block in bc_sweep_stream.cuh).
 template <int COL, bool MEASURE, int HALF, bool PAIR>
 __device__ __forceinline__ void update_half8_bf(const RowCtx& C, const int par, const uint32_t (&o)[4],
                                              const uint32_t (&u)[4], const uint32_t (&m)[4], const uint32_t (&d)[4],
@@ -297,7 +296,7 @@ __device__ __forceinline__ void update_half8_bf(const RowCtx& C, const int par, 
     }
 }
 
-// tiemin = packed signed minimum of all compare lanes of a row: a lane == 0x8000 <=> a tie.  High lane: the word, as a
+// tiemin = packed signed minimum of all compare lanes since it was initialised: a lane == 0x8000 <=> a tie.  High lane: the word, as a
 // signed number, is below 0x80010000; low lane: shifted to the top.
 constexpr uint32_t TIEMIN_INIT = 0x7FFF7FFFu;  // running minimum: the caller initialises it and tests it when it likes
 __device__ __forceinline__ bool has_tie(const uint32_t tiemin) {
