@@ -6,6 +6,16 @@
 
 namespace bc {
 
+// Register cap of the resident kernel.  Left to __launch_bounds__(512) alone the kernel takes 112 registers: four CTAs
+// of 128 threads per SM; this kernel is one work item per thread and a barrier per half-sweep, i.e. latency-bound,
+// and lives on resident warps.  96 registers (five CTAs per SM, no spills): L=64 x 4096 replicas 1114 -> 1256
+// updates/ns, measured every sweep 994 -> 1119, L=32 +13 %, L=128 +7 %, one L=64 replica 3.0 -> 3.2; 80 registers
+// (six CTAs, a few spills): 1181; 64 registers (eight CTAs, 60..80 spill instructions): 1116
+// (profiles/r02_tune_resident.jsonl).
+#ifndef BC_RESIDENT_MAXNREG
+#define BC_RESIDENT_MAXNREG 96
+#endif
+
 // ------------------------------------------------------------------------------------------
 // Resident kernel: lattices small enough (L % 32 == 0, L <= 448) to stay in shared memory for a whole
 // launch.  One CTA holds both colour arrays of its replica(s) and runs ALL n_sweeps sweeps of the call
@@ -35,7 +45,7 @@ struct ResidentParams {
 //                neighbours of a row's first / last site are patched in; the observables are summed here over
 //                the real sites only (update_chunk16 would count the pad sites).
 template <bool OPEN, bool ANY = false>
-__global__ void __launch_bounds__(512)
+__global__ void __maxnreg__(BC_RESIDENT_MAXNREG)
 sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int L = P.L, Wc = P.Wc, cpr = P.cpr, T = P.threads_per_rep;
