@@ -170,7 +170,7 @@ struct bc_engine {
     int wave_grid[2] = {0, 0};
     int opt_pdl = 1;  // programmatic dependent launch between consecutive half-sweeps
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
-    bool resident_attr_set[4] = {false, false, false, false};
+    bool resident_attr_set[8] = {false, false, false, false, false, false, false, false};
     int opt_rows = 0;  // rows per thread, 0 = auto
     int sm_count = 148;
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)

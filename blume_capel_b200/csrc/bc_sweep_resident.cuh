@@ -15,6 +15,11 @@ namespace bc {
 #ifndef BC_RESIDENT_MAXNREG
 #define BC_RESIDENT_MAXNREG 96
 #endif
+// The instantiation for calls that measure nothing (CANMEAS = false) fits 80 registers without spills: six CTAs per SM,
+// 1256 -> 1293 at L=64, 1142 -> 1230 at L=128 (72 registers: 1251 / 1165; 64: 1178 / 1112).
+#ifndef BC_RESIDENT_MAXNREG_PLAIN
+#define BC_RESIDENT_MAXNREG_PLAIN 80
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Resident kernel: lattices small enough (L % 32 == 0, L <= 448) to stay in shared memory for a whole
@@ -44,8 +49,10 @@ struct ResidentParams {
 //                chunk is updated as a whole and only its real sites are stored; on a torus the wrap-around
 //                neighbours of a row's first / last site are patched in; the observables are summed here over
 //                the real sites only (update_chunk16 would count the pad sites).
-template <bool OPEN, bool ANY = false>
-__global__ void __maxnreg__(BC_RESIDENT_MAXNREG)
+//   CANMEAS = false: a call that measures nothing (burn-in, unmeasured stretches): the measuring half-sweeps and the
+//                reduction are not compiled in, which frees registers for a sixth CTA per SM.
+template <bool OPEN, bool ANY = false, bool CANMEAS = true>
+__global__ void __maxnreg__(CANMEAS ? BC_RESIDENT_MAXNREG : BC_RESIDENT_MAXNREG_PLAIN)
 sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const int L = P.L, Wc = P.Wc, cpr = P.cpr, T = P.threads_per_rep;
@@ -171,7 +178,7 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     int64_t to_meas = P.measure_every > 0 ? P.measure_every - 1 - (P.t0 % P.measure_every) : -1;
     for (int64_t s = 0; s < P.n_sweeps; ++s) {
         const int64_t t = P.t0 + s;
-        const bool measure = to_meas == 0;
+        const bool measure = CANMEAS && to_meas == 0;
         to_meas = measure ? P.measure_every - 1 : to_meas - 1;
         ctx.t = t;
         ctx.ctr2 = (uint32_t)((uint64_t)t & 0xFFFFFFFFu);

@@ -495,11 +495,14 @@ static ResidentPlan resident_plan(const bc_engine* e) {
 static int launch_resident(bc_engine* e, const ResidentPlan& rp, int64_t t0, int64_t n, int64_t measure_every) {
     const bool open = e->boundary == BC_OPEN;
     const bool any = e->L % 32 != 0;  // padded rows, wrap patches, masked stores
-    auto fn = any ? (open ? sweep_resident_kernel<true, true> : sweep_resident_kernel<false, true>)
-                  : (open ? sweep_resident_kernel<true, false> : sweep_resident_kernel<false, false>);
-    if (!e->resident_attr_set[2 * any + open]) {
+    const bool meas = measure_every > 0;
+    auto fn = meas ? (any ? (open ? sweep_resident_kernel<true, true, true> : sweep_resident_kernel<false, true, true>)
+                          : (open ? sweep_resident_kernel<true, false, true> : sweep_resident_kernel<false, false, true>))
+                   : (any ? (open ? sweep_resident_kernel<true, true, false> : sweep_resident_kernel<false, true, false>)
+                          : (open ? sweep_resident_kernel<true, false, false> : sweep_resident_kernel<false, false, false>));
+    if (!e->resident_attr_set[4 * meas + 2 * any + open]) {
         BC_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        e->resident_attr_set[2 * any + open] = true;
+        e->resident_attr_set[4 * meas + 2 * any + open] = true;
     }
     ResidentParams P;
     P.c0 = e->d_c[0]; P.c1 = e->d_c[1];
