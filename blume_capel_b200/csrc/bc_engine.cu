@@ -96,7 +96,7 @@ struct bc_engine {
     uint8_t* d_c[2] = {nullptr, nullptr};
     uint16_t* d_tab16 = nullptr;
     uint32_t* d_tab31 = nullptr;
-    uint32_t* d_tab2 = nullptr;   // [replica][54*54] pair tables of the streaming kernel (L % 32 == 0, L >= 128)
+    uint32_t* d_tab2 = nullptr;   // [replica][54*54] pair tables of the streaming kernel (L % 32 == 0, L >= 128) and of the resident kernel
     std::vector<uint32_t> h_tab31;
     std::vector<uint8_t> params_set;
     unsigned long long* d_obs = nullptr;
@@ -170,7 +170,7 @@ struct bc_engine {
     int wave_grid[2] = {0, 0};
     int opt_pdl = 1;  // programmatic dependent launch between consecutive half-sweeps
     int opt_resident = -1;  // small-lattice shared-memory-resident kernel: -1 auto, 0 off, 1 force (if it fits)
-    bool resident_attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool resident_attr_set[16] = {};
     int opt_rows = 0;  // rows per thread, 0 = auto
     int sm_count = 148;
     int opt_pair_min_rows = 8;  // pair-table kernels when a thread marches over at least this many rows (0 = never)
@@ -345,7 +345,9 @@ static int create_common(bc_engine** out, int L, int boundary, int n_replicas, i
     if ((st = cudaMalloc(&e->d_tab16, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_tab31, (size_t)n_replicas * TABLE_ENTRIES * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
     if ((st = cudaMalloc(&e->d_bond_thr, (size_t)n_replicas * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc table", st);
-    if (L % 32 == 0 && L >= 128 &&
+    // pair tables: the streaming kernel's sizes, and the resident kernel's when a CTA holds one replica (more than 32
+    // 16-byte chunks per colour: L >= 48)
+    if (((L % 32 == 0 && L >= 128) || (L <= 448 && (long long)L * ((((L + 1) / 2) + 15) / 16) > 32)) &&
         (st = cudaMalloc(&e->d_tab2, (size_t)n_replicas * TAB2_WORDS * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc pair table", st);
     if (e->d_tab2) {  // 7 CTAs x 30 KB per SM need the large shared-memory carve-out
         fast_fn pf[16];

@@ -35,6 +35,7 @@ struct ResidentParams {
     uint8_t* c1;             // colour-1 array
     const uint16_t* tab16;   // [replica][54]
     const uint32_t* tab31;   // [replica][54]
+    const uint32_t* tab2;    // [replica][54*54] pair tables (PAIR instantiations) or nullptr
     unsigned long long* obs; // raw accumulators [slot][replica][OBS_RAW]
     unsigned long long* ties;
     int64_t t0;              // first sweep index
@@ -51,7 +52,10 @@ struct ResidentParams {
 //                the real sites only (update_chunk16 would count the pad sites).
 //   CANMEAS = false: a call that measures nothing (burn-in, unmeasured stretches): the measuring half-sweeps and the
 //                reduction are not compiled in, which frees registers for a sixth CTA per SM.
-template <bool OPEN, bool ANY = false, bool CANMEAS = true>
+//   PAIR = true  : (one replica per CTA, calls of many sweeps) the replica's 54 x 54 pair table (11.4 KB) is staged
+//                once per launch behind the lattice and two thresholds are looked up with one IDP.4A + LDS.32, as in
+//                the streaming kernel.
+template <bool OPEN, bool ANY = false, bool CANMEAS = true, bool PAIR = false>
 __global__ void __maxnreg__(CANMEAS ? BC_RESIDENT_MAXNREG : BC_RESIDENT_MAXNREG_PLAIN)
 sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -65,6 +69,7 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     uint8_t* s_c1 = s_c0 + arr;
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_c1 + arr);
     uint32_t* s_red = reinterpret_cast<uint32_t*>(s_dyn + (size_t)P.reps_per_cta * rep_stride) + lr * 8;
+    uint32_t* s_tab2 = reinterpret_cast<uint32_t*>(s_dyn + (size_t)P.reps_per_cta * (rep_stride + 32));  // PAIR (reps_per_cta == 1)
 
     // ---- load: global -> shared (16-byte vectors), table, zero the reduction scratch
     if (live) {
@@ -77,6 +82,10 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
         for (int i = ltid; i < TAB16_WORDS; i += T)
             s_tab[i] = reinterpret_cast<const uint32_t*>(P.tab16)[(size_t)rep * TAB16_WORDS + i];
         if (ltid < 8) s_red[ltid] = 0u;
+        if (PAIR) {
+            const uint4* g2 = reinterpret_cast<const uint4*>(P.tab2 + (size_t)rep * TAB2_WORDS);
+            for (int i = ltid; i < TAB2_WORDS / 4; i += T) reinterpret_cast<uint4*>(s_tab2)[i] = g2[i];
+        }
     }
     __syncthreads();
 
@@ -84,6 +93,7 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
     ctx.k0 = P.key0; ctx.k1 = P.key1 ^ (uint32_t)rep;
     ctx.tabm = reinterpret_cast<const char*>(s_tab) - 18;
     ctx.t31_rep = P.tab31 + (size_t)(live ? rep : 0) * TABLE_ENTRIES;
+    ctx.tab2s = PAIR ? (uint32_t)__cvta_generic_to_shared(s_tab2) - TAB2_BIAS : 0u;
     const uint4 ones4 = make_uint4(ONES, ONES, ONES, ONES);
     const int items = L * cpr;
     uint32_t n_ties = 0;
@@ -139,10 +149,10 @@ sweep_resident_kernel(const __grid_constant__ ResidentParams P) {
             ctx.j = (uint32_t)j;
             if (!ANY) {
                 *reinterpret_cast<uint4*>(own + rowo + co) =
-                    update_chunk16<COL, MEAS>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
+                    update_chunk16<COL, MEAS, PAIR>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, a_c, a_c2, a_cS, a_S, n_ties);
             } else {
                 uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-                const uint4 nv = update_chunk16<COL, false>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, d0, d1, d2, d3, n_ties);
+                const uint4 nv = update_chunk16<COL, false, PAIR>(ctx, (uint32_t)y, par, upv, midv, dnv, side, ownv, d0, d1, d2, d3, n_ties);
                 // byte masks of the real sites, word by word
                 uint32_t mk[4];
 #pragma unroll

@@ -469,6 +469,7 @@ static int run_plain_sweeps(bc_engine* e, const LaunchPlan& plan, int64_t t0, in
 // ---- resident (shared-memory) path for small lattices -----------------------------------------------
 struct ResidentPlan {
     bool ok = false;
+    bool pair = false;  // pair table staged behind the lattice (one replica per CTA; launch_resident: calls of >= 32 sweeps)
     int T = 0, reps_per_cta = 0;
     size_t smem = 0;
     unsigned grid = 0;
@@ -484,6 +485,7 @@ static ResidentPlan resident_plan(const bc_engine* e) {
     r.reps_per_cta = r.T < 128 ? 128 / r.T : 1;
     r.smem = (size_t)r.reps_per_cta * (2 * (size_t)L * e->Wc + 128) + (size_t)r.reps_per_cta * 32;
     if (r.smem > 227 * 1024) return r;
+    r.pair = e->d_tab2 != nullptr && r.reps_per_cta == 1 && e->opt_pair_min_rows > 0 && r.smem + TAB2_WORDS * 4 <= 227 * 1024;
     // auto: always for the reference's sizes (L <= 128); for larger resident sizes only when there are
     // enough replicas to keep every SM busy with one CTA per replica
     if (e->opt_resident < 0 && L > 128 && e->n_rep < 2 * 148) return r;
@@ -496,23 +498,33 @@ static int launch_resident(bc_engine* e, const ResidentPlan& rp, int64_t t0, int
     const bool open = e->boundary == BC_OPEN;
     const bool any = e->L % 32 != 0;  // padded rows, wrap patches, masked stores
     const bool meas = measure_every > 0;
-    auto fn = meas ? (any ? (open ? sweep_resident_kernel<true, true, true> : sweep_resident_kernel<false, true, true>)
-                          : (open ? sweep_resident_kernel<true, false, true> : sweep_resident_kernel<false, false, true>))
-                   : (any ? (open ? sweep_resident_kernel<true, true, false> : sweep_resident_kernel<false, true, false>)
-                          : (open ? sweep_resident_kernel<true, false, false> : sweep_resident_kernel<false, false, false>));
-    if (!e->resident_attr_set[4 * meas + 2 * any + open]) {
+    const bool pair = rp.pair && n >= 32;  // staging 11.4 KB pays for itself after a few dozen sweeps
+    typedef void (*res_fn)(const ResidentParams);
+    // [pair][meas][any][open]
+    static const res_fn fns[2][2][2][2] = {
+        {{{sweep_resident_kernel<false, false, false, false>, sweep_resident_kernel<true, false, false, false>},
+          {sweep_resident_kernel<false, true, false, false>, sweep_resident_kernel<true, true, false, false>}},
+         {{sweep_resident_kernel<false, false, true, false>, sweep_resident_kernel<true, false, true, false>},
+          {sweep_resident_kernel<false, true, true, false>, sweep_resident_kernel<true, true, true, false>}}},
+        {{{sweep_resident_kernel<false, false, false, true>, sweep_resident_kernel<true, false, false, true>},
+          {sweep_resident_kernel<false, true, false, true>, sweep_resident_kernel<true, true, false, true>}},
+         {{sweep_resident_kernel<false, false, true, true>, sweep_resident_kernel<true, false, true, true>},
+          {sweep_resident_kernel<false, true, true, true>, sweep_resident_kernel<true, true, true, true>}}}};
+    const res_fn fn = fns[pair][meas][any][open];
+    const int fi = 8 * pair + 4 * meas + 2 * any + open;
+    if (!e->resident_attr_set[fi]) {
         BC_CUDA(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        e->resident_attr_set[4 * meas + 2 * any + open] = true;
+        e->resident_attr_set[fi] = true;
     }
     ResidentParams P;
     P.c0 = e->d_c[0]; P.c1 = e->d_c[1];
-    P.tab16 = e->d_tab16; P.tab31 = e->d_tab31;
+    P.tab16 = e->d_tab16; P.tab31 = e->d_tab31; P.tab2 = e->d_tab2;
     P.obs = e->d_obs; P.ties = e->d_ties;
     P.t0 = t0; P.n_sweeps = n; P.measure_every = measure_every;
     P.L = e->L; P.Wc = e->Wc; P.cpr = e->Wc / 16; P.n_replicas = e->n_rep;
     P.threads_per_rep = rp.T; P.reps_per_cta = rp.reps_per_cta;
     P.key0 = (uint32_t)e->seed; P.key1 = (uint32_t)(e->seed >> 32);
-    fn<<<rp.grid, rp.T * rp.reps_per_cta, rp.smem, e->stream>>>(P);
+    fn<<<rp.grid, rp.T * rp.reps_per_cta, rp.smem + (pair ? TAB2_WORDS * 4 : 0), e->stream>>>(P);
     ++e->launches;
     BC_CUDA(e, cudaGetLastError());
     return BC_OK;
